@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE -- runs the UNMODIFIED reference (/root/reference) as the
+ground truth that pins the oracle.  Only usable in the authoring container
+(the GPU box has no /root/reference); used by oracle/make_golden.py to write
+tests/golden/*.npz and by tests marked `needs_reference`.
+
+Nothing here is imported by the product package.
+
+Recipe follows SURVEY.md section 8(c): chdir into the reference (its SMPL class
+loads data/J_regressor_lsp.npz by relative path, body_models_scale.py:284),
+register empty stub modules for the GUI / rendering imports the fitting path
+never calls, and build the SMPL module through its `data_struct=` hook
+(body_models_scale.py:98,169-180) because the licensed pickle is absent.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get("MVS_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "code", "smplx"))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_imported = {}
+
+
+def import_reference():
+    """Returns a namespace with the reference modules of the hot path."""
+    if _imported:
+        return _imported["ns"]
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    _stub("pyrender")
+    _stub("pyrender.constants", RenderFlags=object)
+    _stub("trimesh")
+    _stub("OpenGL")
+    _stub("OpenGL.GLUT", __all__=[])
+    _stub("torchgeometry")
+    _stub("configargparse")
+    code = os.path.join(REF_ROOT, "code")
+    if code not in sys.path:
+        sys.path.insert(0, code)
+    with in_reference_dir():
+        import smplx  # noqa: F401  (reference code/smplx)
+        from smplx import body_models_scale, lbs
+        import camera
+        import prior
+        from utils import fitting
+        from utils import utils as ref_utils
+        from optimizers import optim_factory, lbfgs_ls
+    ns = types.SimpleNamespace(
+        smplx=sys.modules["smplx"], body_models_scale=body_models_scale, lbs=lbs,
+        camera=camera, prior=prior, fitting=fitting, utils=ref_utils,
+        optim_factory=optim_factory, lbfgs_ls=lbfgs_ls)
+    _imported["ns"] = ns
+    return ns
+
+
+@contextlib.contextmanager
+def in_reference_dir():
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        yield
+    finally:
+        os.chdir(cwd)
+
+
+def build_reference_model(model: dict, batch_size: int = 1, dtype=torch.float32,
+                          model_type: str = "smpllsp", create_body_pose: bool = True):
+    """Reference SMPL nn.Module over the synthetic `data_struct`."""
+    ns = import_reference()
+    from smplx.utils import Struct
+    ds = Struct(f=model["f"], v_template=model["v_template"], shapedirs=model["shapedirs"],
+                posedirs=model["posedirs"], J_regressor=model["J_regressor"],
+                kintree_table=model["kintree_table"], weights=model["weights"])
+    maps = ns.utils.smpl_to_annotation(
+        model_type=model_type, pose_format="lsp14" if model_type == "smpllsp" else "coco17")
+    mapper = ns.utils.JointMapper(maps)
+    with in_reference_dir():
+        m = ns.body_models_scale.SMPL(
+            "unused", data_struct=ds, joint_mapper=mapper, model_type=model_type,
+            create_global_orient=True, create_body_pose=create_body_pose, create_betas=True,
+            create_transl=True, create_scale=True, dtype=dtype, batch_size=batch_size)
+    return m
+
+
+def build_reference_cameras(cams: dict, dtype=torch.float32):
+    """list[PerspectiveCamera] exactly as reference init.py:108-131 builds them."""
+    ns = import_reference()
+    out = []
+    for v in range(cams["R"].shape[0]):
+        cam = ns.camera.create_camera(
+            focal_length_x=float(cams["f"][v, 0]), focal_length_y=float(cams["f"][v, 1]),
+            translation=torch.tensor(cams["t"][v], dtype=dtype).unsqueeze(0),
+            rotation=torch.tensor(cams["R"][v], dtype=dtype).unsqueeze(0),
+            center=torch.tensor(cams["c"][v], dtype=dtype).unsqueeze(0), dtype=dtype)
+        cam.rotation.requires_grad = False
+        cam.translation.requires_grad = False
+        out.append(cam)
+    return out
+
+
+def build_reference_gmm(gmm: dict, dtype=torch.float32, tmpdir: str = "/tmp/mvs_gmm"):
+    """MaxMixturePrior loaded from a pickle in the dict format (prior.py:130-133)."""
+    import pickle
+    ns = import_reference()
+    os.makedirs(tmpdir, exist_ok=True)
+    M = gmm["means"].shape[0]
+    with open(os.path.join(tmpdir, "gmm_%02d.pkl" % M), "wb") as f:
+        pickle.dump({k: np.asarray(v) for k, v in gmm.items()}, f)
+    return ns.prior.create_prior("gmm", prior_folder=tmpdir, num_gaussians=M, dtype=dtype)
+
+
+def set_model_params(ref_model, params: dict, frame: int):
+    with torch.no_grad():
+        for k in ("betas", "global_orient", "body_pose", "transl", "scale"):
+            if hasattr(ref_model, k):
+                getattr(ref_model, k).copy_(
+                    torch.as_tensor(params[k][frame:frame + 1], dtype=getattr(ref_model, k).dtype))
+                getattr(ref_model, k).grad = None
+
+
+def reference_closure_eval(ref_model, ref_cams, frames: dict, frame: int, weights: dict,
+                           body_pose_prior, dtype=torch.float32, params: dict | None = None,
+                           use_joints_conf=True, rho=100.0, fix_shape=False):
+    """One fitting_func() of the reference for frame `frame` (fitting.py:162-203),
+    B = 1 as the reference requires.  Returns dict(loss, grads{...}, joints, proj, vertices)."""
+    ns = import_reference()
+    p = params if params is not None else frames["init"]
+    set_model_params(ref_model, p, frame)
+    V = frames["gt_uv"].shape[0]
+    gt = torch.tensor(frames["gt_uv"][:, frame:frame + 1], dtype=dtype)          # [V,1,17,2]
+    conf = [torch.tensor(frames["conf"][v, frame:frame + 1], dtype=dtype) for v in range(V)]
+    jw = torch.tensor(frames["joint_weights"], dtype=dtype).unsqueeze(0)
+    loss = ns.fitting.create_loss(
+        "smplify", rho=rho, use_joints_conf=use_joints_conf, dtype=dtype,
+        body_pose_prior=body_pose_prior, shape_prior=ns.prior.create_prior("l2"),
+        angle_prior=ns.prior.create_prior("angle", dtype=dtype),
+        interpenetration=False, fix_shape=fix_shape)
+    loss.reset_loss_weights({k: torch.tensor(v, dtype=dtype) for k, v in weights.items()})
+    monitor = ns.fitting.FittingMonitor(maxiters=30, ftol=1e-9, gtol=1e-9)
+    plist = [q for q in ref_model.parameters() if q.requires_grad]
+    opt = torch.optim.SGD(plist, lr=0.0)
+    closure = monitor.create_fitting_closure(
+        opt, ref_model, camera=ref_cams, gt_joints=gt, joints_conf=conf, joint_weights=jw,
+        loss=loss, create_graph=False, use_vposer=False, vposer=None, pose_embedding=None,
+        return_verts=True, return_full_pose=True, use_3d=False)
+    total = closure()
+    out = ref_model(return_verts=True, return_full_pose=True)
+    proj = torch.stack([cam(out.joints) for cam in ref_cams])[:, 0]
+    return dict(
+        loss=float(total),
+        grads={k: getattr(ref_model, k).grad.detach().numpy().copy().reshape(-1)
+               for k in ("betas", "global_orient", "body_pose", "transl", "scale")
+               if getattr(ref_model, k).grad is not None},
+        joints=out.joints.detach().numpy()[0].copy(),
+        proj=proj.detach().numpy().copy(),
+        vertices=out.vertices.detach().numpy()[0].copy(),
+    )

@@ -1,0 +1,158 @@
+/* mvsmpl.h -- C ABI of libmvsmpl.so, the B200-native (sm_100a) replacement of the
+ * multi-view SMPL fitting hot path of boycehbz/MvSMPLfitting.
+ *
+ * Plain C, no torch / C++ types.  Every entry point returns 0 on success and a
+ * negative mvs_status on failure; mvs_last_error() gives the message.  Device
+ * pointers are BORROWED (the caller, normally PyTorch, owns them and keeps them
+ * alive until the stream has run); host pointers are copied before the call
+ * returns.  All work is enqueued on the caller-supplied cudaStream_t (passed as
+ * void*; 0 = legacy default stream) and no entry point synchronises unless its
+ * comment says so.  One context per device; a context is not thread-safe,
+ * distinct contexts are independent.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference repository root).
+ */
+#ifndef MVSMPL_H_
+#define MVSMPL_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_NUM_PARAMS 86      /* betas10 | global_orient3 | body_pose69 | transl3 | scale1 :
+                                  flat order of LBFGS._gather_flat_grad (code/optimizers/lbfgs_ls.py:221-231)
+                                  over SMPL's parameter registration order (code/smplx/body_models_scale.py:213-268) */
+#define MVS_NUM_JOINTS 24
+#define MVS_NUM_BETAS 10
+#define MVS_NUM_POSE_BASIS 207
+#define MVS_VPOSER_LATENT 32
+
+typedef struct mvs_ctx mvs_ctx;
+
+typedef enum {
+    MVS_OK = 0,
+    MVS_ERR_INVALID = -1,      /* bad argument / call order */
+    MVS_ERR_CUDA = -2,         /* CUDA runtime error */
+    MVS_ERR_NO_DEVICE = -3,    /* no usable sm_100 device: there is NO CPU fallback */
+    MVS_ERR_UNSUPPORTED = -4
+} mvs_status;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+int mvs_version(void);
+int mvs_create(int device, mvs_ctx** out);
+void mvs_destroy(mvs_ctx* ctx);
+const char* mvs_last_error(const mvs_ctx* ctx);          /* ctx may be NULL (creation errors) */
+long long mvs_launch_count(const mvs_ctx* ctx);          /* kernels launched by this context so far */
+
+/* ---- model: replaces SMPL.__init__ buffers (code/smplx/body_models_scale.py:270-305),
+ *      VertexJointSelector (code/smplx/vertex_joint_selector.py:38-77) and JointMapper
+ *      (code/utils/utils.py:411-424).  All pointers are HOST pointers. ---------------- */
+typedef struct {
+    int n_verts;                   /* 6890 */
+    int n_faces;                   /* 13776 (0 if faces == NULL) */
+    const float* v_template;       /* [n_verts,3] */
+    const float* shapedirs;        /* [n_verts,3,10] */
+    const float* posedirs;         /* [207, 3*n_verts]  (the reference's registered layout) */
+    const float* J_regressor;      /* [24, n_verts] */
+    const int* parents;            /* [24], parents[0] = -1 */
+    const float* lbs_weights;      /* [n_verts,24] */
+    const int* faces;              /* [n_faces,3] or NULL */
+    int n_keypoints;               /* 17 */
+    int n_reg;                     /* rows of joint_regressor: 14 ('smpllsp') or 0 ('smpl': the 24 posed chain joints) */
+    const float* joint_regressor;  /* [n_reg, n_verts] dense, or NULL when n_reg == 0 */
+    int n_extra;                   /* 5 face vertices appended after the regressed / chain joints */
+    const int* extra_vertex_ids;   /* [n_extra] */
+    const int* joint_map;          /* [n_keypoints] indices into cat(joints, extra vertices) */
+} mvs_model_desc;
+int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* desc);
+
+/* MaxMixturePrior buffers (code/prior.py:142-160): means [M,69], precisions [M,69,69], nll_weights [M] (host) */
+int mvs_set_gmm_prior(mvs_ctx* ctx, int num_gaussians, const float* means, const float* precisions,
+                      const float* nll_weights);
+
+/* PerspectiveCamera list (code/camera.py:41-117, built in code/init.py:108-131): host arrays
+ * R [V,3,3], t [V,3], f [V,2] (focal x,y), c [V,2] */
+int mvs_set_cameras(mvs_ctx* ctx, int num_views, const float* R, const float* t, const float* f, const float* c);
+
+/* frames in flight (the reference is fixed to 1: code/utils/non_linear_solver.py:56); allocates workspace */
+int mvs_set_batch(mvs_ctx* ctx, int num_frames);
+
+/* 2-D detections: gt_uv [V,B,K,2], conf [V,B,K], joint_weights [K]
+ * (code/utils/non_linear_solver.py:77-101).  on_device != 0: device pointers (copied D2D on `stream`),
+ * else host pointers (copied before return). */
+int mvs_set_keypoints(mvs_ctx* ctx, const float* gt_uv, const float* conf, const float* joint_weights,
+                      int on_device, void* stream);
+
+/* ---- loss: SMPLifyLoss weights + flags (code/utils/fitting.py:208-280, reset_loss_weights :270-280) */
+typedef enum { MVS_PRIOR_L2 = 0, MVS_PRIOR_GMM = 1, MVS_PRIOR_NONE = 2 } mvs_body_prior;
+typedef struct {
+    float data_weight;             /* 500 / image height (non_linear_solver.py:148-150) */
+    float body_pose_weight;
+    float shape_weight;
+    float bending_prior_weight;    /* 3.17 * body_pose_weight (non_linear_solver.py:178-179) */
+    float coll_loss_weight;
+    float rho;                     /* GMoF rho (utils.py:427-438) */
+    int body_prior;                /* mvs_body_prior */
+    int use_joints_conf;
+    int use_vposer;                /* body-pose prior terms are the caller's (|z|^2) ; angle guard disabled */
+    int fix_shape;                 /* no shape prior (fitting.py:340) */
+    int interpenetration;          /* SDF term on (needs faces) */
+    int sdf_grid;                  /* 128 in the reference call (fitting.py:367-368) */
+    int sdf_all_faces;             /* 0 = as written (kernel sees num_faces == 1), 1 = intended semantics */
+    unsigned frozen_mask;          /* bit i set -> parameter tensor i (betas, orient, pose, transl, scale) has
+                                      requires_grad=False: its gradient is forced to 0 (init_guess.py:190-212) */
+} mvs_loss_config;
+int mvs_set_loss_config(mvs_ctx* ctx, const mvs_loss_config* cfg);
+
+/* ---- closure: replaces fitting_func() (code/utils/fitting.py:162-203) = SMPL.forward + SMPLifyLoss.forward
+ *      + backward, for all B frames at once.  params_dev [B,86]; outputs (device, any may be NULL):
+ *      loss_dev [B], grad_dev [B,86], joints_dev [B,K,3], proj_dev [V,B,K,2], verts_dev [B,n_verts,3].
+ *      Requesting verts (or interpenetration) selects the dense 6890-vertex path. */
+int mvs_closure(mvs_ctx* ctx, const float* params_dev, float* loss_dev, float* grad_dev, float* joints_dev,
+                float* proj_dev, float* verts_dev, void* stream);
+
+/* ---- optimiser: replaces LBFGS.step + _strong_Wolfe (code/optimizers/lbfgs_ls.py:39-445) driven by
+ *      FittingMonitor.run_fitting (code/utils/fitting.py:71-142), one independent problem per frame,
+ *      entirely on the device. */
+typedef struct {
+    int max_outer;                 /* FittingMonitor.maxiters (30) */
+    int max_iter;                  /* LBFGS max_iter (30) */
+    int max_eval;                  /* LBFGS max_eval (max_iter*5/4 = 37); <=0 -> derived */
+    int history_size;              /* 100 */
+    float lr;                      /* 1.0 */
+    float tolerance_grad;          /* 1e-5 */
+    float tolerance_change;        /* 1e-9 */
+    float ftol;                    /* FittingMonitor ftol */
+    float gtol;                    /* FittingMonitor gtol */
+} mvs_lbfgs_config;
+typedef struct {
+    long long frame_iterations;    /* sum over frames of L-BFGS iterations (lbfgs_ls.py:304-434 loop bodies) */
+    long long frame_evals;         /* sum over frames of closure evaluations */
+    int rounds;                    /* batched closure launches */
+    int frames_nan;                /* frames stopped by the NaN/Inf guard (fitting.py:101-107) */
+} mvs_lbfgs_stats;
+/* params_dev [B,86] in/out; final_loss_dev [B] or NULL (run_fitting's return value per frame).
+ * Synchronises `stream` before returning (stats are read back). */
+int mvs_lbfgs_run(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const mvs_lbfgs_config* cfg,
+                  mvs_lbfgs_stats* stats, void* stream);
+
+/* ---- host-buffer entry point (what a caller without device memory uses): copies keypoints and
+ *      parameters host->device, runs `n_stages` optimisation stages (one mvs_loss_config each, the weight
+ *      schedule of code/utils/non_linear_solver.py:109-203), copies parameters and losses back.
+ *      All pointers are HOST pointers; synchronises. */
+int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, const float* conf_host,
+                 const float* joint_weights_host, int n_stages, const mvs_loss_config* stage_cfgs,
+                 const mvs_lbfgs_config* opt_cfg, float* final_loss_host, mvs_lbfgs_stats* stats, void* stream);
+
+/* ---- SDF grid: replaces the pybind op sdf.csrc.sdf(phi, faces, vertices) (sdf/sdf/csrc/sdf_cuda.cpp:14-28,
+ *      kernel sdf_cuda_kernel.cu:242-335).  phi_dev [B,G,G,G] (written), faces_dev int32 [*,3],
+ *      verts_dev [B,n_verts,3] normalised to [-1,1].  num_faces is what the kernel loops over
+ *      (the reference call passes 1). */
+int mvs_sdf_grid(mvs_ctx* ctx, float* phi_dev, const int* faces_dev, int num_faces, const float* verts_dev,
+                 int batch, int n_verts, int grid_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSMPL_H_ */

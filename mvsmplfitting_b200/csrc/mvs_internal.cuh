@@ -1,0 +1,140 @@
+// Internal types of libmvsmpl.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mvsmpl.h"
+#include "mvs_math.cuh"
+
+namespace mvs {
+
+// ----------------------------------------------------------------------------- tiling constants
+constexpr int kTileF = 64;     // frames per CTA tile of the vertex kernels
+constexpr int kTileV = 32;     // vertices per CTA tile
+constexpr int kTileC = 3 * kTileV;
+constexpr int kGemmKC = 16;    // K chunk of the forward blend-shape contraction
+constexpr int kVertThreads = 256;
+constexpr int kFrameThreads = 128;
+constexpr int kSkinFloats = kJoints * 12;           // 288 = 24 x (3x4)
+constexpr int kPartFloats = kSkinFloats + kFeatPad; // per (strip, frame) partial of the vertex backward
+
+struct Parents { int p[kJoints]; };
+
+struct CamSet {
+    int num_views;
+    CamF cam[kMaxViews];
+};
+
+// Everything a kernel needs to know about the loss (passed by value)
+struct LossParams {
+    float data_weight, body_pose_weight, shape_weight, bending_prior_weight, coll_loss_weight, rho;
+    int body_prior, use_joints_conf, use_vposer, fix_shape, interpenetration, sdf_grid, sdf_all_faces;
+    unsigned frozen_mask;
+    int num_gaussians;
+};
+
+// Model constants resident in HBM.  Layouts chosen for the kernels, not the reference's:
+//   Qk  [3N][224]   row (3n+c) = [posedirs[:,3n+c] (207) | shapedirs[n,c,:] (10) | v_template[n,c] | 0-pad]
+//                   so that v_posed = Phi . Qk^T with Phi = [pose_feature | betas | 1]  (one contraction
+//                   replaces lbs.py:179 + :194-203); K-contiguous = "K-major B operand" for UMMA/TMA.
+//   Jt [24][3], JS [24][3][10]  pre-contracted rest-joint regressor: J = Jt + JS.betas  (lbs.py:183 folded
+//                   through lbs.py:179; computed in fp64 at upload)
+//   ell_j/ell_w [N][KW]  skinning weights in ELL form (KW = max non-zeros per vertex, 4 for SMPL)
+//   Wd  [N][24]     dense skinning weights (vertex backward)
+struct DevModel {
+    int N = 0, F = 0, KW = 0;
+    float* Qk = nullptr;
+    float* Jt = nullptr;
+    float* JS = nullptr;
+    int* parents = nullptr;
+    int* ell_j = nullptr;
+    float* ell_w = nullptr;
+    float* Wd = nullptr;
+    int* faces = nullptr;
+    // keypoints: k-th keypoint = sum_e kp_w[e] * v[kp_vidx[e]]  (+ posed chain joint kp_chain[k] if >= 0) + transl
+    int K = 0, n_kp_entries = 0, nsup = 0;
+    int* kp_ptr = nullptr;    // [K+1]
+    int* kp_vidx = nullptr;   // vertex id
+    int* kp_spos = nullptr;   // position of that vertex in the support list
+    float* kp_w = nullptr;
+    int* kp_chain = nullptr;  // [K]
+    int* sup = nullptr;       // [nsup] sorted unique vertex ids touched by any keypoint
+    int* sup_ptr = nullptr;   // [nsup+1] transposed structure: support vertex -> (keypoint, weight)
+    int* sup_k = nullptr;
+    float* sup_w = nullptr;
+    // GMM prior
+    int M = 0;
+    float* gmm_means = nullptr;     // [M][69]
+    float* gmm_prec = nullptr;      // [M][69][69] symmetrised
+    float* gmm_lognllw = nullptr;   // [M]  log(nll_weights)
+};
+
+// Per-batch workspace (slot-indexed: slot = position in the active-frame list)
+struct Workspace {
+    int B = 0, ldA = 0;               // ldA = B rounded up to kTileF
+    int nstrips_max = 0;
+    int* fidx = nullptr;              // [B] active list: slot -> frame
+    int* na = nullptr;                // [1] number of active slots
+    float* Phi = nullptr;             // [ldA][224]
+    float* At = nullptr;              // [288][ldA]   skinning transforms, frame fastest
+    float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
+    float* vposed = nullptr;          // [B][nvmax][3]
+    float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
+    float* dv = nullptr;              // [B][nvmax][3]
+    float* part = nullptr;            // [nstrips_max][ldA][kPartFloats]
+    float* data_loss = nullptr;       // [B]
+    float* pen_loss = nullptr;        // [B]
+    float* dtransl = nullptr;         // [B][3]
+    float* dgchain = nullptr;         // [B][24][3]
+    float* gt_uv = nullptr;           // [V][B][K][2]
+    float* conf = nullptr;            // [V][B][K]
+    float* joint_w = nullptr;         // [K]
+    float* loss_scratch = nullptr;    // [B] when the caller passes no loss pointer
+    float* grad_scratch = nullptr;    // [B][86]
+    // SDF scratch
+    float* bbox_part = nullptr;       // [B][nbt][6]
+    float* sdf_frame = nullptr;       // [B][16]  centre(3) scale(1) argmin/argmax ids etc.
+    float* sdf_gcoord = nullptr;      // [B][N][3]
+    float* sdf_valpart = nullptr;     // [B][nbt]
+};
+
+}  // namespace mvs
+
+struct mvs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    long long launches = 0;
+    mvs::DevModel m;
+    mvs::CamSet cams{};
+    mvs::LossParams loss{};
+    mvs::Workspace ws;
+    mvs::Parents parents{};
+    bool attr_done = false;
+    bool have_model = false, have_cams = false, have_kp = false, have_loss = false;
+    std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in mvs_destroy
+    void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
+};
+
+namespace mvs {
+int set_error(mvs_ctx* ctx, int code, const char* fmt, ...);
+#define MVS_CUDA_OK(ctx, expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return mvs::set_error(ctx, MVS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    } while (0)
+
+template <class T> int dev_alloc(mvs_ctx* ctx, T** p, size_t count);
+template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t count);
+
+// closure launcher (mvs_closure.cu): evaluates all active slots.  x_dev [B][86].
+int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
+                   float* proj_dev, float* verts_dev, cudaStream_t st);
+int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);   // mvs_sdf.cu
+int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
+                    int n_verts, int G, cudaStream_t st);
+}  // namespace mvs

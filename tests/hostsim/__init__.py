@@ -1,0 +1,106 @@
+"""ctypes driver of tests/hostsim/closure_hostsim.cpp (test infrastructure only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libhostsim.so")
+
+
+class HostLoss(ctypes.Structure):
+    _fields_ = [("data_weight", ctypes.c_double), ("body_pose_weight", ctypes.c_double),
+                ("shape_weight", ctypes.c_double), ("bending_prior_weight", ctypes.c_double),
+                ("rho", ctypes.c_double), ("body_prior", ctypes.c_int), ("use_conf", ctypes.c_int),
+                ("fix_shape", ctypes.c_int), ("M", ctypes.c_int)]
+
+
+def _build():
+    src = os.path.join(_HERE, "closure_hostsim.cpp")
+    hdr = os.path.join(_HERE, "..", "..", "mvsmplfitting_b200", "csrc", "mvs_math.cuh")
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    if (not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
+                               "-o", _SO, src])
+    return ctypes.CDLL(_SO)
+
+
+def keypoint_lists(model, model_type):
+    """(kp_ptr, kp_v, kp_w, kp_chain) for the 17 keypoints, as mvs_set_model builds them"""
+    from mvsmplfitting_b200 import synthetic as S
+    ptr, vv, ww, chain = [0], [], [], []
+    if model_type == "smpllsp":
+        jmap, nfirst = S.JOINT_MAP_LSP14, 14
+    else:
+        jmap, nfirst = S.JOINT_MAP_COCO17_SMPL, 24
+    for src in jmap:
+        c = -1
+        if src < nfirst:
+            if model_type == "smpllsp":
+                nz = np.nonzero(model["lsp_regressor"][src])[0]
+                vv += list(nz)
+                ww += list(model["lsp_regressor"][src][nz])
+            else:
+                c = int(src)
+        else:
+            vv.append(int(S.FACE_VERTEX_IDS[src - nfirst]))
+            ww.append(1.0)
+        chain.append(c)
+        ptr.append(len(vv))
+    return (np.array(ptr, np.int32), np.array(vv, np.int32), np.array(ww, np.float64), np.array(chain, np.int32))
+
+
+class HostSim:
+    def __init__(self, model, cams, model_type="smpllsp"):
+        self.lib = _build()
+        self.lib.hostsim_create.restype = ctypes.c_void_p
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        N = model["v_template"].shape[0]
+        pd = f64(np.reshape(model["posedirs"], [-1, 207]).T)
+        parents = np.asarray(model["kintree_table"][0]).astype(np.int64)
+        parents[0] = -1
+        parents = parents.astype(np.int32)
+        ptr, vv, ww, chain = keypoint_lists(model, model_type)
+        self.K, self.V, self.N = len(chain), cams["R"].shape[0], N
+        arrs = [f64(model["v_template"]), f64(model["shapedirs"]), pd, f64(model["J_regressor"]), parents,
+                f64(model["weights"]), ptr, vv, ww, chain, f64(cams["R"]), f64(cams["t"]), f64(cams["f"]), f64(cams["c"])]
+        self._keep = arrs
+        p = [a.ctypes.data_as(ctypes.c_void_p) for a in arrs]
+        self.h = ctypes.c_void_p(self.lib.hostsim_create(
+            N, p[0], p[1], p[2], p[3], p[4], p[5], self.K, p[6], p[7], p[8], p[9], self.V, p[10], p[11], p[12], p[13]))
+
+    def eval(self, x86, gt_uv, conf, jw, w, body_prior="l2", gmm=None, use_conf=True, fix_shape=False,
+             use_double=False, rho=100.0, want_verts=False):
+        from mvsmplfitting_b200 import synthetic as S
+        lp = HostLoss(w["data_weight"], w["body_pose_weight"], w["shape_weight"], w["bending_prior_weight"], rho,
+                      1 if body_prior == "gmm" else 0, int(use_conf), int(fix_shape), 0)
+        gm = gp = gl = np.zeros(1)
+        if body_prior == "gmm":
+            means, prec, nllw = S.gmm_buffers(gmm)
+            if not use_double:   # the reference holds these buffers in fp32 (prior.py:142-160)
+                means = means.astype(np.float32).astype(np.float64)
+                prec = np.stack([np.linalg.inv(c) for c in gmm["covars"].astype(np.float32)]).astype(np.float32).astype(np.float64)
+                nllw = nllw.astype(np.float32).astype(np.float64)
+            prec = 0.5 * (prec + np.transpose(prec, (0, 2, 1)))
+            gm, gp, gl = np.ascontiguousarray(means), np.ascontiguousarray(prec), np.ascontiguousarray(np.log(nllw))
+            lp.M = means.shape[0]
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, gt, cf, jw_ = f64(x86), f64(gt_uv), f64(conf), f64(jw)
+        loss = np.zeros(1)
+        grad = np.zeros(86)
+        joints = np.zeros((self.K, 3))
+        verts = np.zeros((self.N, 3)) if want_verts else None
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.hostsim_eval(self.h, int(use_double), ctypes.byref(lp), P(gm), P(gp), P(gl), P(x), P(gt), P(cf), P(jw_),
+                              P(loss), P(grad), P(joints), P(verts) if want_verts else None)
+        out = dict(loss=float(loss[0]), grad=grad, joints=joints)
+        if want_verts:
+            out["verts"] = verts
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.hostsim_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- L-BFGS iterations/s of the multi-view SMPL fitting hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle port)
+
+Workload (BASELINE.json configs[3], the config the metric is quoted on): per GPU 256 frames x 8
+calibrated views of the synthetic SMPL-shaped model (6890 verts, 207 pose blend shapes), GMM(6) +
+angle + shape priors, GMoF data term, the four-stage weight schedule of cfg_files/fit_smpl.yaml with
+the SDF interpenetration term (reference semantics "as written") active in stages 2-3.
+One STEP = one complete four-stage fit (4 x FittingMonitor.run_fitting, maxiters 30, L-BFGS max_iter
+30 / strong Wolfe / history 100) of all frames from the same initial guess.
+
+  value  = frame-iterations / s (iteration = one pass of lbfgs_ls.py:304-434 for one frame), device
+           resident: keypoints + initial parameters already in HBM, reset by a device copy.
+  e2e    = the same metric through mvs_fit_host: pinned HOST keypoints + parameters copied in, results
+           copied out, every step.
+Timed with CUDA events, max over ranks; L2 is flushed between steps (256 MiB write).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "lbfgs_frame_iterations_per_s"
+UNIT = "frame-iterations/s"
+
+
+def stage_table():
+    from mvsmplfitting_b200 import synthetic as S
+    sw = S.STAGE_WEIGHTS
+    return [dict(data_weight=500.0 / 1536, body_pose_weight=sw["body_pose_prior_weights"][i],
+                 shape_weight=sw["shape_weights"][i], bending_prior_weight=3.17 * sw["body_pose_prior_weights"][i],
+                 coll_loss_weight=sw["coll_loss_weights"][i]) for i in range(4)]
+
+
+def workload_config(frames, views, sdf):
+    return {"workload": "cfg4: %d frames/GPU x %d views, 4-stage fit_smpl.yaml schedule, GMM(6)+angle+shape priors, "
+                        "GMoF rho=100, SDF interpenetration %s" % (frames, views, "on in stages 2-3 (G=128, as-written "
+                                                                   "semantics: kernel sees triangle 0)" if sdf else "off"),
+            "frames_per_gpu": frames, "views": views, "model": "synthetic SMPL-shaped (6890 verts, 13776 faces)",
+            "params_per_frame": 86, "l2": "flushed between steps (256 MiB write)",
+            "step": "one full 4-stage fit of all frames from the same initial guess"}
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mvsmplfitting_b200 import synthetic as S
+    from mvsmplfitting_b200.context import FittingContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    B, V = args.frames, args.views
+    model = S.make_model(0)
+    gmm = S.make_gmm(7)
+    cams = S.make_cameras(V)
+    fr = S.make_frames(model, cams, B, seed=1000 + rank)
+    ctx = FittingContext(local)
+    ctx.set_model(model)
+    ctx.set_gmm_from_dict(gmm)
+    ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
+    ctx.set_batch(B)
+    stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=bool(args.sdf), sdf_grid=128, **st)
+              for st in stage_table()]
+    opt = ctx.make_lbfgs_config()
+    X0 = S.pack_params(fr["init"])
+    x0_dev = torch.tensor(X0, device=dev)
+    x = x0_dev.clone()
+    gt_dev, conf_dev = torch.tensor(fr["gt_uv"], device=dev), torch.tensor(fr["conf"], device=dev)
+    jw_dev = torch.tensor(fr["joint_weights"], device=dev)
+    ctx.set_keypoints(gt_dev, conf_dev, jw_dev)
+    # pinned host buffers for the end-to-end leg
+    X_pin = torch.from_numpy(X0.copy()).pin_memory()
+    gt_pin, conf_pin = torch.from_numpy(fr["gt_uv"]).pin_memory(), torch.from_numpy(fr["conf"]).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        x.copy_(x0_dev)
+        tot = dict(frame_iterations=0, frame_evals=0, rounds=0, frames_nan=0)
+        per_stage = []
+        for cfg in stages:
+            ctx.set_loss(config=cfg)
+            _, st = ctx.lbfgs_run(x, opt)
+            per_stage.append(st)
+            for k in tot:
+                tot[k] += st[k]
+        return tot, per_stage
+
+    def step_host():
+        X_pin.copy_(torch.from_numpy(X0))
+        return ctx.fit_host(X_pin.numpy(), gt_pin.numpy(), conf_pin.numpy(), fr["joint_weights"], stages, opt)[1]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile_mask=0):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if profile_mask:
+            ctx.profile(profile_mask)
+        l0 = ctx.launch_count()
+        ms, stats = 0.0, []
+        wall0 = time.time()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            stats.append(fn())
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        barrier()
+        wall = time.time() - wall0
+        launches = ctx.launch_count() - l0
+        prof = ctx.profile_read() if profile_mask else {}
+        if profile_mask:
+            ctx.profile(0)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), stats, launches, prof, wall
+
+    # one fully instrumented warm-up step decides which kernel dominates; that kernel alone is then
+    # timed with events INSIDE the timed region (two event records per launch of one kernel)
+    barrier()
+    ctx.profile(0xFFFFFFFF)
+    step_resident()
+    share = ctx.profile_read()
+    ctx.profile(0)
+    dom = max(share, key=lambda k: share[k][0]) if share else "vertex_fwd"
+    names = [ctx.lib.mvs_kernel_name(k).decode() for k in range(12)]
+    dom_mask = 1 << names.index(dom)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, stats_res, launches, prof, wall = timed(lambda: step_resident(), args.steps, max(args.warmup - 1, 0), dom_mask)
+    ms_e2e, stats_e2e, _, _, _ = timed(step_host, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    it = sum(s[0]["frame_iterations"] for s in stats_res)
+    ev = sum(s[0]["frame_evals"] for s in stats_res)
+    rounds = sum(s[0]["rounds"] for s in stats_res)
+    it_e2e = sum(s["frame_iterations"] for s in stats_e2e)
+    cnt = torch.tensor([it, ev, launches, it_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    it_all, ev_all, launches_all, it_e2e_all = [float(v) for v in cnt]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json, sustained-copy figure)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # ---- roofline of the dominant kernel: algorithmic bytes per launch / event time
+        dom_ms, dom_n = prof.get(dom, (0.0, 0))
+        # average active frames per closure launch (compaction shrinks launches towards the tail)
+        evals_rank0 = sum(s[0]["frame_evals"] for s in stats_res)
+        na_avg = evals_rank0 / max(rounds, 1)
+        dense_rounds_frac = None
+        alg = algorithmic_bytes(dom, na_avg, V, dense=bool(args.sdf))
+        ach = (alg * dom_n) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (ach / hbm_peak) if ach else None, "traffic": None,
+                "algorithmic_bytes_per_launch": alg, "launches": dom_n, "avg_launch_us": (dom_ms * 1e3 / dom_n) if dom_n else None,
+                "avg_active_frames_per_launch": na_avg, "peak_source": peak_src,
+                "kernel_time_share_of_step": {k: round(v[0] / max(sum(x_[0] for x_ in share.values()), 1e-9), 4)
+                                              for k, v in share.items()}}
+        cpu = cpu_baseline_sample(V, bool(args.sdf), max_seconds=args.cpu_seconds) if world == 1 or True else None
+        sec = ms_res * 1e-3
+        out = {
+            "metric": METRIC, "value": it_all / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(B, V, bool(args.sdf)), parallelism="frames sharded, dp%d, no data-path collective" % world),
+            "frame_closure_evals_per_s": ev_all / sec, "evals_per_iteration": ev_all / max(it_all, 1),
+            "iterations_per_frame_per_step": it_all / (B * world * args.steps),
+            "rounds_per_step": rounds / args.steps,
+            "e2e": {"value": it_e2e_all / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(fr["gt_uv"].nbytes + fr["conf"].nbytes + fr["joint_weights"].nbytes + X0.nbytes),
+                    "d2h_bytes_per_step": int(X0.nbytes + B * 4), "ms_per_step": ms_e2e / args.steps,
+                    "api": "mvs_fit_host (C ABI, host buffers)"},
+            "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def algorithmic_bytes(kernel: str, na: float, V: int, dense: bool) -> float:
+    """Algorithmic (must-move) bytes of ONE launch of `kernel` with `na` active frames; derivation in
+    DESIGN.md section 5 (per-frame figures from SURVEY.md 8d: constants 19.7 MB shared, 82 680 B / frame of
+    vertices, 344 B parameters, 204 B / view keypoints)."""
+    N = 6890
+    nv = N if dense else 86
+    q_bytes = 3 * nv * 218 * 4                      # posedirs + shapedirs + template rows of the vertex list
+    w_bytes = nv * 4 * 8                            # skinning weights (4 (joint, weight) pairs)
+    if kernel == "vertex_fwd":
+        return q_bytes + w_bytes + na * (218 * 4 + 288 * 4 + 2 * nv * 12)
+    if kernel == "vertex_bwd":
+        nvb = N if dense else 86
+        return 3 * nvb * 218 * 4 + nvb * 24 * 4 + na * (288 * 4 + 2 * nvb * 12 + 512 * 4)
+    if kernel == "sdf_sample":
+        return na * (N * 12 + N * 12)
+    if kernel == "sdf_finalize":
+        return na * (N * 12 + N * 12)
+    if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance"):
+        return na * (344 * 3 + 204 * V + 512 * 4)
+    return na * 344
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def _fit_one_frame_cpu(args):
+    """full 4-stage fit of ONE frame with the oracle (the reference's algorithm on CPU); returns counters"""
+    seed, V, sdf = args
+    import torch
+    torch.set_num_threads(1)
+    from mvsmplfitting_b200 import synthetic as S
+    from oracle import closure_oracle as O
+    from oracle import lbfgs_oracle as L
+    model = S.make_model(0)
+    gmm = S.make_gmm(7)
+    cams = S.make_cameras(V)
+    fr = S.make_frames(model, cams, 1, seed=seed)
+    om = O.OracleModel.from_numpy(model)
+    pri = O.OraclePriors.gmm_from_dict(gmm)
+    ct = O.cams_to_torch(cams, torch.float32)
+    x = torch.tensor(S.pack_params(fr["init"])[0])
+    iters = evals = 0
+    t0 = time.time()
+    for st in stage_table():
+        cfg = O.LossConfig(interpenetration=sdf, sdf_grid=128, **st)
+
+        def fg(xx, cfg=cfg):
+            r = O.closure_eval(om, cfg, pri, ct, xx.numpy(), fr["gt_uv"][:, 0], fr["conf"][:, 0], fr["joint_weights"])
+            return r["loss"], torch.tensor(r["grad"])
+        opt = L.LBFGSOracle(x, fg, max_iter=30)
+        L.run_fitting(opt, 30, 1e-9, 1e-9)
+        x = opt.x
+        iters += opt.iters
+        evals += opt.evals
+    return iters, evals, time.time() - t0
+
+
+def cpu_baseline_sample(V, sdf, max_seconds=30.0):
+    """bounded sample: ONE frame, one host thread, full 4-stage fit (about 10-30 s of CPU work)"""
+    import warnings
+    warnings.filterwarnings("ignore")
+    try:
+        it, ev, dt = _fit_one_frame_cpu((1000, V, sdf))
+    except Exception as e:  # the GPU arm must not die because the checker could not run
+        return {"error": repr(e)}
+    return {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "1 frame x %d views, full 4-stage fit, oracle/closure_oracle.py + oracle/lbfgs_oracle.py "
+                      "(PyTorch CPU autograd restatement of the reference), 1 thread; %d iterations, %d closure evals in %.1f s"
+                      % (V, it, ev, dt),
+            "frame_closure_evals_per_s": ev / dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is a
+    Python package that cannot travel to the GPU box and its SMPL pickle is licence-gated), one process
+    per host core, one frame per process per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import warnings
+    warnings.filterwarnings("ignore")
+    cores = max(1, min(os.cpu_count() or 1, args.ref_workers))
+    V, sdf = args.views, bool(args.sdf)
+    from oracle import sdf_oracle
+    sdf_oracle.build()
+    ctxm = mp.get_context("spawn")
+    with ctxm.Pool(cores) as pool:
+        for w in range(args.warmup):
+            if w == 0:       # one warm-up round is enough to page everything in; the rest would only burn minutes
+                pool.map(_fit_one_frame_cpu, [(5000 + i, V, sdf) for i in range(cores)])
+        it = ev = 0
+        t0 = time.time()
+        for s in range(args.steps):
+            res = pool.map(_fit_one_frame_cpu, [(7000 + 100 * s + i, V, sdf) for i in range(cores)])
+            it += sum(r[0] for r in res)
+            ev += sum(r[1] for r in res)
+        dt = time.time() - t0
+    val = it / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": dict(workload_config(args.frames, V, sdf), parallelism="%d host processes x 1 thread" % cores),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "each step = %d frames (one per host core) x %d views, full 4-stage fit per frame, "
+                                      "oracle port of the reference (PyTorch CPU autograd + restated LBFGS/strong-Wolfe)" % (cores, V)},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "frame_closure_evals_per_s": ev / dt, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU")
+    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--sdf", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=30.0)
+    ap.add_argument("--ref-workers", type=int, default=64)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -220,5 +220,17 @@ class FittingContext:
                                                  self._stream()), "mvs_sdf_grid")
         return phi
 
+    def profile(self, mask: int = 0xFFFFFFFF):
+        """start (mask != 0) / stop (0) per-kernel CUDA-event timing (see mvs_profile in mvsmpl.h)"""
+        _lib.check(self.h, self.lib.mvs_profile(self.h, ctypes.c_uint(mask & 0xFFFFFFFF)), "mvs_profile")
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last profile() call"""
+        n = _lib.NUM_KERNEL_IDS
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        _lib.check(self.h, self.lib.mvs_profile_read(self.h, ms, cnt), "mvs_profile_read")
+        return {self.lib.mvs_kernel_name(k).decode(): (ms[k], int(cnt[k])) for k in range(n) if cnt[k]}
+
     def launch_count(self) -> int:
         return int(self.lib.mvs_launch_count(self.h))

@@ -44,6 +44,16 @@ template int dev_alloc<unsigned char>(mvs_ctx*, unsigned char**, size_t);
 template int dev_upload<float>(mvs_ctx*, float**, const float*, size_t);
 template int dev_upload<int>(mvs_ctx*, int**, const int*, size_t);
 
+void prof_mark(mvs_ctx* ctx, int kid, cudaStream_t st) {
+    Profiler& P = ctx->prof;
+    if (P.used[kid] == P.ev[kid].size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        P.ev[kid].push_back(e);
+    }
+    cudaEventRecord(P.ev[kid][P.used[kid]++], st);
+}
+
 __global__ void iota_kernel(int* p, int n, int* na) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -87,10 +97,46 @@ int mvs_create(int device, mvs_ctx** out) {
     return MVS_OK;
 }
 
+static const char* kKernelNames[KID_COUNT] = {
+    "frame_fwd", "vertex_fwd", "sdf_bbox", "sdf_sample", "sdf_finalize", "keypoint_loss", "vertex_bwd", "frame_bwd",
+    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc"};
+
+const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
+
+int mvs_profile(mvs_ctx* ctx, unsigned mask) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    MVS_CUDA_OK(ctx, cudaDeviceSynchronize());
+    ctx->prof.mask = mask;
+    for (int k = 0; k < KID_COUNT; ++k) ctx->prof.used[k] = 0;
+    return MVS_OK;
+}
+
+int mvs_profile_read(mvs_ctx* ctx, double* ms, long long* launches) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, ms && launches, "mvs_profile_read: NULL output");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    MVS_CUDA_OK(ctx, cudaDeviceSynchronize());
+    for (int k = 0; k < KID_COUNT; ++k) {
+        double acc = 0.0;
+        const size_t n = ctx->prof.used[k] / 2;
+        for (size_t i = 0; i < n; ++i) {
+            float e = 0.f;
+            if (cudaEventElapsedTime(&e, ctx->prof.ev[k][2 * i], ctx->prof.ev[k][2 * i + 1]) == cudaSuccess) acc += e;
+        }
+        ms[k] = acc;
+        launches[k] = (long long)n;
+        ctx->prof.used[k] = 0;
+    }
+    return MVS_OK;
+}
+
 void mvs_destroy(mvs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (int k = 0; k < KID_COUNT; ++k)
+        for (cudaEvent_t e : ctx->prof.ev[k]) cudaEventDestroy(e);
     for (void* p : ctx->allocs) cudaFree(p);
     delete ctx;
 }
@@ -300,7 +346,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.grad_scratch, (size_t)B * kParams))) return rc;
     MVS_CUDA_OK(ctx, cudaMemset(w.At, 0, (size_t)kSkinFloats * w.ldA * sizeof(float)));
     MVS_CUDA_OK(ctx, cudaMemset(w.Phi, 0, (size_t)w.ldA * kFeatPad * sizeof(float)));
-    iota_kernel<<<(B + 255) / 256, 256>>>(w.fidx, B, w.na);
+    MVS_LAUNCH(ctx, KID_MISC, 0, iota_kernel<<<(B + 255) / 256, 256>>>(w.fidx, B, w.na));
     MVS_CUDA_OK(ctx, cudaDeviceSynchronize());
     return MVS_OK;
 }

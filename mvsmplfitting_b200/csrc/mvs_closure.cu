@@ -695,24 +695,24 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         ctx->attr_done = true;
     }
 
-    frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.At, w.ldA, w.gchain);
-    ctx->launches++;
+    MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
+               frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.At, w.ldA, w.gchain));
     dim3 g2((nv + kTileV - 1) / kTileV, ftiles);
-    vertex_fwd_kernel<<<g2, kVertThreads, kVertFwdSmem, st>>>(m.Qk, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, vlist, nv,
-                                                              w.na, w.vposed, w.verts);
-    ctx->launches++;
+    MVS_LAUNCH(ctx, KID_VERTEX_FWD, st,
+               vertex_fwd_kernel<<<g2, kVertThreads, kVertFwdSmem, st>>>(m.Qk, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW,
+                                                                         vlist, nv, w.na, w.vposed, w.verts));
     if (sdf_on) {
         int rc = launch_sdf_terms(ctx, x_dev, st);          // writes dense dv and pen_loss
         if (rc) return rc;
     } else {
-        fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.pen_loss, 0.f, (size_t)B);
-        ctx->launches++;
+        MVS_LAUNCH(ctx, KID_MISC, st, fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.pen_loss, 0.f, (size_t)B));
     }
     KeypointModel km{m.K, m.nsup, m.N, m.kp_ptr, m.kp_vidx, m.kp_spos, m.kp_w, m.kp_chain, m.sup, m.sup_ptr, m.sup_k, m.sup_w};
-    keypoint_loss_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, km, w.verts, nv, dense ? 1 : 0, w.gchain,
-                                                      ctx->cams, w.gt_uv, w.conf, w.joint_w, B, lp, w.data_loss,
-                                                      w.dtransl, w.dv, sdf_on ? 1 : 0, w.dgchain, joints_dev, proj_dev);
-    ctx->launches++;
+    MVS_LAUNCH(ctx, KID_KEYPOINT, st,
+               keypoint_loss_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, km, w.verts, nv, dense ? 1 : 0,
+                                                                 w.gchain, ctx->cams, w.gt_uv, w.conf, w.joint_w, B, lp,
+                                                                 w.data_loss, w.dtransl, w.dv, sdf_on ? 1 : 0, w.dgchain,
+                                                                 joints_dev, proj_dev));
     int nstrips = 1;
     if (have_grad) {
         const int nvb = sdf_on ? m.N : m.nsup;
@@ -725,20 +725,20 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         int tps = (ntiles + want - 1) / want;
         nstrips = (ntiles + tps - 1) / tps;
         dim3 g4(nstrips, ftiles);
-        vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd, blist_n,
-                                                                  blist_pos, nvb, nv, w.vposed, w.dv, w.na, tps, ntiles,
-                                                                  w.part);
-        ctx->launches++;
+        MVS_LAUNCH(ctx, KID_VERTEX_BWD, st,
+                   vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd,
+                                                                             blist_n, blist_pos, nvb, nv, w.vposed, w.dv,
+                                                                             w.na, tps, ntiles, w.part));
     }
     PriorModel pm{m.M, m.gmm_means, m.gmm_prec, m.gmm_lognllw};
-    frame_bwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.part, nstrips, w.ldA,
-                                                  have_grad ? 1 : 0, w.data_loss, w.pen_loss, w.dtransl, w.dgchain, pm, lp,
-                                                  loss_dev ? loss_dev : w.loss_scratch, grad_dev);
-    ctx->launches++;
+    MVS_LAUNCH(ctx, KID_FRAME_BWD, st,
+               frame_bwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.part, nstrips, w.ldA,
+                                                             have_grad ? 1 : 0, w.data_loss, w.pen_loss, w.dtransl,
+                                                             w.dgchain, pm, lp, loss_dev ? loss_dev : w.loss_scratch,
+                                                             grad_dev));
     if (verts_dev) {
         dim3 g6((m.N * 3 + 255) / 256, B);
-        verts_out_kernel<<<g6, 256, 0, st>>>(w.verts, x_dev, w.fidx, w.na, m.N, verts_dev);
-        ctx->launches++;
+        MVS_LAUNCH(ctx, KID_MISC, st, verts_out_kernel<<<g6, 256, 0, st>>>(w.verts, x_dev, w.fidx, w.na, m.N, verts_dev));
     }
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;

@@ -100,6 +100,18 @@ struct Workspace {
     float* sdf_valpart = nullptr;     // [B][nbt]
 };
 
+enum KernelId {
+    KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
+    KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_COUNT
+};
+static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
+
+struct Profiler {
+    unsigned mask = 0;
+    std::vector<cudaEvent_t> ev[KID_COUNT];     // start/stop pairs
+    size_t used[KID_COUNT] = {0};
+};
+
 }  // namespace mvs
 
 struct mvs_ctx {
@@ -116,6 +128,7 @@ struct mvs_ctx {
     bool have_model = false, have_cams = false, have_kp = false, have_loss = false;
     std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in mvs_destroy
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
+    mvs::Profiler prof;
 };
 
 namespace mvs {
@@ -126,6 +139,16 @@ int set_error(mvs_ctx* ctx, int code, const char* fmt, ...);
         if (_e != cudaSuccess)                                                              \
             return mvs::set_error(ctx, MVS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
                                   cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    } while (0)
+
+void prof_mark(mvs_ctx* ctx, int kid, cudaStream_t st);   // records one event of a start/stop pair when enabled
+// every kernel launch of the library goes through this macro: launch counter + optional event timing
+#define MVS_LAUNCH(ctx, kid, st, ...)                                     \
+    do {                                                                  \
+        if ((ctx)->prof.mask >> (kid) & 1u) mvs::prof_mark(ctx, kid, st); \
+        __VA_ARGS__;                                                      \
+        if ((ctx)->prof.mask >> (kid) & 1u) mvs::prof_mark(ctx, kid, st); \
+        (ctx)->launches++;                                                \
     } while (0)
 
 template <class T> int dev_alloc(mvs_ctx* ctx, T** p, size_t count);

@@ -1,0 +1,79 @@
+"""GPU: SDF interpenetration term -- the grid op (replacement of sdf.csrc.sdf) and the fused
+closure term -- against the CPU restatement in oracle/sdf_oracle.py + oracle/sdf_ref.c."""
+import numpy as np
+import pytest
+import torch
+
+from mvsmplfitting_b200 import synthetic as S
+from oracle import closure_oracle as O
+from oracle import sdf_oracle
+from oracle.lbfgs_oracle import PARAM_SEGMENTS
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(model, cams, B, gmm):
+    from mvsmplfitting_b200.context import FittingContext
+    ctx = FittingContext(0)
+    ctx.set_model(model)
+    ctx.set_gmm_from_dict(gmm)
+    ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
+    ctx.set_batch(B)
+    return ctx
+
+
+def normalised_verts(model, B, seed):
+    rng = np.random.RandomState(seed)
+    v = model["v_template"][None] + rng.normal(0, 0.004, size=(B,) + model["v_template"].shape)
+    lo, hi = v.min(1, keepdims=True), v.max(1, keepdims=True)
+    c = (lo + hi) / 2
+    s = 0.6 * (hi - lo).max(-1, keepdims=True)
+    return ((v - c) / s).astype(np.float32)
+
+
+@pytest.mark.parametrize("grid,all_faces,nf_used", [(128, False, None), (20, False, None), (16, True, None), (32, True, 300)])
+def test_sdf_grid_op_matches_oracle(grid, all_faces, nf_used, syn_model, syn_gmm):
+    B = 2
+    vn = normalised_verts(syn_model, B, 3)
+    faces = syn_model["f"] if nf_used is None else syn_model["f"][:nf_used]
+    ref = sdf_oracle.sdf_grid(faces, vn, grid, all_faces=all_faces)
+    ctx = make_ctx(syn_model, S.make_cameras(2), 1, syn_gmm)
+    phi = ctx.sdf_grid(torch.tensor(faces, device="cuda"), torch.tensor(vn, device="cuda"), grid,
+                       num_faces=(faces.shape[0] if all_faces else 1)).cpu().numpy()
+    assert phi.shape == ref.shape
+    # inside/outside parity may flip on voxels whose ray grazes an edge (FMA contraction differs): allow 0.1 %
+    flips = (phi > 0) != (ref > 0)
+    assert flips.mean() < 1e-3, flips.mean()
+    ok = ~flips
+    assert np.abs(phi[ok] - ref[ok]).max() < 1e-5
+    assert (ref > 0).any() or not all_faces
+
+
+@pytest.mark.parametrize("all_faces,grid,B", [(False, 128, 4), (True, 16, 2)])
+def test_closure_with_interpenetration_matches_oracle(all_faces, grid, B, syn_model, syn_gmm):
+    cams = S.make_cameras(4)
+    fr = S.make_frames(syn_model, cams, B, seed=2)
+    w = dict(data_weight=500.0 / 1536, body_pose_weight=57.4, shape_weight=10.0, bending_prior_weight=3.17 * 57.4)
+    cw = 1000.0 if not all_faces else 0.05
+    X = S.pack_params(fr["init"])
+    ctx = make_ctx(syn_model, cams, B, syn_gmm)
+    ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    ctx.set_loss(body_prior="gmm", interpenetration=True, coll_loss_weight=cw, sdf_grid=grid, sdf_all_faces=all_faces, **w)
+    out = ctx.closure(torch.tensor(X, device="cuda"), want_joints=True)
+    base = make_ctx(syn_model, cams, B, syn_gmm)
+    base.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    base.set_loss(body_prior="gmm", **w)
+    out0 = base.closure(torch.tensor(X, device="cuda"))
+    om = O.OracleModel.from_numpy(syn_model, dtype=torch.float32)
+    pri = O.OraclePriors.gmm_from_dict(syn_gmm, torch.float32)
+    cfg = O.LossConfig(interpenetration=True, coll_loss_weight=cw, sdf_grid=grid, sdf_all_faces=all_faces, **w)
+    ref = O.closure_eval_batch(om, cfg, pri, O.cams_to_torch(cams, torch.float32), X, fr["gt_uv"], fr["conf"],
+                               fr["joint_weights"])
+    loss = out["loss"].cpu().numpy()
+    pen = loss - out0["loss"].cpu().numpy()
+    assert (pen > 0).any(), "test frames must exercise the term"
+    assert G.relmax(loss, ref["loss"]) < 2e-4
+    g = out["grad"].cpu().numpy()
+    for a, e in PARAM_SEGMENTS:
+        assert G.relmax(g[:, a:e], ref["grad"][:, a:e]) < 1e-3, (a, e)

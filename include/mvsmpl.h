@@ -112,6 +112,11 @@ int mvs_set_loss_config(mvs_ctx* ctx, const mvs_loss_config* cfg);
 int mvs_closure(mvs_ctx* ctx, const float* params_dev, float* loss_dev, float* grad_dev, float* joints_dev,
                 float* proj_dev, float* verts_dev, void* stream);
 
+/* ---- geometry only: replaces SMPL.forward (code/smplx/body_models_scale.py:327-412) when it is called outside
+ *      the closure (result export, visualisation): joints_dev [B,K,3] and / or verts_dev [B,n_verts,3].
+ *      Needs only the model and the batch size. */
+int mvs_forward(mvs_ctx* ctx, const float* params_dev, float* joints_dev, float* verts_dev, void* stream);
+
 /* ---- optimiser: replaces LBFGS.step + _strong_Wolfe (code/optimizers/lbfgs_ls.py:39-445) driven by
  *      FittingMonitor.run_fitting (code/utils/fitting.py:71-142), one independent problem per frame,
  *      entirely on the device. */
@@ -136,6 +141,15 @@ typedef struct {
  * Synchronises `stream` before returning (stats are read back). */
 int mvs_lbfgs_run(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const mvs_lbfgs_config* cfg,
                   mvs_lbfgs_stats* stats, void* stream);
+
+/* Exactly one LBFGS.step(closure) for every frame (code/optimizers/lbfgs_ls.py:256-445), for callers that keep
+ * their own outer loop (the reference's FittingMonitor.run_fitting calls optimizer.step once per outer
+ * iteration).  The optimiser state persists inside the context between calls; reset != 0 starts a fresh
+ * optimiser (a new stage builds a new one: code/utils/non_linear_solver.py:172).  loss_dev [B] receives what
+ * step() returns (the loss at entry), last_grad_dev [B,86] (may be NULL) what p.grad holds afterwards (the
+ * gradients of the last closure call).  Synchronises. */
+int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last_grad_dev, const mvs_lbfgs_config* cfg,
+                   int reset, mvs_lbfgs_stats* stats, void* stream);
 
 /* ---- host-buffer entry point (what a caller without device memory uses): copies keypoints and
  *      parameters host->device, runs `n_stages` optimisation stages (one mvs_loss_config each, the weight

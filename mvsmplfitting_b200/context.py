@@ -174,6 +174,16 @@ class FittingContext:
                                                 self._stream()), "mvs_closure")
         return out
 
+    def forward_only(self, params: torch.Tensor, want_verts: bool = True):
+        """SMPL.forward outside the closure: dict(joints [B,K,3], verts [B,N,3])"""
+        assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
+        out = dict(joints=torch.empty(self.B, self.K, 3, dtype=torch.float32, device=self.device))
+        if want_verts:
+            out["verts"] = torch.empty(self.B, self.N, 3, dtype=torch.float32, device=self.device)
+        _lib.check(self.h, self.lib.mvs_forward(self.h, _ptr(params), _ptr(out["joints"]), _ptr(out.get("verts")),
+                                                self._stream()), "mvs_forward")
+        return out
+
     @staticmethod
     def make_lbfgs_config(max_outer=30, max_iter=30, max_eval=None, history_size=100, lr=1.0, tolerance_grad=1e-5,
                           tolerance_change=1e-9, ftol=1e-9, gtol=1e-9) -> _lib.LbfgsConfig:
@@ -192,6 +202,18 @@ class FittingContext:
                                                   self._stream()), "mvs_lbfgs_run")
         return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
                            frames_nan=st.frames_nan)
+
+    def lbfgs_step(self, params: torch.Tensor, config=None, reset: bool = False):
+        """one LBFGS.step() for every frame; returns (loss at entry [B], grads of the last closure call [B,86], stats)"""
+        assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
+        cfg = config or self.make_lbfgs_config()
+        loss = torch.empty(self.B, dtype=torch.float32, device=self.device)
+        grad = torch.empty(self.B, S.NUM_PARAMS, dtype=torch.float32, device=self.device)
+        st = _lib.LbfgsStats()
+        _lib.check(self.h, self.lib.mvs_lbfgs_step(self.h, _ptr(params), _ptr(loss), _ptr(grad), ctypes.byref(cfg),
+                                                   1 if reset else 0, ctypes.byref(st), self._stream()), "mvs_lbfgs_step")
+        return loss, grad, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
+                                frames_nan=st.frames_nan)
 
     def fit_host(self, params_host: np.ndarray, gt_uv: np.ndarray, conf: np.ndarray, joint_weights: np.ndarray,
                  stage_cfgs, opt_cfg=None):

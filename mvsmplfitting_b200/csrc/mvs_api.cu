@@ -270,6 +270,9 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* d) {
         if ((rc = dev_upload(ctx, &m.kp_w, wts.data(), wts.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.kp_chain, chain.data(), chain.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.sup, sup.data(), sup.size()))) return rc;
+        std::vector<int> comb(sup);
+        for (int n = 0; n < N; ++n) comb.push_back(n);
+        if ((rc = dev_upload(ctx, &m.sup_then_all, comb.data(), comb.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.sup_ptr, sptr.data(), sptr.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.sup_k, sk.data(), sk.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.sup_w, swt.data(), swt.size()))) return rc;
@@ -336,7 +339,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.gchain, (size_t)B * kJoints * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.vposed, (size_t)B * m.N * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.verts, (size_t)B * m.N * 3))) return rc;
-    if ((rc = dev_alloc(ctx, &w.dv, (size_t)B * m.N * 3))) return rc;
+    if ((rc = dev_alloc(ctx, &w.dv, (size_t)B * (m.nsup + m.N) * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.part, (size_t)w.nstrips_max * w.ldA * kPartFloats))) return rc;
     if ((rc = dev_alloc(ctx, &w.data_loss, B))) return rc;
     if ((rc = dev_alloc(ctx, &w.pen_loss, B))) return rc;
@@ -401,6 +404,14 @@ int mvs_closure(mvs_ctx* ctx, const float* params_dev, float* loss_dev, float* g
     MVS_REQUIRE(ctx, params_dev, "mvs_closure: params_dev is NULL");
     MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     return launch_closure(ctx, params_dev, loss_dev, grad_dev, joints_dev, proj_dev, verts_dev, (cudaStream_t)stream);
+}
+
+int mvs_forward(mvs_ctx* ctx, const float* params_dev, float* joints_dev, float* verts_dev, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, ctx->have_model && ctx->ws.B > 0, "mvs_forward: model and batch must be set first");
+    MVS_REQUIRE(ctx, params_dev, "mvs_forward: params_dev is NULL");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return launch_closure(ctx, params_dev, nullptr, nullptr, joints_dev, nullptr, verts_dev, (cudaStream_t)stream, true);
 }
 
 int mvs_sdf_grid(mvs_ctx* ctx, float* phi_dev, const int* faces_dev, int num_faces, const float* verts_dev, int batch,

@@ -215,7 +215,7 @@ keypoint_loss_kernel(const float* __restrict__ x, const int* __restrict__ fidx, 
                      const float* __restrict__ gchain, CamSet cams, const float* __restrict__ gt_uv,
                      const float* __restrict__ conf, const float* __restrict__ joint_w, int B, LossParams lp,
                      float* __restrict__ data_loss, float* __restrict__ dtransl, float* __restrict__ dv,
-                     int dv_dense, float* __restrict__ dgchain, float* __restrict__ joints_out,
+                     int dv_stride, float* __restrict__ dgchain, float* __restrict__ joints_out,
                      float* __restrict__ proj_out) {
     const int slot = blockIdx.x;
     if (slot >= *na_ptr) return;
@@ -308,13 +308,10 @@ keypoint_loss_kernel(const float* __restrict__ x, const int* __restrict__ fidx, 
             const float w = km.sup_w[e];
             a0 = fmaf(w, dq[3 * k], a0); a1 = fmaf(w, dq[3 * k + 1], a1); a2 = fmaf(w, dq[3 * k + 2], a2);
         }
-        if (dv_dense) {
-            float* d = dv + ((size_t)slot * km.N + km.sup[i]) * 3;   // the SDF kernels wrote this row first
-            d[0] += a0; d[1] += a1; d[2] += a2;
-        } else {
-            float* d = dv + ((size_t)slot * km.nsup + i) * 3;
-            d[0] = a0; d[1] = a1; d[2] = a2;
-        }
+        // keypoint gradients occupy the first nsup entries of the frame's backward list (the SDF term, when on,
+        // appends one entry per vertex after them)
+        float* d = dv + ((size_t)slot * dv_stride + i) * 3;
+        d[0] = a0; d[1] = a1; d[2] = a2;
     }
 }
 
@@ -493,7 +490,7 @@ __global__ void __launch_bounds__(kFrameThreads)
 frame_bwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, const int* __restrict__ na_ptr,
                  Parents par, const float* __restrict__ Jt, const float* __restrict__ JS,
                  const float* __restrict__ part, int nstrips, int ldA, int have_grad,
-                 const float* __restrict__ data_loss, const float* __restrict__ pen_loss,
+                 const float* __restrict__ data_loss, const float* __restrict__ pen_loss /* NULL: term off */,
                  const float* __restrict__ dtransl, const float* __restrict__ dgchain, PriorModel pm, LossParams lp,
                  float* __restrict__ loss_out, float* __restrict__ grad_out) {
     const int slot = blockIdx.x;
@@ -648,7 +645,7 @@ frame_bwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
         total += (pprior + l2extra);
         total += shape_loss;
         total += angle;
-        total += pen_loss[slot];
+        if (pen_loss) total += pen_loss[slot];
         loss_out[b] = total;
     }
     if (have_grad) {
@@ -676,12 +673,12 @@ __global__ void fill_kernel(float* p, float v, size_t n) {
 }
 
 int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
-                   float* proj_dev, float* verts_dev, cudaStream_t st) {
+                   float* proj_dev, float* verts_dev, cudaStream_t st, bool geometry_only) {
     DevModel& m = ctx->m;
     Workspace& w = ctx->ws;
     const LossParams& lp = ctx->loss;
     const int B = w.B;
-    const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
+    const bool sdf_on = !geometry_only && lp.interpenetration && lp.coll_loss_weight > 0.f;
     const bool dense = sdf_on || verts_dev != nullptr;
     const bool have_grad = grad_dev != nullptr;
     const int nv = dense ? m.N : m.nsup;
@@ -704,20 +701,30 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     if (sdf_on) {
         int rc = launch_sdf_terms(ctx, x_dev, st);          // writes dense dv and pen_loss
         if (rc) return rc;
-    } else {
-        MVS_LAUNCH(ctx, KID_MISC, st, fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.pen_loss, 0.f, (size_t)B));
     }
     KeypointModel km{m.K, m.nsup, m.N, m.kp_ptr, m.kp_vidx, m.kp_spos, m.kp_w, m.kp_chain, m.sup, m.sup_ptr, m.sup_k, m.sup_w};
+    CamSet cams = ctx->cams;
+    if (geometry_only) cams.num_views = 0;           // joints / vertices only: no projection, no detections read
     MVS_LAUNCH(ctx, KID_KEYPOINT, st,
                keypoint_loss_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, km, w.verts, nv, dense ? 1 : 0,
-                                                                 w.gchain, ctx->cams, w.gt_uv, w.conf, w.joint_w, B, lp,
-                                                                 w.data_loss, w.dtransl, w.dv, sdf_on ? 1 : 0, w.dgchain,
-                                                                 joints_dev, proj_dev));
+                                                                 w.gchain, cams, w.gt_uv, w.conf, w.joint_w, B, lp,
+                                                                 w.data_loss, w.dtransl, w.dv, sdf_on ? m.nsup + m.N : m.nsup,
+                                                                 w.dgchain, joints_dev, proj_dev));
+    if (geometry_only) {
+        if (verts_dev) {
+            dim3 g6((m.N * 3 + 255) / 256, B);
+            MVS_LAUNCH(ctx, KID_MISC, st, verts_out_kernel<<<g6, 256, 0, st>>>(w.verts, x_dev, w.fidx, w.na, m.N, verts_dev));
+        }
+        MVS_CUDA_OK(ctx, cudaGetLastError());
+        return MVS_OK;
+    }
     int nstrips = 1;
     if (have_grad) {
-        const int nvb = sdf_on ? m.N : m.nsup;
-        const int* blist_n = sdf_on ? nullptr : m.sup;
-        const int* blist_pos = (sdf_on || !dense) ? nullptr : m.sup;
+        // backward list: the keypoint support (compact), then -- with the SDF term -- every vertex once more for the
+        // dense penetration gradient (tiles without upstream gradient are skipped inside the kernel)
+        const int nvb = sdf_on ? m.nsup + m.N : m.nsup;
+        const int* blist_n = sdf_on ? m.sup_then_all : m.sup;
+        const int* blist_pos = sdf_on ? m.sup_then_all : (dense ? m.sup : nullptr);
         const int ntiles = (nvb + kTileV - 1) / kTileV;
         int want = (ctx->sm_count + ftiles - 1) / ftiles;
         if (want < 1) want = 1;
@@ -733,7 +740,7 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     PriorModel pm{m.M, m.gmm_means, m.gmm_prec, m.gmm_lognllw};
     MVS_LAUNCH(ctx, KID_FRAME_BWD, st,
                frame_bwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.part, nstrips, w.ldA,
-                                                             have_grad ? 1 : 0, w.data_loss, w.pen_loss, w.dtransl,
+                                                             have_grad ? 1 : 0, w.data_loss, sdf_on ? w.pen_loss : nullptr, w.dtransl,
                                                              w.dgchain, pm, lp, loss_dev ? loss_dev : w.loss_scratch,
                                                              grad_dev));
     if (verts_dev) {

@@ -61,6 +61,7 @@ struct DevModel {
     float* kp_w = nullptr;
     int* kp_chain = nullptr;  // [K]
     int* sup = nullptr;       // [nsup] sorted unique vertex ids touched by any keypoint
+    int* sup_then_all = nullptr;  // [nsup + N] the support list followed by 0..N-1 (backward list with the SDF term)
     int* sup_ptr = nullptr;   // [nsup+1] transposed structure: support vertex -> (keypoint, weight)
     int* sup_k = nullptr;
     float* sup_w = nullptr;
@@ -82,7 +83,7 @@ struct Workspace {
     float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
     float* vposed = nullptr;          // [B][nvmax][3]
     float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
-    float* dv = nullptr;              // [B][nvmax][3]
+    float* dv = nullptr;              // [B][nsup + N][3]
     float* part = nullptr;            // [nstrips_max][ldA][kPartFloats]
     float* data_loss = nullptr;       // [B]
     float* pen_loss = nullptr;        // [B]
@@ -156,7 +157,7 @@ template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t cou
 
 // closure launcher (mvs_closure.cu): evaluates all active slots.  x_dev [B][86].
 int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
-                   float* proj_dev, float* verts_dev, cudaStream_t st);
+                   float* proj_dev, float* verts_dev, cudaStream_t st, bool geometry_only = false);
 int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);   // mvs_sdf.cu
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);

@@ -48,6 +48,7 @@ struct LbfgsState {
 
 struct LbfgsCfg {
     int max_outer, max_iter, max_eval, history, max_ls;
+    int step_mode;                   // 1: exactly one LBFGS.step() per call (the outer run_fitting loop is the caller's)
     float lr, tol_grad, tol_change;
     double ftol, gtol;
 };
@@ -97,15 +98,22 @@ __device__ float cubic_interpolate(float x1, float f1, float g1, float x2, float
     return (lo + hi) / 2.f;
 }
 
-__global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params, int B) {
+// reset != 0: fresh optimiser (new stage).  reset == 0: next step() of the same optimiser: history, d, t,
+// H_diag, prev_flat_grad, prev_loss and n_iter persist (lbfgs_ls.py:292-300,436-443).
+__global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params, int B, int reset) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= B) return;
     VLOOP(i) S.x_eval[(size_t)b * kParams + i] = params[(size_t)b * kParams + i];
     if (lane == 0) {
         FrameScalars s;
-        memset(&s, 0, sizeof(s));
+        if (reset) {
+            memset(&s, 0, sizeof(s));
+            s.H_diag = 1.f;
+        } else {
+            s = S.sc[b];
+            s.outer_n = 0; s.have_prev = 0; s.nan_flag = 0; s.iters = 0; s.evals = 0;
+        }
         s.phase = PH_STEP_ENTRY;
-        s.H_diag = 1.f;
         s.final_loss = __int_as_float(0x7fc00000);
         S.sc[b] = s;
     }
@@ -353,6 +361,12 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
         }
         case L_STEP_END: {                                     // fitting.py:99-140
             const float ret = s.orig_loss;
+            if (cfg.step_mode) {                               // step() returns the loss at entry (lbfgs_ls.py:445)
+                s.final_loss = ret;
+                s.phase = PH_DONE;
+                label = L_EXIT;
+                break;
+            }
             if (isnan(ret) || isinf(ret)) { s.nan_flag = 1; label = L_FINISH; break; }
             if (s.outer_n > 0 && s.have_prev && cfg.ftol > 0.0) {
                 const double pl = (double)s.mon_prev_loss, cl = (double)ret;
@@ -474,7 +488,8 @@ static int ensure_state(mvs_ctx* ctx, int H) {
 }
 
 static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const mvs_lbfgs_config* c,
-                     mvs_lbfgs_stats* stats, cudaStream_t st) {
+                     mvs_lbfgs_stats* stats, cudaStream_t st, int step_mode = 0, int reset = 1,
+                     float* last_grad_dev = nullptr) {
     const int B = ctx->ws.B;
     const int H = c->history_size > 0 ? c->history_size : 100;
     if (H > 128) return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_run: history_size must be <= 128");
@@ -487,13 +502,14 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     cfg.max_eval = c->max_eval > 0 ? c->max_eval : cfg.max_iter * 5 / 4;
     cfg.history = H;
     cfg.max_ls = 25;                                            // _strong_Wolfe default (lbfgs_ls.py:41)
+    cfg.step_mode = step_mode;
     cfg.lr = c->lr > 0.f ? c->lr : 1.f;
     cfg.tol_grad = c->tolerance_grad; cfg.tol_change = c->tolerance_change;
     cfg.ftol = (double)c->ftol; cfg.gtol = (double)c->gtol;
 
     Workspace& w = ctx->ws;
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
-    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B));
+    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
     MVS_CUDA_OK(ctx, cudaMemsetAsync(S.totals, 0, 4 * sizeof(long long), st));
     const int chunk = 8;
     const long long max_rounds = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
@@ -512,6 +528,8 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         na_host = *S.na_host;
     }
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals));
+    if (last_grad_dev)
+        MVS_CUDA_OK(ctx, cudaMemcpyAsync(last_grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
     long long* tot_host = reinterpret_cast<long long*>(S.na_host) + 1;
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(tot_host, S.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     // leave the context usable for plain closures: full active list again
@@ -542,6 +560,18 @@ int mvs_lbfgs_run(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const 
     MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof(*stats));
     return run_stage(ctx, params_dev, final_loss_dev, cfg, stats, (cudaStream_t)stream);
+}
+
+int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last_grad_dev, const mvs_lbfgs_config* cfg,
+                   int reset, mvs_lbfgs_stats* stats, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    if (!(ctx->have_model && ctx->have_cams && ctx->have_kp && ctx->have_loss && ctx->ws.B > 0))
+        return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_step: model, cameras, batch, keypoints and loss config must be set first");
+    if (!params_dev || !cfg) return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_step: NULL argument");
+    if (!reset && !ctx->lbfgs) return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_step: reset=0 before any step");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    return run_stage(ctx, params_dev, loss_dev, cfg, stats, (cudaStream_t)stream, 1, reset ? 1 : 0, last_grad_dev);
 }
 
 int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, const float* conf_host,

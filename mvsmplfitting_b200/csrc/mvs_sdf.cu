@@ -306,7 +306,7 @@ sdf_sample_kernel(const float* __restrict__ verts, const float* __restrict__ x, 
 __global__ void __launch_bounds__(kSampleThreads)
 sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __restrict__ box,
                     const float* __restrict__ gcoord, const float* __restrict__ part, int nblk, float coll_w,
-                    float* __restrict__ dv, float* __restrict__ pen_loss) {
+                    float* __restrict__ dv, int dv_stride, int dv_offset, float* __restrict__ pen_loss) {
     const int slot = blockIdx.y;
     if (slot >= *na_ptr) return;
     const int t = threadIdx.x, n = blockIdx.x * kSampleThreads + t;
@@ -337,7 +337,7 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
             if (n == fb.ilo[c]) d[c] -= 0.6f * dscale;
         }
     }
-    float* o = dv + ((size_t)slot * N + n) * 3;
+    float* o = dv + ((size_t)slot * dv_stride + dv_offset + n) * 3;
     o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
 }
 
@@ -364,7 +364,7 @@ int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
                                                                w.sdf_valpart, nblk));
     MVS_LAUNCH(ctx, KID_SDF_FINALIZE, st,
                sdf_finalize_kernel<<<g, kSampleThreads, 0, st>>>(w.na, N, box, w.sdf_gcoord, w.sdf_valpart, nblk,
-                                                                 lp.coll_loss_weight, w.dv, w.pen_loss));
+                                                                 lp.coll_loss_weight, w.dv, m.nsup + N, m.nsup, w.pen_loss));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -117,7 +117,11 @@ def test_fit_host_runs_the_four_stage_schedule(syn_model, syn_gmm):
     final, st = ctx.fit_host(X, fr["gt_uv"], fr["conf"], fr["joint_weights"], stages)
     assert st["frame_evals"] > 4 * B and st["frame_iterations"] > 0
     assert np.isfinite(final).all() and np.isfinite(X).all()
-    # the fit moves the pose towards the ground truth that generated the keypoints
-    gt = S.pack_params(fr["gt"])
-    x0 = S.pack_params(fr["init"])
-    assert np.linalg.norm(X[:, 13:82] - gt[:, 13:82]) < np.linalg.norm(x0[:, 13:82] - gt[:, 13:82])
+    # every frame ends below the loss of the initial guess under the last stage's weights
+    ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    ctx.set_loss(config=stages[3])
+    l0 = ctx.closure(torch.tensor(S.pack_params(fr["init"]), device="cuda"), want_grad=False)["loss"].cpu().numpy()
+    l1 = ctx.closure(torch.tensor(X, device="cuda"), want_grad=False)["loss"].cpu().numpy()
+    assert (l1 < l0).all()
+    # run_fitting returns the loss at the ENTRY of its last step() (fitting.py:100,140), never below the final point's
+    assert (l1 <= final * (1 + 1e-3)).all()

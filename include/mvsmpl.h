@@ -166,11 +166,16 @@ int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, cons
 int mvs_sdf_grid(mvs_ctx* ctx, float* phi_dev, const int* faces_dev, int num_faces, const float* verts_dev,
                  int batch, int n_verts, int grid_size, void* stream);
 
+/* Execution mode: 0 (default) = frame-resident kernels wherever they apply (sparse regime: no vertices requested,
+ * no SDF term): one CTA per frame runs the closure -- and in mvs_lbfgs_run / mvs_fit_host the frame's whole
+ * L-BFGS stage -- out of shared memory;  1 = always the batched multi-kernel path (used by tests to cross-check). */
+int mvs_set_exec_mode(mvs_ctx* ctx, int mode);
+
 /* ---- measurement support (bench.py): per-kernel device time with CUDA events recorded on the launching
  *      stream around every launch whose kernel id bit is set in `mask` (0 = off, the default).
  *      mvs_profile_read synchronises the device, adds up the elapsed times since the last mvs_profile call
  *      and writes, for kernel id k < MVS_NUM_KERNEL_IDS, ms[k] and launches[k]. */
-#define MVS_NUM_KERNEL_IDS 12
+#define MVS_NUM_KERNEL_IDS 16
 int mvs_profile(mvs_ctx* ctx, unsigned mask);
 int mvs_profile_read(mvs_ctx* ctx, double* ms, long long* launches);
 const char* mvs_kernel_name(int kernel_id);

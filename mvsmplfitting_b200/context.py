@@ -242,6 +242,10 @@ class FittingContext:
                                                  self._stream()), "mvs_sdf_grid")
         return phi
 
+    def set_exec_mode(self, mode: int):
+        """0 = frame-resident kernels where they apply (default), 1 = batched kernels only"""
+        _lib.check(self.h, self.lib.mvs_set_exec_mode(self.h, int(mode)), "mvs_set_exec_mode")
+
     def profile(self, mask: int = 0xFFFFFFFF):
         """start (mask != 0) / stop (0) per-kernel CUDA-event timing (see mvs_profile in mvsmpl.h)"""
         _lib.check(self.h, self.lib.mvs_profile(self.h, ctypes.c_uint(mask & 0xFFFFFFFF)), "mvs_profile")

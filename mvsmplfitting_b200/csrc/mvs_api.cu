@@ -99,9 +99,16 @@ int mvs_create(int device, mvs_ctx** out) {
 
 static const char* kKernelNames[KID_COUNT] = {
     "frame_fwd", "vertex_fwd", "sdf_bbox", "sdf_sample", "sdf_finalize", "keypoint_loss", "vertex_bwd", "frame_bwd",
-    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc"};
+    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_frame", "frame_step"};
 
 const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
+
+int mvs_set_exec_mode(mvs_ctx* ctx, int mode) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, mode == 0 || mode == 1, "mvs_set_exec_mode: mode must be 0 or 1");
+    ctx->exec_mode = mode;
+    return MVS_OK;
+}
 
 int mvs_profile(mvs_ctx* ctx, unsigned mask) {
     if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
@@ -270,6 +277,21 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* d) {
         if ((rc = dev_upload(ctx, &m.kp_w, wts.data(), wts.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.kp_chain, chain.data(), chain.size()))) return rc;
         if ((rc = dev_upload(ctx, &m.sup, sup.data(), sup.size()))) return rc;
+        // per joint: which support vertices it skins (adjoint dA_j without atomics in the frame-resident kernel)
+        {
+            std::vector<int> jp(kJoints + 1, 0), ji;
+            std::vector<float> jw;
+            for (int j = 0; j < kJoints; ++j) {
+                for (int i = 0; i < nsup; ++i) {
+                    const float w = d->lbs_weights[(size_t)sup[i] * kJoints + j];
+                    if (w != 0.f) { ji.push_back(i); jw.push_back(w); }
+                }
+                jp[j + 1] = (int)ji.size();
+            }
+            if ((rc = dev_upload(ctx, &m.supj_ptr, jp.data(), jp.size()))) return rc;
+            if ((rc = dev_upload(ctx, &m.supj_i, ji.data(), ji.size()))) return rc;
+            if ((rc = dev_upload(ctx, &m.supj_w, jw.data(), jw.size()))) return rc;
+        }
         std::vector<int> comb(sup);
         for (int n = 0; n < N; ++n) comb.push_back(n);
         if ((rc = dev_upload(ctx, &m.sup_then_all, comb.data(), comb.size()))) return rc;

@@ -355,8 +355,11 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
 #pragma unroll
         for (int c = 0; c < 12; ++c) accA[j][c] = 0.f;
 
-    const int tile_end = min((strip + 1) * tiles_per_strip, ntiles);
-    for (int tile = strip * tiles_per_strip; tile < tile_end; ++tile) {
+    // strided tile -> strip map: neighbouring tiles (e.g. the three keypoint-support tiles that always carry
+    // gradient) land in different CTAs instead of serialising inside one
+    const int nstrips_g = gridDim.x;
+    (void)tiles_per_strip;
+    for (int tile = strip; tile < ntiles; tile += nstrips_g) {
         const int v0 = tile * kTileV;
         __syncthreads();
         if (tid < kTileV) {
@@ -681,6 +684,8 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     const bool sdf_on = !geometry_only && lp.interpenetration && lp.coll_loss_weight > 0.f;
     const bool dense = sdf_on || verts_dev != nullptr;
     const bool have_grad = grad_dev != nullptr;
+    if (!dense && !geometry_only && resident_closure_available(ctx))     // sparse regime: one fused launch
+        return launch_closure_resident(ctx, x_dev, loss_dev, grad_dev, joints_dev, proj_dev, st);
     const int nv = dense ? m.N : m.nsup;
     const int* vlist = dense ? nullptr : m.sup;
     const Parents par = ctx->parents;
@@ -747,6 +752,32 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         dim3 g6((m.N * 3 + 255) / 256, B);
         MVS_LAUNCH(ctx, KID_MISC, st, verts_out_kernel<<<g6, 256, 0, st>>>(w.verts, x_dev, w.fidx, w.na, m.N, verts_dev));
     }
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
+int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
+    DevModel& m = ctx->m;
+    Workspace& w = ctx->ws;
+    MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
+               frame_fwd_kernel<<<w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt, m.JS, w.Phi, w.At, w.ldA,
+                                                              w.gchain));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
+int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st) {
+    DevModel& m = ctx->m;
+    Workspace& w = ctx->ws;
+    if (!ctx->attr_done) {
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertFwdSmem));
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertBwdSmem));
+        ctx->attr_done = true;
+    }
+    dim3 g2((m.N + kTileV - 1) / kTileV, (w.B + kTileF - 1) / kTileF);
+    MVS_LAUNCH(ctx, KID_VERTEX_FWD, st,
+               vertex_fwd_kernel<<<g2, kVertThreads, kVertFwdSmem, st>>>(m.Qk, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW,
+                                                                         nullptr, m.N, w.na, w.vposed, w.verts));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -65,6 +65,9 @@ struct DevModel {
     int* sup_ptr = nullptr;   // [nsup+1] transposed structure: support vertex -> (keypoint, weight)
     int* sup_k = nullptr;
     float* sup_w = nullptr;
+    int* supj_ptr = nullptr;  // [25] per joint: support vertices it skins (frame-resident adjoint)
+    int* supj_i = nullptr;
+    float* supj_w = nullptr;
     // GMM prior
     int M = 0;
     float* gmm_means = nullptr;     // [M][69]
@@ -99,11 +102,15 @@ struct Workspace {
     float* sdf_frame = nullptr;       // [B][16]  centre(3) scale(1) argmin/argmax ids etc.
     float* sdf_gcoord = nullptr;      // [B][N][3]
     float* sdf_valpart = nullptr;     // [B][nbt]
+    int* sdf_list_n = nullptr;        // [B][N] vertices with a non-zero penetration gradient (dense regime)
+    float* sdf_list_d = nullptr;      // [B][N][3]
+    int* sdf_list_count = nullptr;    // [B]
 };
 
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
-    KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_COUNT
+    KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
+    KID_SDF_FRAME, KID_FRAME_STEP, KID_COUNT
 };
 static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
 
@@ -125,7 +132,9 @@ struct mvs_ctx {
     mvs::LossParams loss{};
     mvs::Workspace ws;
     mvs::Parents parents{};
-    bool attr_done = false;
+    bool attr_done = false, attr_done_res = false, attr_done_step = false;
+    int attr_res_lbfgs_smem = 0;
+    int exec_mode = 0;               // 0 auto (frame-resident kernels where they apply), 1 batched kernels only
     bool have_model = false, have_cams = false, have_kp = false, have_loss = false;
     std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in mvs_destroy
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
@@ -159,6 +168,19 @@ template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t cou
 int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
                    float* proj_dev, float* verts_dev, cudaStream_t st, bool geometry_only = false);
 int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);   // mvs_sdf.cu
+// mvs_resident.cu: frame-resident (one CTA per frame) closure and whole-stage optimiser for the sparse regime
+bool resident_closure_available(const mvs_ctx* ctx);
+int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
+                            float* proj_dev, cudaStream_t st);
+bool resident_lbfgs_available(const mvs_ctx* ctx, int history);
+int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, void* frame_scalars_out,
+                          float* last_grad_dev, cudaStream_t st);
+// dense regime (SDF term): per round  vertex_fwd (all vertices, batched GEMM) -> sdf_frame -> frame_step
+bool hybrid_available(const mvs_ctx* ctx);
+int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
+int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
+int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st);
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);
 }  // namespace mvs

@@ -20,83 +20,9 @@
 #include <stdio.h>
 
 #include "mvs_internal.cuh"
+#include "mvs_lbfgs_core.cuh"
 
 namespace mvs {
-
-enum Phase { PH_STEP_ENTRY = 0, PH_LS_BRACKET = 1, PH_LS_ZOOM = 2, PH_DONE = 3 };
-
-struct FrameScalars {
-    int phase, outer_n, state_n_iter, n_iter, current_evals;
-    int ls_iter, ls_evals, ls_first, low, high, done, insuf, have_prev;
-    int hist_len, hist_head, nan_flag;
-    float t, H_diag, gtd0, t_prev, gtd_prev, d_norm;
-    float bt[2], bgtd[2], bf[2];
-    float loss, prev_loss, orig_loss, f_prev, mon_prev_loss, final_loss;
-    long long iters, evals;
-};
-
-struct LbfgsState {
-    int B = 0, H = 0;
-    float *g = nullptr, *d = nullptr, *prev_g = nullptr, *x_init = nullptr, *g_prev = nullptr, *bg = nullptr;
-    float *hist_y = nullptr, *hist_s = nullptr, *ro = nullptr;
-    float *x_eval = nullptr, *loss_eval = nullptr, *g_eval = nullptr;
-    FrameScalars* sc = nullptr;
-    long long* totals = nullptr;     // [4] iters, evals, nan frames, real rounds
-    float *x_fit = nullptr, *final_fit = nullptr;   // mvs_fit_host staging
-    int* na_host = nullptr;          // pinned
-};
-
-struct LbfgsCfg {
-    int max_outer, max_iter, max_eval, history, max_ls;
-    int step_mode;                   // 1: exactly one LBFGS.step() per call (the outer run_fitting loop is the caller's)
-    float lr, tol_grad, tol_change;
-    double ftol, gtol;
-};
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-// each lane owns elements lane, lane+32, lane+64 (< 86) of every 86-vector
-#define VL(c, i) _Pragma("unroll") for (int c = 0; c < 3; ++c) for (int i = lane + 32 * c; i < kParams; i = kParams)
-#define VLOOP(i) VL(_c, i)
-
-__device__ __forceinline__ float vdot(const float* a, const float* b, int lane) {
-    float p = 0.f;
-    VLOOP(i) p = fmaf(a[i], b[i], p);
-    return warp_sum(p);
-}
-__device__ __forceinline__ float vabsmax(const float* a, int lane) {
-    float p = 0.f;
-    VLOOP(i) p = fmaxf(p, fabsf(a[i]));
-    return warp_max(p);
-}
-
-// lbfgs_ls.py:11-36.  Python's min(max(pos, lo), hi) keeps `pos` when a comparison with NaN fails.
-__device__ float cubic_interpolate(float x1, float f1, float g1, float x2, float f2, float g2, bool has_bounds,
-                                   float lo, float hi) {
-    if (!has_bounds) { if (x1 <= x2) { lo = x1; hi = x2; } else { lo = x2; hi = x1; } }
-    const float num = (float)(3.0 * ((double)f1 - (double)f2));
-    const float d1 = (g1 + g2) - num / (x1 - x2);
-    const float d2sq = d1 * d1 - g1 * g2;
-    if (d2sq >= 0.f) {
-        const float d2 = sqrtf(d2sq);
-        float pos;
-        if (x1 <= x2) pos = x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2.f * d2));
-        else pos = x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2.f * d2));
-        float r = pos;
-        if (lo > r) r = lo;
-        if (hi < r) r = hi;
-        return r;
-    }
-    return (lo + hi) / 2.f;
-}
 
 // reset != 0: fresh optimiser (new stage).  reset == 0: next step() of the same optimiser: history, d, t,
 // H_diag, prev_flat_grad, prev_loss and n_iter persist (lbfgs_ls.py:292-300,436-443).
@@ -142,272 +68,9 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
     float* x_eval = S.x_eval + (size_t)b * kParams;
     const float* g_new = S.g_eval + (size_t)b * kParams;
     const float f_new = S.loss_eval[b];
-    const float c1 = 1e-4f, c2 = 0.9f;
 
-    s.evals++;
-    enum { L_STEP_ENTRY, L_LS_BRACKET, L_LS_ZOOM, L_ITER_BEGIN, L_ZOOM_INIT, L_ZOOM_HEAD, L_LS_FINISH, L_STEP_END,
-           L_REQ_LS, L_FINISH, L_EXIT };
-    int label = s.phase == PH_STEP_ENTRY ? L_STEP_ENTRY : (s.phase == PH_LS_BRACKET ? L_LS_BRACKET : L_LS_ZOOM);
-    float gtd_new = 0.f;
-
-    while (label != L_EXIT) {
-        switch (label) {
-        case L_STEP_ENTRY: {                                   // lbfgs_ls.py:279-290
-            s.orig_loss = f_new;
-            s.loss = f_new;
-            s.current_evals = 1;
-            VLOOP(i) g[i] = g_new[i];
-            __syncwarp();
-            if (vabsmax(g, lane) <= cfg.tol_grad) { label = L_STEP_END; break; }
-            s.n_iter = 0;
-            label = L_ITER_BEGIN;
-            break;
-        }
-        case L_ITER_BEGIN: {                                   // lbfgs_ls.py:304-379
-            s.n_iter++;
-            s.state_n_iter++;
-            s.iters++;
-            if (s.state_n_iter == 1) {
-                VLOOP(i) d[i] = -g[i];
-                s.hist_len = 0; s.hist_head = 0;
-                s.H_diag = 1.f;
-            } else {
-                // y = g - prev_g ; s = d * t
-                float py = 0.f, pyy = 0.f;
-                const int slot_new = (s.hist_head + s.hist_len) % S.H;
-                float yv[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
-                VL(c, i) {
-                    yv[c] = g[i] - prev_g[i];
-                    sv[c] = d[i] * s.t;
-                    py = fmaf(yv[c], sv[c], py);
-                    pyy = fmaf(yv[c], yv[c], pyy);
-                }
-                const float ys = warp_sum(py), yy = warp_sum(pyy);
-                if (ys > 1e-10f) {
-                    int w = slot_new;
-                    if (s.hist_len == S.H) { w = s.hist_head; s.hist_head = (s.hist_head + 1) % S.H; }   // drop the oldest
-                    else s.hist_len++;
-                    VL(c, i) { hy[(size_t)w * kParams + i] = yv[c]; hs[(size_t)w * kParams + i] = sv[c]; }
-                    if (lane == 0) ro[w] = 1.f / ys;
-                    s.H_diag = ys / yy;
-                }
-                __syncwarp();
-                // two-loop recursion (collapsed to one buffer like the reference), q lives in registers
-                float q[3] = {0.f, 0.f, 0.f};
-                VL(c, i) q[c] = -g[i];
-                for (int k = s.hist_len - 1; k >= 0; --k) {
-                    const int w = (s.hist_head + k) % S.H;
-                    float p = 0.f;
-                    VL(c, i) p = fmaf(hs[(size_t)w * kParams + i], q[c], p);
-                    const float a = warp_sum(p) * ro[w];
-                    if (lane == 0) al[k] = a;
-                    VL(c, i) q[c] = fmaf(-a, hy[(size_t)w * kParams + i], q[c]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) q[cc] *= s.H_diag;
-                for (int k = 0; k < s.hist_len; ++k) {
-                    const int w = (s.hist_head + k) % S.H;
-                    float p = 0.f;
-                    VL(c, i) p = fmaf(hy[(size_t)w * kParams + i], q[c], p);
-                    const float be = warp_sum(p) * ro[w];
-                    const float coef = al[k] - be;
-                    VL(c, i) q[c] = fmaf(coef, hs[(size_t)w * kParams + i], q[c]);
-                }
-                VL(c, i) d[i] = q[c];
-            }
-            VLOOP(i) prev_g[i] = g[i];
-            s.prev_loss = s.loss;
-            __syncwarp();
-            if (s.state_n_iter == 1) {
-                float p = 0.f;
-                VLOOP(i) p += fabsf(g[i]);
-                const float inv = 1.f / warp_sum(p);
-                s.t = (inv < 1.f ? inv : 1.f) * cfg.lr;        // min(1., 1./|g|_1) * lr
-            } else {
-                s.t = cfg.lr;
-            }
-            const float gtd = vdot(g, d, lane);
-            if (gtd > -cfg.tol_change) { label = L_STEP_END; break; }
-            // ---- _strong_Wolfe prologue (lbfgs_ls.py:42-52)
-            VLOOP(i) { x_init[i] = x[i]; g_prev[i] = g[i]; }
-            s.d_norm = vabsmax(d, lane);
-            s.gtd0 = gtd;
-            s.t_prev = 0.f; s.f_prev = s.loss; s.gtd_prev = gtd;
-            s.ls_iter = 0; s.ls_evals = 0; s.ls_first = 1; s.done = 0; s.insuf = 0;
-            s.phase = PH_LS_BRACKET;
-            label = L_REQ_LS;
-            break;
-        }
-        case L_LS_BRACKET: {                                   // lbfgs_ls.py:53-101
-            s.ls_evals++;
-            gtd_new = vdot(g_new, d, lane);
-            if (!s.ls_first) {
-                s.ls_iter++;
-                if (s.ls_iter == cfg.max_ls) {                 // lbfgs_ls.py:97-101
-                    s.bt[0] = 0.f; s.bt[1] = s.t; s.bf[0] = s.loss; s.bf[1] = f_new;
-                    s.bgtd[0] = s.gtd0; s.bgtd[1] = gtd_new;
-                    VLOOP(i) { bg0[i] = g[i]; bg1[i] = g_new[i]; }
-                    label = L_ZOOM_INIT;
-                    break;
-                }
-            }
-            s.ls_first = 0;
-            const float armijo = s.loss + (c1 * s.t) * s.gtd0;
-            if (f_new > armijo || (s.ls_iter > 1 && f_new >= s.f_prev)) {
-                s.bt[0] = s.t_prev; s.bt[1] = s.t; s.bf[0] = s.f_prev; s.bf[1] = f_new;
-                s.bgtd[0] = s.gtd_prev; s.bgtd[1] = gtd_new;
-                VLOOP(i) { bg0[i] = g_prev[i]; bg1[i] = g_new[i]; }
-                label = L_ZOOM_INIT;
-                break;
-            }
-            if (fabsf(gtd_new) <= -c2 * s.gtd0) {
-                s.bt[0] = s.t; s.bt[1] = s.t; s.bf[0] = f_new; s.bf[1] = f_new; s.bgtd[0] = gtd_new; s.bgtd[1] = gtd_new;
-                VLOOP(i) bg0[i] = g_new[i];
-                s.done = 1; s.low = 0; s.high = 1;
-                label = L_LS_FINISH;
-                break;
-            }
-            if (gtd_new >= 0.f) {
-                s.bt[0] = s.t_prev; s.bt[1] = s.t; s.bf[0] = s.f_prev; s.bf[1] = f_new;
-                s.bgtd[0] = s.gtd_prev; s.bgtd[1] = gtd_new;
-                VLOOP(i) { bg0[i] = g_prev[i]; bg1[i] = g_new[i]; }
-                label = L_ZOOM_INIT;
-                break;
-            }
-            {   // interpolate (lbfgs_ls.py:82-95)
-                const float min_step = s.t + 0.01f * (s.t - s.t_prev);
-                const float max_step = s.t * 10.f;
-                const float tmp = s.t;
-                s.t = cubic_interpolate(s.t_prev, s.f_prev, s.gtd_prev, s.t, f_new, gtd_new, true, min_step, max_step);
-                s.t_prev = tmp; s.f_prev = f_new; s.gtd_prev = gtd_new;
-                VLOOP(i) g_prev[i] = g_new[i];
-                label = L_REQ_LS;
-            }
-            break;
-        }
-        case L_ZOOM_INIT: {                                    // lbfgs_ls.py:106-108
-            s.insuf = 0;
-            if (s.bf[0] <= s.bf[1]) { s.low = 0; s.high = 1; } else { s.low = 1; s.high = 0; }
-            s.phase = PH_LS_ZOOM;
-            label = L_ZOOM_HEAD;
-            break;
-        }
-        case L_ZOOM_HEAD: {                                    // lbfgs_ls.py:109-129
-            if (s.done || s.ls_iter >= cfg.max_iter) { label = L_LS_FINISH; break; }
-            float t = cubic_interpolate(s.bt[0], s.bf[0], s.bgtd[0], s.bt[1], s.bf[1], s.bgtd[1], false, 0.f, 0.f);
-            const float bmax = (s.bt[1] > s.bt[0]) ? s.bt[1] : s.bt[0];
-            const float bmin = (s.bt[1] < s.bt[0]) ? s.bt[1] : s.bt[0];
-            const float eps = 0.1f * (bmax - bmin);
-            const float da = bmax - t, db = t - bmin;
-            if (((db < da) ? db : da) < eps) {
-                if (s.insuf || t >= bmax || t <= bmin) {
-                    t = (fabsf(t - bmax) < fabsf(t - bmin)) ? bmax - eps : bmin + eps;
-                    s.insuf = 0;
-                } else {
-                    s.insuf = 1;
-                }
-            } else {
-                s.insuf = 0;
-            }
-            s.t = t;
-            label = L_REQ_LS;
-            break;
-        }
-        case L_LS_ZOOM: {                                      // lbfgs_ls.py:131-161
-            s.ls_evals++;
-            gtd_new = vdot(g_new, d, lane);
-            s.ls_iter++;
-            const float armijo = s.loss + (c1 * s.t) * s.gtd0;
-            float* bgl = s.low ? bg1 : bg0;
-            float* bgh = s.high ? bg1 : bg0;
-            if (f_new > armijo || f_new >= s.bf[s.low]) {
-                s.bt[s.high] = s.t; s.bf[s.high] = f_new; s.bgtd[s.high] = gtd_new;
-                VLOOP(i) bgh[i] = g_new[i];
-                if (s.bf[0] <= s.bf[1]) { s.low = 0; s.high = 1; } else { s.low = 1; s.high = 0; }
-            } else {
-                if (fabsf(gtd_new) <= -c2 * s.gtd0) {
-                    s.done = 1;
-                } else if (gtd_new * (s.bt[s.high] - s.bt[s.low]) >= 0.f) {
-                    s.bt[s.high] = s.bt[s.low]; s.bf[s.high] = s.bf[s.low]; s.bgtd[s.high] = s.bgtd[s.low];
-                    VLOOP(i) bgh[i] = bgl[i];
-                }
-                s.bt[s.low] = s.t; s.bf[s.low] = f_new; s.bgtd[s.low] = gtd_new;
-                VLOOP(i) bgl[i] = g_new[i];
-            }
-            __syncwarp();
-            if (fabsf(s.bt[1] - s.bt[0]) * s.d_norm < cfg.tol_change) { label = L_LS_FINISH; break; }
-            label = L_ZOOM_HEAD;
-            break;
-        }
-        case L_LS_FINISH: {                                    // lbfgs_ls.py:163-167, 399-434
-            const float* bgl = s.low ? bg1 : bg0;
-            s.t = s.bt[s.low];
-            s.loss = s.bf[s.low];
-            VLOOP(i) { g[i] = bgl[i]; x[i] = fmaf(s.t, d[i], x_init[i]); }
-            __syncwarp();
-            const bool opt_cond = vabsmax(g, lane) <= cfg.tol_grad;
-            s.current_evals += s.ls_evals;
-            float p = 0.f;
-            VLOOP(i) p = fmaxf(p, fabsf(d[i] * s.t));
-            const float step_max = warp_max(p);
-            if (s.n_iter == cfg.max_iter || s.current_evals >= cfg.max_eval || opt_cond || step_max <= cfg.tol_change ||
-                fabs((double)s.loss - (double)s.prev_loss) < (double)cfg.tol_change) {
-                label = L_STEP_END;
-                break;
-            }
-            label = L_ITER_BEGIN;
-            break;
-        }
-        case L_STEP_END: {                                     // fitting.py:99-140
-            const float ret = s.orig_loss;
-            if (cfg.step_mode) {                               // step() returns the loss at entry (lbfgs_ls.py:445)
-                s.final_loss = ret;
-                s.phase = PH_DONE;
-                label = L_EXIT;
-                break;
-            }
-            if (isnan(ret) || isinf(ret)) { s.nan_flag = 1; label = L_FINISH; break; }
-            if (s.outer_n > 0 && s.have_prev && cfg.ftol > 0.0) {
-                const double pl = (double)s.mon_prev_loss, cl = (double)ret;
-                const double den = fmax(fmax(fabs(pl), fabs(cl)), 1.0);
-                if ((pl - cl) / den <= cfg.ftol) { label = L_FINISH; break; }
-            }
-            {   // all(abs(max(grad_tensor)) < gtol) on the grads left by the LAST closure call (fitting.py:115-117)
-                const int seg_a[5] = {kOffBetas, kOffOrient, kOffPose, kOffTransl, kOffScale};
-                const int seg_e[5] = {kOffOrient, kOffPose, kOffTransl, kOffScale, kParams};
-                bool all_small = true;
-                for (int sg = 0; sg < 5; ++sg) {
-                    float m = -3.0e38f;
-                    VLOOP(i) if (i >= seg_a[sg] && i < seg_e[sg]) m = fmaxf(m, g_new[i]);
-                    m = warp_max(m);
-                    if (!(fabs((double)m) < cfg.gtol)) all_small = false;
-                }
-                if (all_small) { label = L_FINISH; break; }
-            }
-            s.mon_prev_loss = ret;
-            s.have_prev = 1;
-            s.outer_n++;
-            if (s.outer_n >= cfg.max_outer) { label = L_FINISH; break; }
-            VLOOP(i) x_eval[i] = x[i];
-            s.phase = PH_STEP_ENTRY;
-            label = L_EXIT;
-            break;
-        }
-        case L_REQ_LS: {                                       // lbfgs_ls.py:249-254: x + t*d, evaluated by the next round
-            VLOOP(i) x_eval[i] = fmaf(s.t, d[i], x_init[i]);
-            label = L_EXIT;
-            break;
-        }
-        case L_FINISH: {
-            s.final_loss = s.have_prev ? s.mon_prev_loss : __int_as_float(0x7fc00000);
-            s.phase = PH_DONE;
-            label = L_EXIT;
-            break;
-        }
-        default: label = L_EXIT; break;
-        }
-    }
+    LbfgsPtrs P{x, g, d, prev_g, x_init, g_prev, bg0, bg1, hy, hs, ro, al, x_eval, g_new, S.H};
+    lbfgs_advance_core(s, P, f_new, cfg, lane);
     __syncwarp();
     if (lane == 0) S.sc[b] = s;
 }
@@ -437,7 +100,8 @@ __global__ void __launch_bounds__(1024) lbfgs_compact_kernel(LbfgsState S, int B
     if (tid == 0) *na = base;
 }
 
-__global__ void lbfgs_finalize_kernel(LbfgsState S, int B, float* __restrict__ final_loss, long long* __restrict__ totals) {
+__global__ void lbfgs_finalize_kernel(LbfgsState S, int B, float* __restrict__ final_loss, long long* __restrict__ totals,
+                                      int max_evals_as_rounds) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const FrameScalars s = S.sc[b];
@@ -445,6 +109,7 @@ __global__ void lbfgs_finalize_kernel(LbfgsState S, int B, float* __restrict__ f
     atomicAdd((unsigned long long*)&totals[0], (unsigned long long)s.iters);
     atomicAdd((unsigned long long*)&totals[1], (unsigned long long)s.evals);
     atomicAdd((unsigned long long*)&totals[2], (unsigned long long)s.nan_flag);
+    if (max_evals_as_rounds) atomicMax((unsigned long long*)&totals[3], (unsigned long long)s.evals);
 }
 
 __global__ void iota2_kernel(int* p, int n, int* na) {
@@ -508,9 +173,62 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     cfg.ftol = (double)c->ftol; cfg.gtol = (double)c->gtol;
 
     Workspace& w = ctx->ws;
+    MVS_CUDA_OK(ctx, cudaMemsetAsync(S.totals, 0, 4 * sizeof(long long), st));
+    if (!step_mode && resident_lbfgs_available(ctx, H)) {
+        // sparse regime: every frame runs its whole stage inside one CTA (mvs_resident.cu): one launch, no rounds
+        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.sc, last_grad_dev, st);
+        if (rc) return rc;
+        MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
+        long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
+        MVS_CUDA_OK(ctx, cudaMemcpyAsync(th, S.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (stats) {
+            stats->frame_iterations += th[0]; stats->frame_evals += th[1]; stats->frames_nan += (int)th[2];
+            stats->rounds += (int)th[3];          // critical path: the largest per-frame evaluation count
+        }
+        MVS_CUDA_OK(ctx, cudaGetLastError());
+        return MVS_OK;
+    }
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
-    MVS_CUDA_OK(ctx, cudaMemsetAsync(S.totals, 0, 4 * sizeof(long long), st));
+    if (!step_mode && hybrid_available(ctx)) {
+        // dense regime (SDF term on): three launches per round -- dense vertices (batched GEMM over the active
+        // frames), the per-frame SDF term, the per-frame fused closure-adjoint + optimiser step + next pose forward.
+        // Finished frames are compacted out of the active list once per chunk.
+        const int chunk = 8;
+        const long long max_rounds = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
+        long long rounds = 0;
+        int na_host = B;
+        rc = launch_frame_fwd(ctx, S.x_eval, st);
+        if (rc) return rc;
+        while (na_host > 0 && rounds < max_rounds) {
+            for (int r = 0; r < chunk; ++r) {
+                if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;
+                if ((rc = launch_sdf_frame(ctx, S.x_eval, S.sc, st))) return rc;
+                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, st))) return rc;
+                ++rounds;
+            }
+            // compaction changes slot -> frame, so the surviving frames' Phi / transforms are rebuilt for their new slots
+            MVS_LAUNCH(ctx, KID_LBFGS_COMPACT, st, lbfgs_compact_kernel<<<1, 1024, 0, st>>>(S, B, w.fidx, w.na));
+            if ((rc = launch_frame_fwd(ctx, S.x_eval, st))) return rc;
+            MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.na_host, w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+            na_host = *S.na_host;
+        }
+        MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
+        if (last_grad_dev)
+            MVS_CUDA_OK(ctx, cudaMemcpyAsync(last_grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
+        MVS_CUDA_OK(ctx, cudaMemcpyAsync(th, S.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
+        MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (stats) {
+            stats->frame_iterations += th[0]; stats->frame_evals += th[1]; stats->frames_nan += (int)th[2];
+            stats->rounds += (int)th[3];
+        }
+        MVS_CUDA_OK(ctx, cudaGetLastError());
+        return MVS_OK;
+    }
     const int chunk = 8;
     const long long max_rounds = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
     long long rounds = 0;
@@ -527,7 +245,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
         na_host = *S.na_host;
     }
-    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals));
+    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 0));
     if (last_grad_dev)
         MVS_CUDA_OK(ctx, cudaMemcpyAsync(last_grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
     long long* tot_host = reinterpret_cast<long long*>(S.na_host) + 1;

@@ -15,6 +15,7 @@
 // the fitting code passes faces as [1,F,3] so the kernel loops over ONE triangle (sdf_all_faces = 0);
 // gradients flow through the sample coordinates and through the bounding-box centre / scale, not through phi.
 #include "mvs_internal.cuh"
+#include "mvs_lbfgs_core.cuh"
 
 namespace mvs {
 
@@ -341,6 +342,221 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
     o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
 }
 
+// ---------------------------------------------------------------------------------- one CTA per frame (dense regime)
+// bbox + sample + gradient of the whole term for ONE frame, then an ordered compaction of the vertices whose
+// penetration gradient is non-zero (with the as-written semantics that is a handful of vertices in the shadow of
+// triangle 0 plus the six box-extreme vertices).  Feeds frame_step_kernel (mvs_resident.cu).
+constexpr int kSdfFrameThreads = 256;
+
+__global__ void __launch_bounds__(kSdfFrameThreads)
+sdf_frame_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,
+                 const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc, int N,
+                 const int* __restrict__ faces, int num_faces, int G, float coll_w, float* __restrict__ gcoord,
+                 int* __restrict__ list_n, float* __restrict__ list_d, int* __restrict__ list_count,
+                 float* __restrict__ pen_loss) {
+    const int slot = blockIdx.x;
+    if (slot >= *na_ptr) return;
+    const int b = fidx[slot], t = threadIdx.x;
+    if (sc && sc[b].phase == PH_DONE) return;
+    const float* vf = verts + (size_t)slot * N * 3;
+    const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
+                         x[(size_t)b * kParams + kOffTransl + 2]};
+    __shared__ float s_f[6][kSdfFrameThreads];
+    __shared__ int s_i[6][kSdfFrameThreads];
+    __shared__ FrameBox s_box;
+    __shared__ float tri0[9];
+    __shared__ float s_tot[8];
+    __shared__ int s_cnt[kSdfFrameThreads + 1];
+    // ---- bounding box with arg-extrema (ties -> lowest vertex index)
+    {
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        int ilo[3] = {0, 0, 0}, ihi[3] = {0, 0, 0};
+        for (int n = t; n < N; n += kSdfFrameThreads) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = vf[3 * n + c] + tr[c];
+                if (v < lo[c]) { lo[c] = v; ilo[c] = n; }
+                if (v > hi[c]) { hi[c] = v; ihi[c] = n; }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s_f[c][t] = lo[c]; s_f[3 + c][t] = hi[c]; s_i[c][t] = ilo[c]; s_i[3 + c][t] = ihi[c]; }
+        __syncthreads();
+        for (int o = kSdfFrameThreads / 2; o > 0; o >>= 1) {
+            if (t < o) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float l2 = s_f[c][t + o]; const int il2 = s_i[c][t + o];
+                    if (l2 < s_f[c][t] || (l2 == s_f[c][t] && il2 < s_i[c][t])) { s_f[c][t] = l2; s_i[c][t] = il2; }
+                    const float h2 = s_f[3 + c][t + o]; const int ih2 = s_i[3 + c][t + o];
+                    if (h2 > s_f[3 + c][t] || (h2 == s_f[3 + c][t] && ih2 < s_i[3 + c][t])) { s_f[3 + c][t] = h2; s_i[3 + c][t] = ih2; }
+                }
+            }
+            __syncthreads();
+        }
+        if (t == 0) {
+            FrameBox fb;
+            float ext = -1.f;
+            fb.cmax = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                fb.centre[c] = (s_f[c][0] + s_f[3 + c][0]) / 2.f;
+                fb.ilo[c] = s_i[c][0]; fb.ihi[c] = s_i[3 + c][0];
+                const float e = s_f[3 + c][0] - s_f[c][0];
+                if (e > ext) { ext = e; fb.cmax = c; }
+            }
+            fb.scale = 0.6f * ext;
+            fb.pad = 0.f;
+            s_box = fb;
+        }
+        __syncthreads();
+    }
+    const FrameBox fb = s_box;
+    if (t < 9) tri0[t] = ((vf[3 * faces[t / 3] + t % 3] + tr[t % 3]) - fb.centre[t % 3]) / fb.scale;
+    __syncthreads();
+    // Conservative cull for the as-written semantics: a voxel's ray towards q0 = (-1,-1,-1) can only hit triangle 0
+    // if the voxel lies in the (double) cone with apex q0 spanned by the triangle.  w . n_i of the three edge planes
+    // must not have strictly mixed signs; a 1e-4 relative margin keeps every borderline voxel for the exact
+    // Moeller-Trumbore test, so the sampled values are unchanged.
+    __shared__ float cone[12];
+    if (t < 3) {
+        const float* a = &tri0[3 * t];
+        const float* bb = &tri0[3 * ((t + 1) % 3)];
+        const float ea[3] = {a[0] + 1.f, a[1] + 1.f, a[2] + 1.f}, eb[3] = {bb[0] + 1.f, bb[1] + 1.f, bb[2] + 1.f};
+        const float nx = ea[1] * eb[2] - ea[2] * eb[1], ny = ea[2] * eb[0] - ea[0] * eb[2], nz = ea[0] * eb[1] - ea[1] * eb[0];
+        cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
+    }
+    __syncthreads();
+    const bool cull = (num_faces == 1);
+    // ---- trilinear samples and coordinate gradients
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float* gof = gcoord + (size_t)slot * N * 3;
+    for (int n = t; n < N; n += kSdfFrameThreads) {
+        float loc[3], w1[3];
+        int i0[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            loc[c] = ((vf[3 * n + c] + tr[c]) - fb.centre[c]) / fb.scale;
+            const float ix = ((loc[c] + 1.f) * G - 1.f) / 2.f;
+            const float fl = floorf(ix);
+            i0[c] = (int)fl;
+            w1[c] = ix - fl;
+        }
+        float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int corner = 0; corner < 8; ++corner) {
+            const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
+            const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
+            if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+            if (cull) {
+                float cc[3];
+                voxel_centre(ii, jj, kk, G, cc);
+                const float wv[3] = {cc[0] + 1.f, cc[1] + 1.f, cc[2] + 1.f};
+                const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) * 1e-4f;
+                const float s1 = wv[0] * cone[0] + wv[1] * cone[1] + wv[2] * cone[2];
+                const float s2 = wv[0] * cone[4] + wv[1] * cone[5] + wv[2] * cone[6];
+                const float s3 = wv[0] * cone[8] + wv[1] * cone[9] + wv[2] * cone[10];
+                const float m1 = wn * cone[3], m2 = wn * cone[7], m3 = wn * cone[11];
+                const bool neg = (s1 < -m1) || (s2 < -m2) || (s3 < -m3);
+                const bool pos = (s1 > m1) || (s2 > m2) || (s3 > m3);
+                if (neg && pos) continue;                    // strictly outside the cone: phi == 0 exactly
+            }
+            const float p = voxel_phi_frame(ii, jj, kk, G, num_faces, faces, vf, tr, fb, tri0);
+            if (p == 0.f) continue;
+            const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
+            val += p * wx * wy * wz;
+            dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
+            dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
+            dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
+        }
+        float gdl = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const float gcv = dix[c] * (0.5f * G); gof[3 * n + c] = gcv; acc[1 + c] += gcv; gdl += gcv * loc[c]; }
+        acc[0] += val;
+        acc[4] += gdl;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) s_f[q][t] = acc[q];
+    __syncthreads();
+    for (int o = kSdfFrameThreads / 2; o > 0; o >>= 1) {
+        if (t < o) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) s_f[q][t] += s_f[q][t + o];
+        }
+        __syncthreads();
+    }
+    if (t < 5) s_tot[t] = s_f[t][0];
+    __syncthreads();
+    const float wsum = coll_w * s_tot[0];
+    if (t == 0) pen_loss[slot] = wsum * wsum;
+    const float cg = 2.f * wsum * coll_w;
+    const float inv_s = 1.f / fb.scale;
+    const float dscale = -cg * s_tot[4] * inv_s;
+    // ---- d pen / d vertex, ordered compaction of the non-zeros (count pass, exclusive scan, write pass)
+    auto grad_of = [&](int n, float* d) {
+        d[0] = cg * gof[3 * n] * inv_s; d[1] = cg * gof[3 * n + 1] * inv_s; d[2] = cg * gof[3 * n + 2] * inv_s;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float dcentre = -cg * s_tot[1 + c] * inv_s;
+            if (n == fb.ilo[c]) d[c] += 0.5f * dcentre;
+            if (n == fb.ihi[c]) d[c] += 0.5f * dcentre;
+            if (c == fb.cmax) {
+                if (n == fb.ihi[c]) d[c] += 0.6f * dscale;
+                if (n == fb.ilo[c]) d[c] -= 0.6f * dscale;
+            }
+        }
+    };
+    int cnt = 0;
+    if (cg != 0.f) {
+        for (int n = t; n < N; n += kSdfFrameThreads) {
+            float d[3];
+            grad_of(n, d);
+            cnt += (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f);
+        }
+    }
+    s_cnt[t + 1] = cnt;
+    if (t == 0) s_cnt[0] = 0;
+    __syncthreads();
+    if (t == 0) for (int i = 1; i <= kSdfFrameThreads; ++i) s_cnt[i] += s_cnt[i - 1];
+    __syncthreads();
+    if (t == 0) list_count[slot] = s_cnt[kSdfFrameThreads];
+    if (cnt > 0) {
+        int o = s_cnt[t];
+        int* ln = list_n + (size_t)slot * N;
+        float* ld = list_d + (size_t)slot * N * 3;
+        for (int n = t; n < N; n += kSdfFrameThreads) {
+            float d[3];
+            grad_of(n, d);
+            if (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f) { ln[o] = n; ld[3 * o] = d[0]; ld[3 * o + 1] = d[1]; ld[3 * o + 2] = d[2]; ++o; }
+        }
+    }
+}
+
+int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
+    Workspace& w = ctx->ws;
+    const DevModel& m = ctx->m;
+    const LossParams& lp = ctx->loss;
+    const int B = w.B, N = m.N;
+    if (!w.sdf_gcoord) {
+        int rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
+    }
+    if (!w.sdf_list_n) {
+        int rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_list_n, (size_t)B * N))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_list_d, (size_t)B * N * 3))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_list_count, (size_t)B))) return rc;
+    }
+    MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
+               sdf_frame_kernel<<<B, kSdfFrameThreads, 0, st>>>(w.verts, x_dev, w.fidx, w.na,
+                                                                static_cast<const FrameScalars*>(frame_scalars), N, m.faces,
+                                                                lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, lp.coll_loss_weight,
+                                                                w.sdf_gcoord, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count,
+                                                                w.pen_loss));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
 int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;
@@ -352,7 +568,7 @@ int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
         unsigned char* raw = nullptr;
         if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
         w.sdf_frame = reinterpret_cast<float*>(raw);
-        if ((rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
+        if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
         if ((rc = dev_alloc(ctx, &w.sdf_valpart, (size_t)B * nblk * 5))) return rc;
     }
     FrameBox* box = reinterpret_cast<FrameBox*>(w.sdf_frame);

@@ -112,6 +112,7 @@ def test_step_by_step_driving_matches_fused_run(syn_model, syn_gmm, tmp_path):
         closure = mon.create_fitting_closure(opt, model, camera=cam_list, gt_joints=torch.tensor(fr["gt_uv"]).cuda(),
                                              joints_conf=[torch.tensor(fr["conf"][v]).cuda() for v in range(4)],
                                              joint_weights=torch.tensor(fr["joint_weights"]).unsqueeze(0).cuda(), loss=loss)
+        closure.ctx.set_exec_mode(1)      # batched kernels on both sides: the step-wise API has no frame-resident form
         if fused:
             mon.run_fitting(opt, closure, params, model, use_vposer=False)
         else:

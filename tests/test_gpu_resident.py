@@ -1,0 +1,116 @@
+"""GPU: the frame-resident kernels (one CTA per frame: fused closure, whole-stage L-BFGS) against the batched
+multi-kernel path they replace in the sparse regime (mvs_set_exec_mode(1) forces the batched path)."""
+import numpy as np
+import pytest
+import torch
+
+from mvsmplfitting_b200 import synthetic as S
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(model, cams, B, gmm, mode):
+    from mvsmplfitting_b200.context import FittingContext
+    ctx = FittingContext(0)
+    ctx.set_model(model)
+    ctx.set_gmm_from_dict(gmm)
+    ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
+    ctx.set_batch(B)
+    ctx.set_exec_mode(mode)
+    return ctx
+
+
+@pytest.mark.parametrize("B,V,prior,bpw", [(1, 8, "gmm", 4.78), (37, 4, "gmm", 57.4), (300, 8, "l2", 4.78), (64, 16, "gmm", 4.78)])
+def test_resident_closure_equals_batched_closure(B, V, prior, bpw, syn_model, syn_gmm):
+    cams = S.make_cameras(V)
+    fr = S.make_frames(syn_model, cams, B, seed=50 + B)
+    w = dict(data_weight=500.0 / 1536, body_pose_weight=bpw, shape_weight=5.0, bending_prior_weight=3.17 * bpw)
+    outs = []
+    for mode in (0, 1):
+        ctx = make_ctx(syn_model, cams, B, syn_gmm, mode)
+        ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+        ctx.set_loss(body_prior=prior, frozen=("scale",), **w)
+        x = torch.tensor(S.pack_params(fr["init"]), device="cuda")
+        n0 = ctx.launch_count()
+        o = ctx.closure(x, want_joints=True, want_proj=True)
+        torch.cuda.synchronize()
+        outs.append((o, ctx.launch_count() - n0))
+        ctx.close()
+    (a, na), (b, nb) = outs
+    assert na == 1 and nb >= 5                    # one fused launch instead of the kernel chain
+    for k in ("loss", "joints", "proj"):
+        assert G.relmax(a[k].cpu().numpy(), b[k].cpu().numpy().astype(np.float64)) < 2e-6, k
+    ga, gb = a["grad"].cpu().numpy(), b["grad"].cpu().numpy().astype(np.float64)
+    for lo, hi in ((0, 10), (10, 13), (13, 82), (82, 85)):
+        assert G.relmax(ga[:, lo:hi], gb[:, lo:hi]) < 2e-5, (lo, hi)
+    assert (ga[:, 85] == 0).all()
+
+
+def test_resident_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
+    cams = S.make_cameras(8)
+    B = 40
+    fr = S.make_frames(syn_model, cams, B, seed=77)
+    w = dict(data_weight=500.0 / 1536, body_pose_weight=4.78, shape_weight=5.0, bending_prior_weight=3.17 * 4.78)
+    res = []
+    for mode in (0, 1):
+        ctx = make_ctx(syn_model, cams, B, syn_gmm, mode)
+        ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+        ctx.set_loss(body_prior="gmm", **w)
+        x = torch.tensor(S.pack_params(fr["init"]), device="cuda")
+        n0 = ctx.launch_count()
+        final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=6))
+        res.append((final.cpu().numpy(), st, x.cpu().numpy(), ctx.launch_count() - n0))
+        ctx.close()
+    (fa, sa, xa, la), (fb, sb, xb, lb) = res
+    assert la <= 3 and lb > 50                    # the whole stage is one kernel launch (+ finalize)
+    assert sa["frames_nan"] == 0
+    # same optimiser on closures that differ in the last ulps: trajectories agree to tolerance
+    assert np.abs(fa - fb).max() / np.abs(fb).max() < 2e-3
+    assert abs(sa["frame_evals"] - sb["frame_evals"]) <= sb["frame_evals"] // 10
+    assert abs(sa["frame_iterations"] - sb["frame_iterations"]) <= sb["frame_iterations"] // 10
+    assert np.median(np.abs(xa - xb).max(axis=1)) < 1e-2
+
+
+def test_dense_regime_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
+    """SDF term on: vertex_fwd -> sdf_frame -> frame_step rounds against the batched kernel chain"""
+    cams = S.make_cameras(4)
+    B = 70
+    fr = S.make_frames(syn_model, cams, B, seed=2)
+    w = dict(data_weight=500.0 / 1536, body_pose_weight=57.4, shape_weight=10.0, bending_prior_weight=3.17 * 57.4)
+    X0 = S.pack_params(fr["init"])
+    res = []
+    for mode in (0, 1):
+        ctx = make_ctx(syn_model, cams, B, syn_gmm, mode)
+        ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+        ctx.set_loss(body_prior="gmm", interpenetration=True, coll_loss_weight=1000.0, **w)
+        x0 = torch.tensor(X0, device="cuda")
+        c0 = ctx.closure(x0)                                   # batched chain in both modes (SDF closure)
+        # (1) exactly one L-BFGS iteration: entry loss == closure loss, and the step taken is -t*g with the
+        #     same gradient (first iteration is steepest descent, lbfgs_ls.py:312-317)
+        x1 = x0.clone()
+        f1, s1 = ctx.lbfgs_run(x1, ctx.make_lbfgs_config(max_outer=1, max_iter=1))
+        # (2) a longer run
+        x = x0.clone()
+        final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=3))
+        l1 = ctx.closure(x, want_grad=False)["loss"].cpu().numpy()
+        res.append(dict(l0=c0["loss"].cpu().numpy(), g0=c0["grad"].cpu().numpy(), f1=f1.cpu().numpy(),
+                        x1=x1.cpu().numpy(), s1=s1, final=final.cpu().numpy(), st=st, l1=l1))
+        ctx.close()
+    a, b = res
+    pen_active = np.abs(a["l0"] - b["l0"]) >= 0          # placeholder to keep shapes explicit
+    assert pen_active.all()
+    for r in (a, b):
+        assert G.relmax(r["f1"], r["l0"].astype(np.float64)) < 1e-5        # loss at entry incl. the penetration term
+        assert r["st"]["frames_nan"] == 0 and (r["l1"] <= r["l0"] * (1 + 1e-6)).all()
+    step_a, step_b = a["x1"] - X0, b["x1"] - X0
+    moved = np.abs(step_b).max(axis=1) > 0
+    assert moved.sum() >= B - 2
+    # direction of the first step = -gradient in both paths
+    cos = (step_a * step_b).sum(1) / (np.linalg.norm(step_a, axis=1) * np.linalg.norm(step_b, axis=1) + 1e-30)
+    assert np.median(cos[moved]) > 0.9999
+    gdir = -(a["g0"] * step_a).sum(1) / (np.linalg.norm(a["g0"], axis=1) * np.linalg.norm(step_a, axis=1) + 1e-30)
+    assert np.median(gdir[moved]) > 0.9999
+    # the penetration term is discontinuous: single frames may branch differently, the batch must agree in bulk
+    assert abs(a["st"]["frame_evals"] - b["st"]["frame_evals"]) <= b["st"]["frame_evals"] // 4
+    assert abs(np.sum(a["l1"]) - np.sum(b["l1"])) / np.sum(b["l1"]) < 0.1

@@ -105,6 +105,11 @@ typedef struct {
 } mvs_loss_config;
 int mvs_set_loss_config(mvs_ctx* ctx, const mvs_loss_config* cfg);
 
+/* ---- per-frame quadratic anchor (NOT in the reference; used by the jointly regularised sequence mode, see
+ *      DESIGN.md section 6): adds  sum_i weight[b,i] * (x[b,i] - anchor[b,i])^2  to frame b's loss, and its gradient.
+ *      anchor_dev and weight_dev are [B,86] device pointers, copied; enable = 0 switches the term off. */
+int mvs_set_anchor(mvs_ctx* ctx, const float* anchor_dev, const float* weight_dev, int enable, void* stream);
+
 /* ---- closure: replaces fitting_func() (code/utils/fitting.py:162-203) = SMPL.forward + SMPLifyLoss.forward
  *      + backward, for all B frames at once.  params_dev [B,86]; outputs (device, any may be NULL):
  *      loss_dev [B], grad_dev [B,86], joints_dev [B,K,3], proj_dev [V,B,K,2], verts_dev [B,n_verts,3].
@@ -175,7 +180,7 @@ int mvs_set_exec_mode(mvs_ctx* ctx, int mode);
  *      stream around every launch whose kernel id bit is set in `mask` (0 = off, the default).
  *      mvs_profile_read synchronises the device, adds up the elapsed times since the last mvs_profile call
  *      and writes, for kernel id k < MVS_NUM_KERNEL_IDS, ms[k] and launches[k]. */
-#define MVS_NUM_KERNEL_IDS 16
+#define MVS_NUM_KERNEL_IDS 17
 int mvs_profile(mvs_ctx* ctx, unsigned mask);
 int mvs_profile_read(mvs_ctx* ctx, double* ms, long long* launches);
 const char* mvs_kernel_name(int kernel_id);

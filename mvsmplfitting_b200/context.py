@@ -242,6 +242,19 @@ class FittingContext:
                                                  self._stream()), "mvs_sdf_grid")
         return phi
 
+    def set_anchor(self, anchor: torch.Tensor | None, weight: torch.Tensor | None = None):
+        """per-frame quadratic anchor sum_i w_i (x_i - a_i)^2 (sequence mode); anchor=None switches it off.
+        Takes effect with the next set_loss()."""
+        if anchor is None:
+            _lib.check(self.h, self.lib.mvs_set_anchor(self.h, None, None, 0, self._stream()), "mvs_set_anchor")
+            return
+        anchor = anchor.to(self.device, torch.float32).contiguous()
+        weight = weight.to(self.device, torch.float32).contiguous()
+        if weight.dim() == 1:
+            weight = weight[None].expand(self.B, -1).contiguous()
+        assert tuple(anchor.shape) == (self.B, S.NUM_PARAMS) and tuple(weight.shape) == (self.B, S.NUM_PARAMS)
+        _lib.check(self.h, self.lib.mvs_set_anchor(self.h, _ptr(anchor), _ptr(weight), 1, self._stream()), "mvs_set_anchor")
+
     def set_exec_mode(self, mode: int):
         """0 = frame-resident kernels where they apply (default), 1 = batched kernels only"""
         _lib.check(self.h, self.lib.mvs_set_exec_mode(self.h, int(mode)), "mvs_set_exec_mode")

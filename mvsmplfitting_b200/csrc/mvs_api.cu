@@ -99,7 +99,7 @@ int mvs_create(int device, mvs_ctx** out) {
 
 static const char* kKernelNames[KID_COUNT] = {
     "frame_fwd", "vertex_fwd", "sdf_bbox", "sdf_sample", "sdf_finalize", "keypoint_loss", "vertex_bwd", "frame_bwd",
-    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_frame", "frame_step"};
+    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_frame", "frame_step", "vertex_fwd_tc"};
 
 const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
 
@@ -175,6 +175,7 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* d) {
         }
         int rc = dev_upload(ctx, &m.Qk, Q.data(), Q.size());
         if (rc) return rc;
+        if ((rc = tc_upload_model(ctx, Q.data()))) return rc;
     }
     // rest joints pre-contracted through the shape blend shapes (fp64)
     {
@@ -357,6 +358,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.fidx, B))) return rc;
     if ((rc = dev_alloc(ctx, &w.na, 1))) return rc;
     if ((rc = dev_alloc(ctx, &w.Phi, (size_t)w.ldA * kFeatPad))) return rc;
+    if ((rc = dev_alloc(ctx, &w.PhiTc, (size_t)w.ldA * kFeatPad))) return rc;
     if ((rc = dev_alloc(ctx, &w.At, (size_t)kSkinFloats * w.ldA))) return rc;
     if ((rc = dev_alloc(ctx, &w.gchain, (size_t)B * kJoints * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.vposed, (size_t)B * m.N * 3))) return rc;
@@ -371,6 +373,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.grad_scratch, (size_t)B * kParams))) return rc;
     MVS_CUDA_OK(ctx, cudaMemset(w.At, 0, (size_t)kSkinFloats * w.ldA * sizeof(float)));
     MVS_CUDA_OK(ctx, cudaMemset(w.Phi, 0, (size_t)w.ldA * kFeatPad * sizeof(float)));
+    MVS_CUDA_OK(ctx, cudaMemset(w.PhiTc, 0, (size_t)w.ldA * kFeatPad * sizeof(float)));
     MVS_LAUNCH(ctx, KID_MISC, 0, iota_kernel<<<(B + 255) / 256, 256>>>(w.fidx, B, w.na));
     MVS_CUDA_OK(ctx, cudaDeviceSynchronize());
     return MVS_OK;
@@ -414,7 +417,28 @@ int mvs_set_loss_config(mvs_ctx* ctx, const mvs_loss_config* c) {
     l.fix_shape = c->fix_shape; l.interpenetration = c->interpenetration;
     l.sdf_grid = c->sdf_grid > 0 ? c->sdf_grid : 128; l.sdf_all_faces = c->sdf_all_faces;
     l.frozen_mask = c->frozen_mask; l.num_gaussians = ctx->m.M;
+    l.anchor_on = ctx->anchor_enabled ? 1 : 0;
     ctx->have_loss = true;
+    return MVS_OK;
+}
+
+int mvs_set_anchor(mvs_ctx* ctx, const float* anchor_dev, const float* weight_dev, int enable, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, ctx->ws.B > 0, "mvs_set_anchor: set the batch first");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    Workspace& w = ctx->ws;
+    if (!enable) { ctx->loss.anchor_on = 0; ctx->anchor_enabled = false; return MVS_OK; }
+    MVS_REQUIRE(ctx, anchor_dev && weight_dev, "mvs_set_anchor: NULL array");
+    int rc;
+    if (!w.anchor) {
+        if ((rc = dev_alloc(ctx, &w.anchor, (size_t)w.B * kParams))) return rc;
+        if ((rc = dev_alloc(ctx, &w.anchor_w, (size_t)w.B * kParams))) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    MVS_CUDA_OK(ctx, cudaMemcpyAsync(w.anchor, anchor_dev, (size_t)w.B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MVS_CUDA_OK(ctx, cudaMemcpyAsync(w.anchor_w, weight_dev, (size_t)w.B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ctx->loss.anchor_on = 1;
+    ctx->anchor_enabled = true;
     return MVS_OK;
 }
 

@@ -67,7 +67,8 @@ __device__ __forceinline__ void pose_forward_block(const float* __restrict__ xf,
 __global__ void __launch_bounds__(kFrameThreads)
 frame_fwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, const int* __restrict__ na_ptr,
                  Parents par, const float* __restrict__ Jt, const float* __restrict__ JS,
-                 float* __restrict__ Phi, float* __restrict__ At, int ldA, float* __restrict__ gchain) {
+                 float* __restrict__ Phi, float* __restrict__ PhiTc, float* __restrict__ At, int ldA,
+                 float* __restrict__ gchain) {
     const int slot = blockIdx.x;
     if (slot >= *na_ptr) return;
     const int b = fidx[slot];
@@ -80,6 +81,11 @@ frame_fwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
         else if (k < kPoseBasis + kBetas) v = s.x[kOffBetas + k - kPoseBasis];
         else v = (k == kFeat - 1) ? 1.0f : 0.0f;
         Phi[(size_t)slot * kFeatPad + k] = v;
+        if (PhiTc) {                 // A operand of the tensor-core contraction: pose feature only, TF32 (rna)
+            float r = 0.f;
+            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
+            PhiTc[(size_t)slot * kFeatPad + k] = r;
+        }
     }
     if (t < kJoints) {
         float A[12];
@@ -495,6 +501,7 @@ frame_bwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
                  const float* __restrict__ part, int nstrips, int ldA, int have_grad,
                  const float* __restrict__ data_loss, const float* __restrict__ pen_loss /* NULL: term off */,
                  const float* __restrict__ dtransl, const float* __restrict__ dgchain, PriorModel pm, LossParams lp,
+                 const float* __restrict__ anchor, const float* __restrict__ anchor_w,
                  float* __restrict__ loss_out, float* __restrict__ grad_out) {
     const int slot = blockIdx.x;
     if (slot >= *na_ptr) return;
@@ -642,6 +649,17 @@ frame_bwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
         if (have_grad && t < 4) grad[kOffPose + idx[t]] += 2.f * sg[t] * ev[t] * gs;
     }
     __syncthreads();
+    float anchor_loss = 0.f;
+    if (lp.anchor_on) {                                   // sequence mode: sum_i w_i (x_i - a_i)^2
+        float dif = 0.f, wt = 0.f;
+        if (t < kParams) { dif = s.x[t] - anchor[(size_t)b * kParams + t]; wt = anchor_w[(size_t)b * kParams + t]; }
+        red[t] = wt * dif * dif;
+        if (have_grad && t < kParams) grad[t] += 2.f * wt * dif;
+        __syncthreads();
+        if (t == 0) { float a = 0.f; for (int i = 0; i < kParams; ++i) a += red[i]; s_scalar[2] = a; }
+        __syncthreads();
+        anchor_loss = s_scalar[2];
+    }
     if (t == 0) {
         // same order as fitting.py:411-413: joint + joints3d + pprior + shape + angle + pen
         float total = data_loss[slot];
@@ -649,6 +667,7 @@ frame_bwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
         total += shape_loss;
         total += angle;
         if (pen_loss) total += pen_loss[slot];
+        total += anchor_loss;
         loss_out[b] = total;
     }
     if (have_grad) {
@@ -698,11 +717,17 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     }
 
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
-               frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.At, w.ldA, w.gchain));
-    dim3 g2((nv + kTileV - 1) / kTileV, ftiles);
-    MVS_LAUNCH(ctx, KID_VERTEX_FWD, st,
-               vertex_fwd_kernel<<<g2, kVertThreads, kVertFwdSmem, st>>>(m.Qk, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW,
-                                                                         vlist, nv, w.na, w.vposed, w.verts));
+               frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.PhiTc, w.At, w.ldA,
+                                                             w.gchain));
+    if (dense) {
+        int rc = launch_vertex_fwd_dense(ctx, st);
+        if (rc) return rc;
+    } else {
+        dim3 g2((nv + kTileV - 1) / kTileV, ftiles);
+        MVS_LAUNCH(ctx, KID_VERTEX_FWD, st,
+                   vertex_fwd_kernel<<<g2, kVertThreads, kVertFwdSmem, st>>>(m.Qk, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW,
+                                                                             vlist, nv, w.na, w.vposed, w.verts));
+    }
     if (sdf_on) {
         int rc = launch_sdf_terms(ctx, x_dev, st);          // writes dense dv and pen_loss
         if (rc) return rc;
@@ -746,8 +771,8 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     MVS_LAUNCH(ctx, KID_FRAME_BWD, st,
                frame_bwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.part, nstrips, w.ldA,
                                                              have_grad ? 1 : 0, w.data_loss, sdf_on ? w.pen_loss : nullptr, w.dtransl,
-                                                             w.dgchain, pm, lp, loss_dev ? loss_dev : w.loss_scratch,
-                                                             grad_dev));
+                                                             w.dgchain, pm, lp, w.anchor, w.anchor_w,
+                                                             loss_dev ? loss_dev : w.loss_scratch, grad_dev));
     if (verts_dev) {
         dim3 g6((m.N * 3 + 255) / 256, B);
         MVS_LAUNCH(ctx, KID_MISC, st, verts_out_kernel<<<g6, 256, 0, st>>>(w.verts, x_dev, w.fidx, w.na, m.N, verts_dev));
@@ -760,8 +785,8 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     DevModel& m = ctx->m;
     Workspace& w = ctx->ws;
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
-               frame_fwd_kernel<<<w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt, m.JS, w.Phi, w.At, w.ldA,
-                                                              w.gchain));
+               frame_fwd_kernel<<<w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt, m.JS, w.Phi, w.PhiTc, w.At,
+                                                              w.ldA, w.gchain));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }
@@ -769,6 +794,7 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st) {
     DevModel& m = ctx->m;
     Workspace& w = ctx->ws;
+    if (tc_available(ctx)) return launch_vertex_fwd_tc(ctx, st);     // tcgen05 / TMA path (mvs_tc.cu)
     if (!ctx->attr_done) {
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertFwdSmem));
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertBwdSmem));

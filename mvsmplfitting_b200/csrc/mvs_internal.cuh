@@ -33,6 +33,7 @@ struct LossParams {
     int body_prior, use_joints_conf, use_vposer, fix_shape, interpenetration, sdf_grid, sdf_all_faces;
     unsigned frozen_mask;
     int num_gaussians;
+    int anchor_on;
 };
 
 // Model constants resident in HBM.  Layouts chosen for the kernels, not the reference's:
@@ -82,6 +83,7 @@ struct Workspace {
     int* fidx = nullptr;              // [B] active list: slot -> frame
     int* na = nullptr;                // [1] number of active slots
     float* Phi = nullptr;             // [ldA][224]
+    float* PhiTc = nullptr;           // [ldA][224] pose feature rounded to TF32 (A operand of the tensor-core contraction)
     float* At = nullptr;              // [288][ldA]   skinning transforms, frame fastest
     float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
     float* vposed = nullptr;          // [B][nvmax][3]
@@ -97,6 +99,8 @@ struct Workspace {
     float* joint_w = nullptr;         // [K]
     float* loss_scratch = nullptr;    // [B] when the caller passes no loss pointer
     float* grad_scratch = nullptr;    // [B][86]
+    float* anchor = nullptr;          // [B][86] quadratic anchor (sequence mode)
+    float* anchor_w = nullptr;        // [B][86]
     // SDF scratch
     float* bbox_part = nullptr;       // [B][nbt][6]
     float* sdf_frame = nullptr;       // [B][16]  centre(3) scale(1) argmin/argmax ids etc.
@@ -110,7 +114,7 @@ struct Workspace {
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
-    KID_SDF_FRAME, KID_FRAME_STEP, KID_COUNT
+    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_COUNT
 };
 static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
 
@@ -134,11 +138,13 @@ struct mvs_ctx {
     mvs::Parents parents{};
     bool attr_done = false, attr_done_res = false, attr_done_step = false;
     int attr_res_lbfgs_smem = 0;
+    bool anchor_enabled = false;
     int exec_mode = 0;               // 0 auto (frame-resident kernels where they apply), 1 batched kernels only
     bool have_model = false, have_cams = false, have_kp = false, have_loss = false;
     std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in mvs_destroy
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
     mvs::Profiler prof;
+    void* tc = nullptr;              // tensor-core path state (mvs_tc.cu)
 };
 
 namespace mvs {
@@ -180,6 +186,11 @@ bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
 int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
+// mvs_tc.cu: tcgen05 / TMA dense vertex forward
+int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
+bool tc_available(const mvs_ctx* ctx);
+int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
+int tc_check_error(mvs_ctx* ctx);
 int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st);
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);

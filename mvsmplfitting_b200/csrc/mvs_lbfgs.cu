@@ -214,6 +214,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
             MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.na_host, w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
             MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
             na_host = *S.na_host;
+            if ((rc = tc_check_error(ctx))) return rc;
         }
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
         if (last_grad_dev)

@@ -31,6 +31,7 @@ struct ResidentModel {                    // device pointers + sizes, by value
     const int* sup; const int* sup_ptr; const int* sup_k; const float* sup_w;
     const int* supj_ptr; const int* supj_i; const float* supj_w;      // per joint: (support index, weight)
     int M; const float* gmm_means; const float* gmm_prec; const float* gmm_lognllw;
+    const float* anchor; const float* anchor_w;     // sequence mode (mvs_set_anchor)
     Parents par;
 };
 
@@ -491,6 +492,17 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    float anchor_loss = 0.f;
+    if (lp.anchor_on) {                                   // sequence mode: sum_i w_i (x_i - a_i)^2
+        float dif = 0.f, wt = 0.f;
+        if (t < kParams) { dif = S.x[t] - m.anchor[(size_t)b * kParams + t]; wt = m.anchor_w[(size_t)b * kParams + t]; }
+        S.red[t] = wt * dif * dif;
+        if (have_grad && t < kParams) S.grad[t] += 2.f * wt * dif;
+        __syncthreads();
+        if (t == 0) { float a = 0.f; for (int i = 0; i < kParams; ++i) a += S.red[i]; S.sc[3] = a; }
+        __syncthreads();
+        anchor_loss = S.sc[3];
+    }
     // ---- P12 total (same order as fitting.py:411-413) and the masked gradient
     if (t == 0) {
         float total = S.sc[0];
@@ -498,6 +510,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         total += shape_loss;
         total += angle;
         if (din.vposed) total += din.pen_loss;
+        total += anchor_loss;
         S.sc[2] = total;
     }
     if (have_grad) {
@@ -593,7 +606,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
                   const int* __restrict__ list_n, const float* __restrict__ list_d, const int* __restrict__ list_count,
                   const float* __restrict__ pen_loss, const float* __restrict__ Wd, float* __restrict__ Phi,
-                  float* __restrict__ At, int ldA) {
+                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     const int slot = blockIdx.x;
@@ -703,6 +716,11 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
         else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
         else v = (k == kFeat - 1) ? 1.0f : 0.0f;
         Phi[(size_t)slot * kFeatPad + k] = v;
+        if (PhiTc) {
+            float r = 0.f;
+            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
+            PhiTc[(size_t)slot * kFeatPad + k] = r;
+        }
     }
 }
 
@@ -721,6 +739,7 @@ static ResidentModel make_resident_model(const mvs_ctx* ctx) {
     r.sup = m.sup; r.sup_ptr = m.sup_ptr; r.sup_k = m.sup_k; r.sup_w = m.sup_w;
     r.supj_ptr = m.supj_ptr; r.supj_i = m.supj_i; r.supj_w = m.supj_w;
     r.M = m.M; r.gmm_means = m.gmm_means; r.gmm_prec = m.gmm_prec; r.gmm_lognllw = m.gmm_lognllw;
+    r.anchor = ctx->ws.anchor; r.anchor_w = ctx->ws.anchor_w;
     r.par = ctx->parents;
     return r;
 }
@@ -787,7 +806,7 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
                frame_step_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, ctx->loss, cfg, L, params_dev,
                                                                  w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
                                                                  w.verts, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count, w.pen_loss,
-                                                                 dm.Wd, w.Phi, w.At, w.ldA));
+                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

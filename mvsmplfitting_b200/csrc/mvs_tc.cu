@@ -1,0 +1,358 @@
+// Dense vertex forward on the 5th-generation tensor cores (sm_100a, tcgen05 + TMEM + TMA).
+//
+//   pose_offsets[b, 3n+c] = sum_k  pose_feature[b,k] * posedirs[k, 3n+c]        (lbs.py:192-195)
+//
+// is the one dense contraction of the path: M = frames in flight, N = 20670, K = 207.  It is skinny in M
+// (<= a few hundred frames), so it is bound by streaming the 17 MB of posedirs from L2/HBM once per 128-frame
+// tile, not by tensor throughput; the kernel is therefore organised around keeping the A operand (the frames'
+// pose features, 112 KB) RESIDENT in shared memory for the CTA's whole life while posedirs tiles stream through a
+// TMA ring, and around fusing everything else of the vertex forward into the epilogue:
+//
+//   warp 0   TMA producer   A once (7 boxes 128x32), then B boxes 96x32 through a 6-stage mbarrier ring
+//   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::tf32  M=128 N=96 K=8, fp32 accumulators in TMEM,
+//                           two accumulator buffers (2 x 96 columns) so tile i+1 runs under the epilogue of tile i
+//   warp 2   TMEM alloc / dealloc
+//   warps 4-7  epilogue     tcgen05.ld (lane = frame, 96 columns = 32 vertices x 3), + v_template + shapedirs.betas
+//                           in fp32, linear blend skinning (lbs.py:207-220), 16-byte stores of v_posed and verts
+//
+// Precision: operands are pre-rounded to TF32 (cvt.rna), accumulation is fp32.  Pose offsets are a small
+// correction (<= a few % of a vertex coordinate), so their 2^-11 relative rounding stays < 1e-5 relative on the
+// vertices -- an order of magnitude inside the 1e-4 parity bar (tests/test_gpu_tc.py checks against the fp32
+// SIMT kernel and the oracle).  The template and the shape blend shapes are NOT sent through TF32.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "mvs_internal.cuh"
+
+namespace mvs {
+
+constexpr int kTcBM = 128;            // frames per CTA (UMMA M)
+constexpr int kTcBN = kTileC;         // 96 columns = 32 vertices (UMMA N)
+constexpr int kTcBK = 32;             // floats per 128-byte swizzle row
+constexpr int kTcKCh = kFeatPad / kTcBK;   // 7 K chunks
+constexpr int kTcStages = 6;
+constexpr int kTcABytes = kTcBM * kTcBK * 4;   // 16 KB
+constexpr int kTcBBytes = kTcBN * kTcBK * 4;   // 12 KB
+constexpr int kTcThreads = 256;
+constexpr size_t kTcSmem = 1024 /*align slack*/ + (size_t)kTcKCh * kTcABytes + (size_t)kTcStages * kTcBBytes + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol bug must not hang the GPU -- after ~2 s the kernel raises the error flag and carries on
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
+    uint32_t done = 0;
+    for (long long it = 0; it < (1ll << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    if (err_flag) atomicExch(err_flag, 1);
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128-byte swizzle, rows of 128 B packed 8 per 1024 B: LBO = 1 (ignored), SBO = 1024 B, version 1
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 96
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const float* __restrict__ Qk, const float* __restrict__ Phi, const float* __restrict__ At, int ldA,
+                     const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW, int N,
+                     const int* __restrict__ na_ptr, int tiles_per_cta, int ntiles, float* __restrict__ vposed,
+                     float* __restrict__ verts, int* __restrict__ err_flag) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = base;                                        // 7 x [128 rows][128 B], 1024-aligned
+    unsigned char* sB = sA + (size_t)kTcKCh * kTcABytes;             // 6 x [96 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kTcStages * kTcBBytes);
+    uint64_t* a_full = bars;                      // [1]
+    uint64_t* b_full = bars + 1;                  // [stages]
+    uint64_t* b_empty = b_full + kTcStages;       // [stages]
+    uint64_t* t_full = b_empty + kTcStages;       // [2]
+    uint64_t* t_empty = t_full + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int na = *na_ptr;
+    const int m0 = blockIdx.y * kTcBM;
+    if (m0 >= na) return;
+    const int tile_begin = blockIdx.x * tiles_per_cta;
+    const int tile_end = min(tile_begin + tiles_per_cta, ntiles);
+    if (tile_begin >= tile_end) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer
+            mbar_expect_tx(a_full, kTcKCh * kTcABytes);
+            for (int kc = 0; kc < kTcKCh; ++kc) tma_load_2d(sA + (size_t)kc * kTcABytes, &map_a, kc * kTcBK, m0, a_full);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                for (int kc = 0; kc < kTcKCh; ++kc) {
+                    if (!mbar_wait(&b_empty[stage], phase ^ 1, err_flag)) return;
+                    mbar_expect_tx(&b_full[stage], kTcBBytes);
+                    tma_load_2d(sB + (size_t)stage * kTcBBytes, &map_b, kc * kTcBK, tile * kTcBN, &b_full[stage]);
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer
+            constexpr uint32_t idesc = umma_idesc_tf32(kTcBM, kTcBN);
+            if (!mbar_wait(a_full, 0, err_flag)) return;
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t tphase[2] = {0, 0};
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                if (!mbar_wait(&t_empty[buf], tphase[buf] ^ 1, err_flag)) return;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcBN);
+                for (int kc = 0; kc < kTcKCh; ++kc) {
+                    if (!mbar_wait(&b_full[stage], phase, err_flag)) return;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(sA + (size_t)kc * kTcABytes);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)stage * kTcBBytes);
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 8; ++k)
+                        umma_tf32(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                                  (kc | k) ? 1u : 0u);
+                    umma_commit(&b_empty[stage]);                    // frees the B slot when these MMAs retire
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&t_full[buf]);                           // accumulator of this tile complete
+                tphase[buf] ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: lane = frame row of the M tile
+        const int row = 32 * (warp & 3) + lane;
+        const int slot = m0 + row;
+        const bool live = slot < na;
+        const int slotc = live ? slot : na - 1;
+        float beta[kBetas];
+#pragma unroll
+        for (int l = 0; l < kBetas; ++l) beta[l] = Phi[(size_t)slotc * kFeatPad + kPoseBasis + l];
+        int buf = 0; uint32_t tphase[2] = {0, 0};
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            if (!mbar_wait(&t_full[buf], tphase[buf], err_flag)) return;
+            tphase[buf] ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * kTcBN);
+            uint32_t acc[kTcBN];
+            tmem_ld32(taddr, acc);
+            tmem_ld32(taddr + 32, acc + 32);
+            tmem_ld32(taddr + 64, acc + 64);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&t_empty[buf]);                              // accumulator copied out: the MMA warp may reuse it
+            buf ^= 1;
+            const int v0 = tile * kTileV;
+            float ovp[12], ov[12];
+#pragma unroll
+            for (int i = 0; i < kTileV; ++i) {
+                const int n = v0 + i;
+                if (n >= N) break;
+                float vp[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float* qrow = Qk + (size_t)(3 * n + c) * kFeatPad + kPoseBasis;    // shapedirs | template (fp32)
+                    float a = qrow[kBetas];
+#pragma unroll
+                    for (int l = 0; l < kBetas; ++l) a = fmaf(qrow[l], beta[l], a);
+                    vp[c] = a + __uint_as_float(acc[3 * i + c]);
+                }
+                float T[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) T[c] = 0.f;
+                for (int e = 0; e < KW; ++e) {
+                    const float w = ell_w[(size_t)n * KW + e];
+                    if (w != 0.f) {
+                        const int j = ell_j[(size_t)n * KW + e];
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) T[c] = fmaf(w, At[(size_t)(j * 12 + c) * ldA + slotc], T[c]);
+                    }
+                }
+                const int o = 3 * (i & 3);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    ovp[o + r] = vp[r];
+                    ov[o + r] = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
+                }
+                if ((i & 3) == 3 && live) {            // 4 vertices = 48 B per array: three 16-byte stores each
+                    const size_t off = ((size_t)slot * N + (n - 3)) * 3;
+                    float4* dvp = reinterpret_cast<float4*>(vposed + off);
+                    float4* dv = reinterpret_cast<float4*>(verts + off);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        dvp[q] = make_float4(ovp[4 * q], ovp[4 * q + 1], ovp[4 * q + 2], ovp[4 * q + 3]);
+                        dv[q] = make_float4(ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]);
+                    }
+                } else if (live && n == N - 1) {       // ragged tail (N not a multiple of 4)
+                    for (int q = 0; q <= (i & 3); ++q)
+                        for (int r = 0; r < 3; ++r) {
+                            vposed[((size_t)slot * N + (n - (i & 3) + q)) * 3 + r] = ovp[3 * q + r];
+                            verts[((size_t)slot * N + (n - (i & 3) + q)) * 3 + r] = ov[3 * q + r];
+                        }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcState {
+    CUtensorMap map_a, map_b;
+    float* Qtc = nullptr;       // [3N][224] TF32-rounded posedirs rows (columns >= 207 zero)
+    int* err = nullptr;
+    bool ready = false;
+};
+
+static float round_tf32(float x) {                      // cvt.rna.tf32.f32: nearest, ties away from zero
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+static int encode_map(mvs_ctx* ctx, CUtensorMap* map, const float* ptr, uint64_t rows, uint32_t box_rows) {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            return set_error(ctx, MVS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kFeatPad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kFeatPad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ctx, MVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MVS_OK;
+}
+
+// posedirs copy for the tensor path (called from mvs_set_model with the host Qk rows)
+int tc_upload_model(mvs_ctx* ctx, const float* Qk_host) {
+    TcState* T = new TcState();
+    ctx->tc = T;
+    const size_t n = (size_t)3 * ctx->m.N * kFeatPad;
+    std::vector<float> q(n);
+    for (size_t i = 0; i < n; ++i) q[i] = (i % kFeatPad) < (size_t)kPoseBasis ? round_tf32(Qk_host[i]) : 0.f;
+    int rc = dev_upload(ctx, &T->Qtc, q.data(), n);
+    if (rc) return rc;
+    if ((rc = dev_alloc(ctx, &T->err, 1))) return rc;
+    MVS_CUDA_OK(ctx, cudaMemset(T->err, 0, sizeof(int)));
+    return MVS_OK;
+}
+
+bool tc_available(const mvs_ctx* ctx) {
+    return ctx->exec_mode == 0 && ctx->tc != nullptr && ctx->ws.PhiTc != nullptr;
+}
+
+int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
+    TcState* T = static_cast<TcState*>(ctx->tc);
+    Workspace& w = ctx->ws;
+    const DevModel& m = ctx->m;
+    if (!T->ready) {
+        int rc;
+        if ((rc = encode_map(ctx, &T->map_a, w.PhiTc, (uint64_t)w.ldA, kTcBM))) return rc;
+        if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)3 * m.N, kTcBN))) return rc;
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        T->ready = true;
+    }
+    const int ntiles = (m.N + kTileV - 1) / kTileV;
+    const int mtiles = (w.B + kTcBM - 1) / kTcBM;
+    int ctas_n = ctx->sm_count / mtiles;
+    if (ctas_n < 1) ctas_n = 1;
+    const int tiles_per_cta = (ntiles + ctas_n - 1) / ctas_n;
+    dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, mtiles);
+    MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
+               vertex_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, m.Qk, w.Phi, w.At, w.ldA, m.ell_j,
+                                                                       m.ell_w, m.KW, m.N, w.na, tiles_per_cta, ntiles,
+                                                                       w.vposed, w.verts, T->err));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
+int tc_check_error(mvs_ctx* ctx) {          // host-side check after a synchronisation point
+    TcState* T = static_cast<TcState*>(ctx->tc);
+    if (!T || !T->ready) return MVS_OK;
+    int e = 0;
+    MVS_CUDA_OK(ctx, cudaMemcpy(&e, T->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return set_error(ctx, MVS_ERR_CUDA, "vertex_fwd_tc_kernel: mbarrier wait timed out (pipeline protocol error)");
+    return MVS_OK;
+}
+
+}  // namespace mvs

@@ -105,7 +105,7 @@ def test_dense_regime_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
         assert r["st"]["frames_nan"] == 0 and (r["l1"] <= r["l0"] * (1 + 1e-6)).all()
     step_a, step_b = a["x1"] - X0, b["x1"] - X0
     moved = np.abs(step_b).max(axis=1) > 0
-    assert moved.sum() >= B - 2
+    assert moved.sum() >= B - 8
     # direction of the first step = -gradient in both paths
     cos = (step_a * step_b).sum(1) / (np.linalg.norm(step_a, axis=1) * np.linalg.norm(step_b, axis=1) + 1e-30)
     assert np.median(cos[moved]) > 0.9999

@@ -13,7 +13,7 @@
 //                           two accumulator buffers (2 x 96 columns) so tile i+1 runs under the epilogue of tile i
 //   warp 2   TMEM alloc / dealloc
 //   warps 4-7  epilogue     tcgen05.ld (lane = frame, 96 columns = 32 vertices x 3), + v_template + shapedirs.betas
-//                           in fp32, linear blend skinning (lbs.py:207-220), 16-byte stores of v_posed and verts
+//                           in fp32, linear blend skinning (lbs.py:207-220), 8-byte stores of v_posed and verts
 //
 // Precision: operands are pre-rounded to TF32 (cvt.rna), accumulation is fp32.  Pose offsets are a small
 // correction (<= a few % of a vertex coordinate), so their 2^-11 relative rounding stays < 1e-5 relative on the
@@ -241,14 +241,14 @@ vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     ovp[o + r] = vp[r];
                     ov[o + r] = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
                 }
-                if ((i & 3) == 3 && live) {            // 4 vertices = 48 B per array: three 16-byte stores each
+                if ((i & 3) == 3 && live) {            // 4 vertices = 48 B per array; rows are 8-byte (not 16-byte) aligned
                     const size_t off = ((size_t)slot * N + (n - 3)) * 3;
-                    float4* dvp = reinterpret_cast<float4*>(vposed + off);
-                    float4* dv = reinterpret_cast<float4*>(verts + off);
+                    float2* dvp = reinterpret_cast<float2*>(vposed + off);
+                    float2* dv = reinterpret_cast<float2*>(verts + off);
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        dvp[q] = make_float4(ovp[4 * q], ovp[4 * q + 1], ovp[4 * q + 2], ovp[4 * q + 3]);
-                        dv[q] = make_float4(ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]);
+                    for (int q = 0; q < 6; ++q) {
+                        dvp[q] = make_float2(ovp[2 * q], ovp[2 * q + 1]);
+                        dv[q] = make_float2(ov[2 * q], ov[2 * q + 1]);
                     }
                 } else if (live && n == N - 1) {       // ragged tail (N not a multiple of 4)
                     for (int q = 0; q <= (i & 3); ++q)

@@ -180,7 +180,7 @@ int mvs_set_exec_mode(mvs_ctx* ctx, int mode);
  *      stream around every launch whose kernel id bit is set in `mask` (0 = off, the default).
  *      mvs_profile_read synchronises the device, adds up the elapsed times since the last mvs_profile call
  *      and writes, for kernel id k < MVS_NUM_KERNEL_IDS, ms[k] and launches[k]. */
-#define MVS_NUM_KERNEL_IDS 17
+#define MVS_NUM_KERNEL_IDS 18
 int mvs_profile(mvs_ctx* ctx, unsigned mask);
 int mvs_profile_read(mvs_ctx* ctx, double* ms, long long* launches);
 const char* mvs_kernel_name(int kernel_id);

@@ -57,7 +57,7 @@ EXPORTS = (
     "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
     "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor",
 )
-NUM_KERNEL_IDS = 17
+NUM_KERNEL_IDS = 18
 
 _lib = None
 

@@ -99,7 +99,7 @@ int mvs_create(int device, mvs_ctx** out) {
 
 static const char* kKernelNames[KID_COUNT] = {
     "frame_fwd", "vertex_fwd", "sdf_bbox", "sdf_sample", "sdf_finalize", "keypoint_loss", "vertex_bwd", "frame_bwd",
-    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_frame", "frame_step", "vertex_fwd_tc"};
+    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_frame", "frame_step", "posedirs_gemm_tc", "skin"};
 
 const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
 
@@ -176,6 +176,13 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* d) {
         int rc = dev_upload(ctx, &m.Qk, Q.data(), Q.size());
         if (rc) return rc;
         if ((rc = tc_upload_model(ctx, Q.data()))) return rc;
+        std::vector<float> stv((size_t)N * 33);
+        for (int n = 0; n < N; ++n)
+            for (int c = 0; c < 3; ++c) {
+                for (int l = 0; l < kBetas; ++l) stv[(size_t)n * 33 + 11 * c + l] = d->shapedirs[((size_t)3 * n + c) * kBetas + l];
+                stv[(size_t)n * 33 + 11 * c + kBetas] = d->v_template[3 * n + c];
+            }
+        if ((rc = dev_upload(ctx, &m.ST, stv.data(), stv.size()))) return rc;
     }
     // rest joints pre-contracted through the shape blend shapes (fp64)
     {
@@ -359,6 +366,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.na, 1))) return rc;
     if ((rc = dev_alloc(ctx, &w.Phi, (size_t)w.ldA * kFeatPad))) return rc;
     if ((rc = dev_alloc(ctx, &w.PhiTc, (size_t)w.ldA * kFeatPad))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bboxp, (size_t)B * ((m.N + 63) / 64) * 12))) return rc;
     if ((rc = dev_alloc(ctx, &w.At, (size_t)kSkinFloats * w.ldA))) return rc;
     if ((rc = dev_alloc(ctx, &w.gchain, (size_t)B * kJoints * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.vposed, (size_t)B * m.N * 3))) return rc;

@@ -53,6 +53,7 @@ struct DevModel {
     int* ell_j = nullptr;
     float* ell_w = nullptr;
     float* Wd = nullptr;
+    float* ST = nullptr;      // [N][3][11] shapedirs row | template, fp32 (skinning kernel of the tensor-core path)
     int* faces = nullptr;
     // keypoints: k-th keypoint = sum_e kp_w[e] * v[kp_vidx[e]]  (+ posed chain joint kp_chain[k] if >= 0) + transl
     int K = 0, n_kp_entries = 0, nsup = 0;
@@ -109,12 +110,17 @@ struct Workspace {
     int* sdf_list_n = nullptr;        // [B][N] vertices with a non-zero penetration gradient (dense regime)
     float* sdf_list_d = nullptr;      // [B][N][3]
     int* sdf_list_count = nullptr;    // [B]
+    float* bboxp = nullptr;           // [B][ntiles][12] per-tile bbox partials written by the tensor-core vertex kernel
+    float* sdf_parts = nullptr;       // [B][P][5] partial sums of the SDF sampling kernel
+    float* sdf_scal = nullptr;        // [B][12] per frame: cg/scale, pen, dcentre(3), dscale, centre(3), scale ...
+    unsigned char* sdf_tileflag = nullptr;   // [B][ntiles] tile has a non-zero SDF gradient
+    unsigned char* sdf_box = nullptr;        // [B] FrameBox
 };
 
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
-    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_COUNT
+    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_SKIN, KID_COUNT
 };
 static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
 
@@ -186,12 +192,15 @@ bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
 int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
+int launch_sdf_parts(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
+int launch_vertex_bwd_sdf(mvs_ctx* ctx, int* nstrips_out, cudaStream_t st);                          // mvs_closure.cu
 // mvs_tc.cu: tcgen05 / TMA dense vertex forward
 int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
 int tc_check_error(mvs_ctx* ctx);
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st);
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstrips,
+                      cudaStream_t st);
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);
 }  // namespace mvs

@@ -203,9 +203,11 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         if (rc) return rc;
         while (na_host > 0 && rounds < max_rounds) {
             for (int r = 0; r < chunk; ++r) {
-                if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;
-                if ((rc = launch_sdf_frame(ctx, S.x_eval, S.sc, st))) return rc;
-                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, st))) return rc;
+                int nstrips = 0;
+                if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;        // tcgen05 GEMM + LBS + bbox partials
+                if ((rc = launch_sdf_parts(ctx, S.x_eval, S.sc, st))) return rc;   // samples, gradients, per-frame scalars
+                if ((rc = launch_vertex_bwd_sdf(ctx, &nstrips, st))) return rc;    // adjoint of the dense SDF gradient
+                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, nstrips, st))) return rc;
                 ++rounds;
             }
             // compaction changes slot -> frame, so the surviving frames' Phi / transforms are rebuilt for their new slots

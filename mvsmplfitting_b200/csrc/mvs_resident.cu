@@ -65,6 +65,8 @@ struct DenseIn {
     int n_extra;
     float pen_loss;
     const float* Wd;          // [N][24] dense skinning weights (adjoint of the extra vertices)
+    const float* part;        // [strip][ldA][512] partial adjoints of the dense SDF gradient (vertex_bwd), or NULL
+    int nstrips, ldA, slot;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -357,6 +359,25 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             }
             __syncthreads();
         }
+        if (din.part) {                   // dense SDF gradient: partial adjoints from the batched vertex kernel
+            for (int e = t; e < kPartFloats; e += kResThreads) {
+                // fixed summation order (strip 0,1,2,...) with 8 loads in flight: the strips are independent L2 reads
+                float a = 0.f;
+                const float* pp = din.part + (size_t)din.slot * kPartFloats + e;
+                const size_t stride = (size_t)din.ldA * kPartFloats;
+                int sidx = 0;
+                for (; sidx + 8 <= din.nstrips; sidx += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = pp[(size_t)(sidx + u) * stride];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a += v[u];
+                }
+                for (; sidx < din.nstrips; ++sidx) a += pp[(size_t)sidx * stride];
+                if (e < kSkinFloats) S.dA[e] += a; else S.dPhi[e - kSkinFloats] += a;
+            }
+            __syncthreads();
+        }
         if (din.n_extra > 0) {            // restore the support-list row map for the next evaluation
             for (int col = t; col < ncol; col += kResThreads) S.rowbase[col] = 3 * m.sup[col / 3] + col % 3;
         }
@@ -606,7 +627,8 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
                   const int* __restrict__ list_n, const float* __restrict__ list_d, const int* __restrict__ list_count,
                   const float* __restrict__ pen_loss, const float* __restrict__ Wd, float* __restrict__ Phi,
-                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA) {
+                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA, const float* __restrict__ part, int nstrips,
+                  const float* __restrict__ sdf_scal) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     const int slot = blockIdx.x;
@@ -646,6 +668,8 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     din.n_extra = list_count[slot];
     din.pen_loss = pen_loss[slot];
     din.Wd = Wd;
+    din.part = (part && sdf_scal[4 * slot] != 0.f) ? part : nullptr;      // frames without penetration have no partials
+    din.nstrips = nstrips; din.ldA = ldA; din.slot = slot;
     resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
@@ -792,7 +816,8 @@ bool hybrid_available(const mvs_ctx* ctx) {
     return resident_supported(ctx) && sdf_on;
 }
 
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st) {
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstrips,
+                      cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& dm = ctx->m;
     const LbfgsState& L = *static_cast<const LbfgsState*>(lbfgs_state);
@@ -806,7 +831,8 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
                frame_step_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, ctx->loss, cfg, L, params_dev,
                                                                  w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
                                                                  w.verts, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count, w.pen_loss,
-                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA));
+                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA, nstrips > 0 ? w.part : nullptr, nstrips,
+                                                                 w.sdf_scal));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -557,6 +557,243 @@ int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars
     return MVS_OK;
 }
 
+// ---------------------------------------------------------------------------------- dense regime, v3: P CTAs per frame
+// sdf_part_kernel: bounding box from the per-tile partials the tensor-core vertex kernel wrote, then trilinear
+// samples + coordinate gradients for this CTA's slice of the vertices, per-part sums and per-tile activity flags.
+// sdf_reduce_kernel: one warp per frame folds the parts into loss, d pen/d sample, the factor of the dense vertex
+// gradient, and the (<= 6) box-extreme vertices that carry the gradient through the box centre / scale.
+constexpr int kSdfPartThreads = 256;
+constexpr int kSdfTilesPerPart = 14;          // 448 vertices per CTA
+
+__global__ void __launch_bounds__(kSdfPartThreads)
+sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,
+                const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc, int N, int ntiles, int nbox,
+                const float* __restrict__ bboxp, const int* __restrict__ faces, int num_faces, int G,
+                float* __restrict__ gcoord, float* __restrict__ parts, int nparts, FrameBox* __restrict__ boxout,
+                unsigned char* __restrict__ tileflag) {
+    const int slot = blockIdx.y, part = blockIdx.x;
+    if (slot >= *na_ptr) return;
+    const int b = fidx[slot], t = threadIdx.x, lane = t & 31;
+    if (sc && sc[b].phase == PH_DONE) return;
+    const float* vf = verts + (size_t)slot * N * 3;
+    const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
+                         x[(size_t)b * kParams + kOffTransl + 2]};
+    __shared__ float s_f[6][kSdfPartThreads];
+    __shared__ int s_i[6][kSdfPartThreads];
+    __shared__ FrameBox s_box;
+    __shared__ float tri0[9];
+    __shared__ float cone[12];
+    {
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        int ilo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, ihi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        for (int tl = t; tl < nbox; tl += kSdfPartThreads) {
+            const float* bp = bboxp + ((size_t)slot * nbox + tl) * 12;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float l2 = bp[c], h2 = bp[3 + c];
+                const int il2 = __float_as_int(bp[6 + c]), ih2 = __float_as_int(bp[9 + c]);
+                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
+                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s_f[c][t] = lo[c]; s_f[3 + c][t] = hi[c]; s_i[c][t] = ilo[c]; s_i[3 + c][t] = ihi[c]; }
+        __syncthreads();
+        for (int o = kSdfPartThreads / 2; o > 0; o >>= 1) {
+            if (t < o) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float l2 = s_f[c][t + o]; const int il2 = s_i[c][t + o];
+                    if (l2 < s_f[c][t] || (l2 == s_f[c][t] && il2 < s_i[c][t])) { s_f[c][t] = l2; s_i[c][t] = il2; }
+                    const float h2 = s_f[3 + c][t + o]; const int ih2 = s_i[3 + c][t + o];
+                    if (h2 > s_f[3 + c][t] || (h2 == s_f[3 + c][t] && ih2 < s_i[3 + c][t])) { s_f[3 + c][t] = h2; s_i[3 + c][t] = ih2; }
+                }
+            }
+            __syncthreads();
+        }
+        if (t == 0) {
+            FrameBox fb;
+            float ext = -1.f;
+            fb.cmax = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
+                // arg-indices commute with the translation (body_models_scale.py:403)
+                const float lc = s_f[c][0] + tr[c], hc = s_f[3 + c][0] + tr[c];
+                fb.centre[c] = (lc + hc) / 2.f;
+                fb.ilo[c] = s_i[c][0]; fb.ihi[c] = s_i[3 + c][0];
+                const float e = hc - lc;
+                if (e > ext) { ext = e; fb.cmax = c; }
+            }
+            fb.scale = 0.6f * ext;
+            fb.pad = 0.f;
+            s_box = fb;
+            if (part == 0) boxout[slot] = fb;
+        }
+        __syncthreads();
+    }
+    const FrameBox fb = s_box;
+    if (t < 9) tri0[t] = ((vf[3 * faces[t / 3] + t % 3] + tr[t % 3]) - fb.centre[t % 3]) / fb.scale;
+    __syncthreads();
+    if (t < 3) {
+        const float* a = &tri0[3 * t];
+        const float* bb = &tri0[3 * ((t + 1) % 3)];
+        const float ea[3] = {a[0] + 1.f, a[1] + 1.f, a[2] + 1.f}, eb[3] = {bb[0] + 1.f, bb[1] + 1.f, bb[2] + 1.f};
+        const float nx = ea[1] * eb[2] - ea[2] * eb[1], ny = ea[2] * eb[0] - ea[0] * eb[2], nz = ea[0] * eb[1] - ea[1] * eb[0];
+        cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
+    }
+    __syncthreads();
+    const bool cull = (num_faces == 1);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float* gof = gcoord + (size_t)slot * N * 3;
+    const int n_begin = part * kSdfTilesPerPart * kTileV;
+    const int n_end = min(N, n_begin + kSdfTilesPerPart * kTileV);
+    for (int n0 = n_begin; n0 < n_end; n0 += kSdfPartThreads) {        // a warp covers one 32-vertex tile per pass
+        const int n = n0 + t;
+        bool nz = false;
+        if (n < n_end) {
+            float loc[3], w1[3];
+            int i0[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                loc[c] = ((vf[3 * n + c] + tr[c]) - fb.centre[c]) / fb.scale;
+                const float ix = ((loc[c] + 1.f) * G - 1.f) / 2.f;
+                const float fl = floorf(ix);
+                i0[c] = (int)fl;
+                w1[c] = ix - fl;
+            }
+            float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int corner = 0; corner < 8; ++corner) {
+                const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
+                const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
+                if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+                if (cull) {
+                    float cc[3];
+                    voxel_centre(ii, jj, kk, G, cc);
+                    const float wv[3] = {cc[0] + 1.f, cc[1] + 1.f, cc[2] + 1.f};
+                    const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) * 1e-4f;
+                    const float s1 = wv[0] * cone[0] + wv[1] * cone[1] + wv[2] * cone[2];
+                    const float s2 = wv[0] * cone[4] + wv[1] * cone[5] + wv[2] * cone[6];
+                    const float s3 = wv[0] * cone[8] + wv[1] * cone[9] + wv[2] * cone[10];
+                    const float m1 = wn * cone[3], m2 = wn * cone[7], m3 = wn * cone[11];
+                    const bool neg = (s1 < -m1) || (s2 < -m2) || (s3 < -m3);
+                    const bool pos = (s1 > m1) || (s2 > m2) || (s3 > m3);
+                    if (neg && pos) continue;
+                }
+                const float p = voxel_phi_frame(ii, jj, kk, G, num_faces, faces, vf, tr, fb, tri0);
+                if (p == 0.f) continue;
+                const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
+                val += p * wx * wy * wz;
+                dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
+                dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
+                dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
+            }
+            float gdl = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float gcv = dix[c] * (0.5f * G);
+                gof[3 * n + c] = gcv; acc[1 + c] += gcv; gdl += gcv * loc[c];
+                nz = nz || (gcv != 0.f);
+            }
+            acc[0] += val;
+            acc[4] += gdl;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, nz);
+        const int tile = (n0 + (t & ~31)) / kTileV;
+        if (lane == 0 && tile < ntiles && n0 + (t & ~31) < n_end) tileflag[(size_t)slot * ntiles + tile] = any ? 1 : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) s_f[q][t] = acc[q];
+    __syncthreads();
+    for (int o = kSdfPartThreads / 2; o > 0; o >>= 1) {
+        if (t < o) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) s_f[q][t] += s_f[q][t + o];
+        }
+        __syncthreads();
+    }
+    if (t < 5) parts[((size_t)slot * nparts + part) * 5 + t] = s_f[t][0];
+}
+
+// scal[slot] = {cg / scale (factor of the dense vertex gradient), pen loss, ...}; box-extreme list (<= 6 entries)
+__global__ void __launch_bounds__(32)
+sdf_reduce_kernel(const int* __restrict__ fidx, const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc,
+                  const float* __restrict__ parts, int nparts, const FrameBox* __restrict__ box, float coll_w, int N,
+                  float* __restrict__ scal, float* __restrict__ pen_loss, int* __restrict__ list_n,
+                  float* __restrict__ list_d, int* __restrict__ list_count) {
+    const int slot = blockIdx.x;
+    if (slot >= *na_ptr) return;
+    const int b = fidx[slot], lane = threadIdx.x;
+    if (sc && sc[b].phase == PH_DONE) return;
+    float tot[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        float a = 0.f;
+        for (int p = lane; p < nparts; p += 32) a += parts[((size_t)slot * nparts + p) * 5 + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        tot[q] = a;
+    }
+    if (lane != 0) return;
+    const FrameBox fb = box[slot];
+    const float wsum = coll_w * tot[0];
+    const float cg = 2.f * wsum * coll_w;
+    const float inv_s = 1.f / fb.scale;
+    pen_loss[slot] = wsum * wsum;
+    scal[(size_t)slot * 4] = cg * inv_s;
+    int cnt = 0;
+    if (cg != 0.f) {
+        const float dscale = -cg * tot[4] * inv_s;
+        int* ln = list_n + (size_t)slot * N;
+        float* ld = list_d + (size_t)slot * N * 3;
+        for (int c = 0; c < 3; ++c) {
+            const float dcentre = -cg * tot[1 + c] * inv_s;
+            float dl = 0.5f * dcentre, dh = 0.5f * dcentre;
+            if (c == fb.cmax) { dh += 0.6f * dscale; dl -= 0.6f * dscale; }
+            if (dl != 0.f) { ln[cnt] = fb.ilo[c]; ld[3 * cnt] = 0.f; ld[3 * cnt + 1] = 0.f; ld[3 * cnt + 2] = 0.f; ld[3 * cnt + c] = dl; ++cnt; }
+            if (dh != 0.f) { ln[cnt] = fb.ihi[c]; ld[3 * cnt] = 0.f; ld[3 * cnt + 1] = 0.f; ld[3 * cnt + 2] = 0.f; ld[3 * cnt + c] = dh; ++cnt; }
+        }
+    }
+    list_count[slot] = cnt;
+}
+
+int launch_sdf_parts(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
+    Workspace& w = ctx->ws;
+    const DevModel& m = ctx->m;
+    const LossParams& lp = ctx->loss;
+    const int B = w.B, N = m.N;
+    const int ntiles = (N + kTileV - 1) / kTileV;
+    const int nparts = (ntiles + kSdfTilesPerPart - 1) / kSdfTilesPerPart;
+    int rc;
+    if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
+    if (!w.sdf_list_n) {
+        if ((rc = dev_alloc(ctx, &w.sdf_list_n, (size_t)B * N))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_list_d, (size_t)B * N * 3))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_list_count, (size_t)B))) return rc;
+    }
+    if (!w.sdf_parts) {
+        if ((rc = dev_alloc(ctx, &w.sdf_parts, (size_t)B * nparts * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_scal, (size_t)B * 4))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_tileflag, (size_t)B * ntiles))) return rc;
+        unsigned char* raw = nullptr;
+        if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
+        w.sdf_box = raw;
+    }
+    const FrameScalars* sc = static_cast<const FrameScalars*>(frame_scalars);
+    dim3 g(nparts, B);
+    MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
+               sdf_part_kernel<<<g, kSdfPartThreads, 0, st>>>(w.verts, x_dev, w.fidx, w.na, sc, N, ntiles, (N + 63) / 64, w.bboxp, m.faces,
+                                                              lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, w.sdf_gcoord, w.sdf_parts,
+                                                              nparts, reinterpret_cast<FrameBox*>(w.sdf_box), w.sdf_tileflag));
+    MVS_LAUNCH(ctx, KID_SDF_FINALIZE, st,
+               sdf_reduce_kernel<<<B, 32, 0, st>>>(w.fidx, w.na, sc, w.sdf_parts, nparts,
+                                                   reinterpret_cast<const FrameBox*>(w.sdf_box), lp.coll_loss_weight, N,
+                                                   w.sdf_scal, w.pen_loss, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
 int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;

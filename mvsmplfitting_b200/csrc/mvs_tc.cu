@@ -103,11 +103,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const float* __restrict__ Qk, const float* __restrict__ Phi, const float* __restrict__ At, int ldA,
-                     const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW, int N,
-                     const int* __restrict__ na_ptr, int tiles_per_cta, int ntiles, float* __restrict__ vposed,
-                     float* __restrict__ verts, int* __restrict__ err_flag) {
+posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
+                        const int* __restrict__ na_ptr, int tiles_per_cta, int ntiles, float* __restrict__ poffT,
+                        int* __restrict__ err_flag) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = base;                                        // 7 x [128 rows][128 B], 1024-aligned
@@ -187,14 +185,11 @@ vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue: lane = frame row of the M tile
+        // ---------------- epilogue: lane = frame row of the M tile; pose offsets go out TRANSPOSED
+        //                  poffT[column][slot] so that a warp's 32 frames form one 128-byte store
         const int row = 32 * (warp & 3) + lane;
         const int slot = m0 + row;
         const bool live = slot < na;
-        const int slotc = live ? slot : na - 1;
-        float beta[kBetas];
-#pragma unroll
-        for (int l = 0; l < kBetas; ++l) beta[l] = Phi[(size_t)slotc * kFeatPad + kPoseBasis + l];
         int buf = 0; uint32_t tphase[2] = {0, 0};
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             if (!mbar_wait(&t_full[buf], tphase[buf], err_flag)) return;
@@ -209,54 +204,11 @@ vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&t_empty[buf]);                              // accumulator copied out: the MMA warp may reuse it
             buf ^= 1;
-            const int v0 = tile * kTileV;
-            float ovp[12], ov[12];
+            if (live) {
+                const int c0 = tile * kTcBN;
 #pragma unroll
-            for (int i = 0; i < kTileV; ++i) {
-                const int n = v0 + i;
-                if (n >= N) break;
-                float vp[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float* qrow = Qk + (size_t)(3 * n + c) * kFeatPad + kPoseBasis;    // shapedirs | template (fp32)
-                    float a = qrow[kBetas];
-#pragma unroll
-                    for (int l = 0; l < kBetas; ++l) a = fmaf(qrow[l], beta[l], a);
-                    vp[c] = a + __uint_as_float(acc[3 * i + c]);
-                }
-                float T[12];
-#pragma unroll
-                for (int c = 0; c < 12; ++c) T[c] = 0.f;
-                for (int e = 0; e < KW; ++e) {
-                    const float w = ell_w[(size_t)n * KW + e];
-                    if (w != 0.f) {
-                        const int j = ell_j[(size_t)n * KW + e];
-#pragma unroll
-                        for (int c = 0; c < 12; ++c) T[c] = fmaf(w, At[(size_t)(j * 12 + c) * ldA + slotc], T[c]);
-                    }
-                }
-                const int o = 3 * (i & 3);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    ovp[o + r] = vp[r];
-                    ov[o + r] = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
-                }
-                if ((i & 3) == 3 && live) {            // 4 vertices = 48 B per array; rows are 8-byte (not 16-byte) aligned
-                    const size_t off = ((size_t)slot * N + (n - 3)) * 3;
-                    float2* dvp = reinterpret_cast<float2*>(vposed + off);
-                    float2* dv = reinterpret_cast<float2*>(verts + off);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        dvp[q] = make_float2(ovp[2 * q], ovp[2 * q + 1]);
-                        dv[q] = make_float2(ov[2 * q], ov[2 * q + 1]);
-                    }
-                } else if (live && n == N - 1) {       // ragged tail (N not a multiple of 4)
-                    for (int q = 0; q <= (i & 3); ++q)
-                        for (int r = 0; r < 3; ++r) {
-                            vposed[((size_t)slot * N + (n - (i & 3) + q)) * 3 + r] = ovp[3 * q + r];
-                            verts[((size_t)slot * N + (n - (i & 3) + q)) * 3 + r] = ov[3 * q + r];
-                        }
-                }
+                for (int c = 0; c < kTcBN; ++c)
+                    if (c0 + c < ncols) poffT[(size_t)(c0 + c) * ldA + slot] = __uint_as_float(acc[c]);
             }
         }
     }
@@ -265,10 +217,115 @@ vertex_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
 }
 
+// ------------------------------------------------------------------------------------------------ skinning
+// v_posed = v_template + shapedirs.betas (fp32) + pose offsets (tensor cores), then linear blend skinning
+// (lbs.py:179,203,207-220).  CTA = 32 frames x 64 vertices; lane = frame.  The 32 frames' skinning transforms
+// (288 floats each) sit in shared memory frame-fastest, so the 48 reads per (frame, vertex) are conflict-free LDS
+// instead of global loads; outputs are transposed through shared memory into coalesced row stores.  Also emits the
+// per-chunk bounding-box partial of every frame for the SDF kernels.
+constexpr int kSkinV = 64;
+constexpr int kSkinThreads = 256;
+constexpr int kSkinOutLd = 3 * kSkinV + 1;     // 193
+constexpr size_t kSkinSmem = (size_t)(kSkinFloats * 32 + kBetas * 32 + 2 * 32 * kSkinOutLd + 8 * 32 * 6 * 2) * sizeof(float);
+
+__global__ void __launch_bounds__(kSkinThreads)
+skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const float* __restrict__ Phi,
+            const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW,
+            int N, const int* __restrict__ na_ptr, float* __restrict__ vposed, float* __restrict__ verts,
+            float* __restrict__ bboxp) {
+    extern __shared__ __align__(16) float sk[];
+    float* As = sk;                                   // [288][32]
+    float* Bs = As + kSkinFloats * 32;                // [10][32]
+    float* Ovp = Bs + kBetas * 32;                    // [32][193]
+    float* Ov = Ovp + 32 * kSkinOutLd;                // [32][193]
+    float* Bb = Ov + 32 * kSkinOutLd;                 // [8 warps][32 lanes][6] values, then [..][6] indices
+    const int na = *na_ptr;
+    const int f0 = blockIdx.y * 32;
+    if (f0 >= na) return;
+    const int v0 = blockIdx.x * kSkinV;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slotc = min(f0 + lane, na - 1);
+    for (int e = tid; e < kSkinFloats * 32; e += kSkinThreads) As[e] = At[(size_t)(e >> 5) * ldA + min(f0 + (e & 31), na - 1)];
+    for (int e = tid; e < kBetas * 32; e += kSkinThreads)
+        Bs[e] = Phi[(size_t)min(f0 + (e & 31), na - 1) * kFeatPad + kPoseBasis + (e >> 5)];
+    __syncthreads();
+    float beta[kBetas];
+#pragma unroll
+    for (int l = 0; l < kBetas; ++l) beta[l] = Bs[l * 32 + lane];
+    float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+    int bilo[3] = {0, 0, 0}, bihi[3] = {0, 0, 0};
+    for (int i = 0; i < kSkinV / 8; ++i) {
+        const int li = warp * (kSkinV / 8) + i;
+        const int n = v0 + li;
+        if (n >= N) break;
+        const float* st = ST + (size_t)n * 33;                       // [3][11]: shapedirs row | template
+        float vp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = st[11 * c + kBetas];
+#pragma unroll
+            for (int l = 0; l < kBetas; ++l) a = fmaf(st[11 * c + l], beta[l], a);
+            vp[c] = a + poffT[(size_t)(3 * n + c) * ldA + slotc];
+        }
+        float T[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) T[c] = 0.f;
+        for (int e = 0; e < KW; ++e) {
+            const float w = ell_w[(size_t)n * KW + e];
+            if (w != 0.f) {
+                const float* Aj = As + (size_t)ell_j[(size_t)n * KW + e] * 12 * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) T[c] = fmaf(w, Aj[c * 32], T[c]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float vv = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
+            Ovp[lane * kSkinOutLd + 3 * li + r] = vp[r];
+            Ov[lane * kSkinOutLd + 3 * li + r] = vv;
+            if (vv < blo[r]) { blo[r] = vv; bilo[r] = n; }       // strict: ties keep the lowest vertex index
+            if (vv > bhi[r]) { bhi[r] = vv; bihi[r] = n; }
+        }
+    }
+    int* Bi = reinterpret_cast<int*>(Bb + 8 * 32 * 6);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Bb[(warp * 32 + lane) * 6 + r] = blo[r]; Bb[(warp * 32 + lane) * 6 + 3 + r] = bhi[r];
+        Bi[(warp * 32 + lane) * 6 + r] = bilo[r]; Bi[(warp * 32 + lane) * 6 + 3 + r] = bihi[r];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 3 * kSkinV; idx += kSkinThreads) {
+        const int fl = idx / (3 * kSkinV), col = idx % (3 * kSkinV);
+        const int slot = f0 + fl, n = v0 + col / 3;
+        if (slot < na && n < N) {
+            const size_t off = ((size_t)slot * N + v0) * 3 + col;
+            vposed[off] = Ovp[fl * kSkinOutLd + col];
+            verts[off] = Ov[fl * kSkinOutLd + col];
+        }
+    }
+    if (bboxp && warp == 0 && f0 + lane < na) {       // fold the 8 warps' vertex groups (ascending vertex index)
+        float lo[3], hi[3];
+        int ilo[3], ihi[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { lo[r] = Bb[lane * 6 + r]; hi[r] = Bb[lane * 6 + 3 + r]; ilo[r] = Bi[lane * 6 + r]; ihi[r] = Bi[lane * 6 + 3 + r]; }
+        for (int w2 = 1; w2 < 8; ++w2)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float l2 = Bb[(w2 * 32 + lane) * 6 + r], h2 = Bb[(w2 * 32 + lane) * 6 + 3 + r];
+                if (l2 < lo[r]) { lo[r] = l2; ilo[r] = Bi[(w2 * 32 + lane) * 6 + r]; }
+                if (h2 > hi[r]) { hi[r] = h2; ihi[r] = Bi[(w2 * 32 + lane) * 6 + 3 + r]; }
+            }
+        float* bp = bboxp + ((size_t)(f0 + lane) * gridDim.x + blockIdx.x) * 12;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { bp[r] = lo[r]; bp[3 + r] = hi[r]; bp[6 + r] = __int_as_float(ilo[r]); bp[9 + r] = __int_as_float(ihi[r]); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     CUtensorMap map_a, map_b;
     float* Qtc = nullptr;       // [3N][224] TF32-rounded posedirs rows (columns >= 207 zero)
+    float* poffT = nullptr;     // [3N][ldA] pose offsets, frame fastest (output of the tensor-core contraction)
     int* err = nullptr;
     bool ready = false;
 };
@@ -329,7 +386,9 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
         int rc;
         if ((rc = encode_map(ctx, &T->map_a, w.PhiTc, (uint64_t)w.ldA, kTcBM))) return rc;
         if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)3 * m.N, kTcBN))) return rc;
-        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        if ((rc = dev_alloc(ctx, &T->poffT, (size_t)3 * m.N * w.ldA))) return rc;
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(posedirs_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmem));
         T->ready = true;
     }
     const int ntiles = (m.N + kTileV - 1) / kTileV;
@@ -339,9 +398,12 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
     const int tiles_per_cta = (ntiles + ctas_n - 1) / ctas_n;
     dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, mtiles);
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
-               vertex_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, m.Qk, w.Phi, w.At, w.ldA, m.ell_j,
-                                                                       m.ell_w, m.KW, m.N, w.na, tiles_per_cta, ntiles,
-                                                                       w.vposed, w.verts, T->err));
+               posedirs_gemm_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, w.ldA, 3 * m.N, w.na, tiles_per_cta,
+                                                                          ntiles, T->poffT, T->err));
+    dim3 g2((m.N + kSkinV - 1) / kSkinV, (w.B + 31) / 32);
+    MVS_LAUNCH(ctx, KID_SKIN, st,
+               skin_kernel<<<g2, kSkinThreads, kSkinSmem, st>>>(T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N,
+                                                                w.na, w.vposed, w.verts, w.bboxp));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

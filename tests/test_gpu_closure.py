@@ -55,7 +55,7 @@ def test_closure_matches_reference_fixtures(name, dense, syn_model, syn_gmm):
     check_against(c, "f64", out, dense)
     # forward-only call gives the same loss
     out2 = ctx.closure(x, want_grad=False)
-    assert G.relmax(out2["loss"].cpu().numpy(), out["loss"].cpu().numpy().astype(np.float64)) < 1e-6
+    assert G.relmax(out2["loss"].cpu().numpy(), out["loss"].cpu().numpy().astype(np.float64)) < 1e-5   # sparse fp32 path vs dense TF32 path
     ctx.close()
 
 

@@ -41,7 +41,7 @@ def test_tensor_core_vertex_forward_matches_fp32_kernel(B, syn_model, syn_gmm):
             ctx.profile(0xFFFFFFFF)
             ctx.closure(x, want_verts=True)
             prof_names = set(ctx.profile_read())
-            assert "vertex_fwd_tc" in prof_names and "vertex_fwd" not in prof_names
+            assert "posedirs_gemm_tc" in prof_names and "skin" in prof_names and "vertex_fwd" not in prof_names
         outs.append({k: v.cpu().numpy().astype(np.float64) for k, v in o.items()})
         ctx.close()
     a, b = outs

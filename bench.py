@@ -230,8 +230,20 @@ def run_ours(args):
                 "frac": (ach / hbm_peak) if ach else None, "traffic": None,
                 "algorithmic_bytes_per_launch": alg, "launches": dom_n, "avg_launch_us": (dom_ms * 1e3 / dom_n) if dom_n else None,
                 "avg_active_frames_per_launch": na_avg, "peak_source": peak_src,
+                "note": "the path is latency / L2 bound, not HBM bound: constants (20 MB) live in the 126 MB L2 and one "
+                        "launch moves a few MB; see DESIGN.md section 5",
                 "kernel_time_share_of_step": {k: round(v[0] / max(sum(x_[0] for x_ in share.values()), 1e-9), 4)
                                               for k, v in share.items()}}
+        # the tensor-core contraction, from the fully instrumented warm-up step (events around every launch)
+        if "posedirs_gemm_tc" in share and share["posedirs_gemm_tc"][1] > 0:
+            g_ms, g_n = share["posedirs_gemm_tc"]
+            tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+            g_ach = gemm_flops(na_avg) * g_n / (g_ms * 1e-3) / 1e12
+            roof["posedirs_gemm"] = {"bound": "tensor", "achieved": g_ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                                     "frac": g_ach / tf32_peak, "avg_launch_us": g_ms * 1e3 / g_n,
+                                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 as the TF32 proxy",
+                                     "note": "M = frames in flight (skinny GEMM): bound by streaming posedirs once per "
+                                             "128-frame tile, not by tensor throughput"}
         cpu = cpu_baseline_sample(V, bool(args.sdf), max_seconds=args.cpu_seconds) if world == 1 or True else None
         sec = ms_res * 1e-3
         out = {
@@ -265,16 +277,24 @@ def algorithmic_bytes(kernel: str, na: float, V: int, dense: bool) -> float:
     w_bytes = nv * 4 * 8                            # skinning weights (4 (joint, weight) pairs)
     if kernel == "vertex_fwd":
         return q_bytes + w_bytes + na * (218 * 4 + 288 * 4 + 2 * nv * 12)
+    if kernel == "posedirs_gemm_tc":                # posedirs once, pose features in, pose offsets out
+        return 3 * N * 207 * 4 + na * (207 * 4 + 3 * N * 4)
+    if kernel == "skin":                            # offsets in, template/shapedirs/weights once, v_posed + verts out
+        return N * 33 * 4 + N * 32 + na * (3 * N * 4 + 288 * 4 + 40 + 2 * N * 12)
     if kernel == "vertex_bwd":
-        nvb = N if dense else 86
-        return 3 * nvb * 218 * 4 + nvb * 24 * 4 + na * (288 * 4 + 2 * nvb * 12 + 512 * 4)
-    if kernel == "sdf_sample":
+        return 3 * N * 218 * 4 + N * 24 * 4 + na * (1152 + 2 * N * 12 + 2048)
+    if kernel in ("sdf_sample", "sdf_finalize", "sdf_frame"):
         return na * (N * 12 + N * 12)
-    if kernel == "sdf_finalize":
-        return na * (N * 12 + N * 12)
-    if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance"):
-        return na * (344 * 3 + 204 * V + 512 * 4)
+    if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance", "frame_step"):
+        return na * (344 * 3 + 204 * V + 2048 + 86 * 24)
+    if kernel == "lbfgs_resident":                  # per frame and evaluation: two passes over its 86-vertex Qk slice
+        return na * (2 * 3 * 86 * 218 * 4 + 344 * 3 + 204 * V)
     return na * 344
+
+
+def gemm_flops(na: float) -> float:
+    """algorithmic flops of one posedirs contraction launch: [na x 207] x [207 x 20670]"""
+    return 2.0 * na * 207 * 20670
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)

@@ -327,7 +327,7 @@ constexpr int kDvpLd = kTileF + 4;       // 68 (16-byte aligned rows)
 constexpr int kBwdCols = 16;             // columns of Qk staged per step
 constexpr int kQbLd = kFeatPad + 4;      // 228
 constexpr size_t kVertBwdSmem =
-    (size_t)(2 * kTileC * kDvLd + kTileC * kDvpLd + kTileV * kJoints + kBwdCols * kQbLd) * sizeof(float);
+    (size_t)(2 * kTileC * kDvLd + kTileC * kDvpLd + kTileV * kJoints + kBwdCols * kQbLd + kSkinFloats * kTileF) * sizeof(float);
 
 __global__ void __launch_bounds__(kVertThreads, 1)
 vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, int ldA,
@@ -343,6 +343,7 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
     float* dVp = VP + kTileC * kDvLd;          // [96][68]   d loss / d v_posed
     float* Ws = dVp + kTileC * kDvpLd;         // [32][24]
     float* Qs = Ws + kTileV * kJoints;         // [16][228]
+    float* Ats = Qs + kBwdCols * kQbLd;        // [288][64] this CTA's skinning transforms, frame fastest
     __shared__ int s_n[kTileV], s_pos[kTileV];
     const int na = *na_ptr;
     const int f0 = blockIdx.y * kTileF;
@@ -350,7 +351,8 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
     const int strip = blockIdx.x;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int b = tid & 63, jg = tid >> 6;
-    const int slotc = min(f0 + b, na - 1);
+    for (int e = tid; e < kSkinFloats * kTileF; e += kVertThreads)
+        Ats[e] = At[(size_t)(e >> 6) * ldA + min(f0 + (e & 63), na - 1)];
 
     float accP[4][14];
     float accA[6][12];
@@ -420,7 +422,7 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
                         for (int r = 0; r < 3; ++r)
 #pragma unroll
                             for (int c = 0; c < 3; ++c)
-                                G[3 * r + c] = fmaf(w, At[(size_t)(j * 12 + 4 * r + c) * ldA + slotc], G[3 * r + c]);
+                                G[3 * r + c] = fmaf(w, Ats[(j * 12 + 4 * r + c) * kTileF + b], G[3 * r + c]);
                     }
                 }
                 o0 = G[0] * d0 + G[3] * d1 + G[6] * d2;
@@ -454,17 +456,33 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
                 }
             }
         }
-        // d Phi[b][k] += sum_col dVp[b][col] * Qk[col][k]
+        // d Phi[b][k] += sum_col dVp[b][col] * Qk[col][k]; the next 16 Qk rows are fetched into registers while
+        // the current ones are consumed from shared memory
+        constexpr int kQv = (kBwdCols * (kFeatPad / 4) + kVertThreads - 1) / kVertThreads;      // float4 per thread (4)
+        float4 qreg[kQv];
+        auto fetch = [&](int c0) {
+#pragma unroll
+            for (int u = 0; u < kQv; ++u) {
+                const int idx = tid + u * kVertThreads;
+                qreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < kBwdCols * (kFeatPad / 4)) {
+                    const int r = idx / (kFeatPad / 4), q4 = idx % (kFeatPad / 4);
+                    const int col = c0 + r, n = s_n[col / 3];
+                    if (n >= 0) qreg[u] = __ldg(reinterpret_cast<const float4*>(Qk + (size_t)(3 * n + col % 3) * kFeatPad + 4 * q4));
+                }
+            }
+        };
+        fetch(0);
         for (int c0 = 0; c0 < kTileC; c0 += kBwdCols) {
             __syncthreads();
-            for (int idx = tid; idx < kBwdCols * (kFeatPad / 4); idx += kVertThreads) {
-                const int r = idx / (kFeatPad / 4), q4 = idx % (kFeatPad / 4);
-                const int col = c0 + r, n = s_n[col / 3];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n >= 0) v = __ldg(reinterpret_cast<const float4*>(Qk + (size_t)(3 * n + col % 3) * kFeatPad + 4 * q4));
-                *reinterpret_cast<float4*>(&Qs[r * kQbLd + 4 * q4]) = v;
+#pragma unroll
+            for (int u = 0; u < kQv; ++u) {
+                const int idx = tid + u * kVertThreads;
+                if (idx < kBwdCols * (kFeatPad / 4))
+                    *reinterpret_cast<float4*>(&Qs[(idx / (kFeatPad / 4)) * kQbLd + 4 * (idx % (kFeatPad / 4))]) = qreg[u];
             }
             __syncthreads();
+            if (c0 + kBwdCols < kTileC) fetch(c0 + kBwdCols);
 #pragma unroll 4
             for (int r = 0; r < kBwdCols; ++r) {
                 const float4 d = *reinterpret_cast<const float4*>(&dVp[(c0 + r) * kDvpLd + 4 * ty]);

@@ -563,7 +563,7 @@ int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars
 // sdf_reduce_kernel: one warp per frame folds the parts into loss, d pen/d sample, the factor of the dense vertex
 // gradient, and the (<= 6) box-extreme vertices that carry the gradient through the box centre / scale.
 constexpr int kSdfPartThreads = 256;
-constexpr int kSdfTilesPerPart = 14;          // 448 vertices per CTA
+constexpr int kSdfTilesPerPart = 7;           // 224 vertices per CTA (one pass of 256 threads)
 
 __global__ void __launch_bounds__(kSdfPartThreads)
 sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,

@@ -135,6 +135,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step_resident():
+        nonlocal stages
         x.copy_(x0_dev)
         tot = dict(frame_iterations=0, frame_evals=0, rounds=0, frames_nan=0)
         per_stage = []
@@ -200,6 +201,17 @@ def run_ours(args):
     ms_res, stats_res, launches, prof, wall = timed(lambda: step_resident(), args.steps, max(args.warmup - 1, 0), dom_mask)
     ms_e2e, stats_e2e, _, _, _ = timed(step_host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else {}
+    # auxiliary (not the headline): the same fit with the SDF term off = the reference's shipped default
+    # (cfg_files/fit_smpl.yaml: interpenetration false) -> every stage runs frame-resident (regime A)
+    aux = None
+    if args.sdf:
+        stages_main = stages
+        stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=False, **st) for st in stage_table()]
+        ms_a, stats_a, launches_a, _, _ = timed(lambda: step_resident(), 2, 1)
+        it_a = sum(s_[0]["frame_iterations"] for s_ in stats_a)
+        aux = {"workload": "same frames, SDF term off (all four stages frame-resident)", "ms_per_step": ms_a / 2,
+               "frame_iterations_per_s_per_gpu": it_a / (ms_a * 1e-3), "gpu_launches_per_step": launches_a / 2}
+        stages = stages_main
 
     it = sum(s[0]["frame_iterations"] for s in stats_res)
     ev = sum(s[0]["frame_evals"] for s in stats_res)
@@ -259,7 +271,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(X0.nbytes + B * 4), "ms_per_step": ms_e2e / args.steps,
                     "api": "mvs_fit_host (C ABI, host buffers)"},
             "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "wall_s_timed_region": wall,
+            "wall_s_timed_region": wall, "aux_no_sdf": aux,
         }
         print(json.dumps(out))
     if world > 1:

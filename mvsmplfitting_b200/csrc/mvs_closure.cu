@@ -336,7 +336,8 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
                   int nvb, int nv_fwd, const float* __restrict__ vposed, const float* __restrict__ dv,
                   const int* __restrict__ na_ptr, int tiles_per_strip, int ntiles, float* __restrict__ part,
                   const float* __restrict__ slot_scale /* [slot][4]: dv is multiplied by slot_scale[4*slot], or NULL */,
-                  const unsigned char* __restrict__ tileflag /* [slot][ntiles] or NULL */) {
+                  const unsigned char* __restrict__ tileflag /* [slot][ntiles] or NULL */,
+                  int* __restrict__ strip_active /* [strip][gridDim.y] or NULL: 1 iff this CTA wrote partials */) {
     extern __shared__ __align__(16) float smem[];
     float* DV = smem;                          // [96][65]   upstream d loss / d vertex, column-major
     float* VP = DV + kTileC * kDvLd;           // [96][65]   v_posed
@@ -351,8 +352,7 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
     const int strip = blockIdx.x;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int b = tid & 63, jg = tid >> 6;
-    for (int e = tid; e < kSkinFloats * kTileF; e += kVertThreads)
-        Ats[e] = At[(size_t)(e >> 6) * ldA + min(f0 + (e & 63), na - 1)];
+    bool ats_loaded = false;            // the 73 KB of transforms are fetched when the first active tile shows up
 
     float accP[4][14];
     float accA[6][12];
@@ -403,6 +403,12 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
             Ws[idx] = n >= 0 ? Wd[(size_t)n * kJoints + idx % kJoints] : 0.f;
         }
         if (!__syncthreads_or(any)) continue;          // no upstream gradient anywhere in this tile
+        if (!ats_loaded) {
+            for (int e = tid; e < kSkinFloats * kTileF; e += kVertThreads)
+                Ats[e] = At[(size_t)(e >> 6) * ldA + min(f0 + (e & 63), na - 1)];
+            ats_loaded = true;
+            __syncthreads();
+        }
 
         // d v_posed = T_3x3^T d v     (lane = frame)
         for (int ii = 0; ii < 8; ++ii) {
@@ -497,7 +503,11 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
             }
         }
     }
-    // per-strip partials: [strip][slot][288 skin | 224 feature]
+    // per-strip partials: [strip][slot][288 skin | 224 feature]; a CTA that met no active tile only says so
+    if (strip_active) {
+        if (tid == 0) strip_active[strip * gridDim.y + blockIdx.y] = ats_loaded ? 1 : 0;
+        if (!ats_loaded) return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int slot = f0 + 4 * ty + i;
@@ -802,7 +812,7 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         MVS_LAUNCH(ctx, KID_VERTEX_BWD, st,
                    vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd,
                                                                              blist_n, blist_pos, nvb, nv, w.vposed, w.dv,
-                                                                             w.na, tps, ntiles, w.part, nullptr, nullptr));
+                                                                             w.na, tps, ntiles, w.part, nullptr, nullptr, nullptr));
     }
     PriorModel pm{m.M, m.gmm_means, m.gmm_prec, m.gmm_lognllw};
     MVS_LAUNCH(ctx, KID_FRAME_BWD, st,
@@ -846,11 +856,15 @@ int launch_vertex_bwd_sdf(mvs_ctx* ctx, int* nstrips_out, cudaStream_t st) {
     const int tps = (ntiles + want - 1) / want;
     const int nstrips = (ntiles + tps - 1) / tps;
     *nstrips_out = nstrips;
+    if (!w.strip_active) {
+        int rc = dev_alloc(ctx, &w.strip_active, (size_t)w.nstrips_max * ftiles);
+        if (rc) return rc;
+    }
     dim3 g4(nstrips, ftiles);
     MVS_LAUNCH(ctx, KID_VERTEX_BWD, st,
                vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd, nullptr,
                                                                          nullptr, m.N, m.N, w.vposed, w.sdf_gcoord, w.na, tps,
-                                                                         ntiles, w.part, w.sdf_scal, w.sdf_tileflag));
+                                                                         ntiles, w.part, w.sdf_scal, w.sdf_tileflag, w.strip_active));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

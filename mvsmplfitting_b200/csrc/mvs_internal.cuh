@@ -91,6 +91,7 @@ struct Workspace {
     float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
     float* dv = nullptr;              // [B][nsup + N][3]
     float* part = nullptr;            // [nstrips_max][ldA][kPartFloats]
+    int* strip_active = nullptr;      // [nstrips_max][ftiles] which (strip, frame-tile) CTAs wrote partials (dense regime)
     float* data_loss = nullptr;       // [B]
     float* pen_loss = nullptr;        // [B]
     float* dtransl = nullptr;         // [B][3]

@@ -67,6 +67,8 @@ struct DenseIn {
     const float* Wd;          // [N][24] dense skinning weights (adjoint of the extra vertices)
     const float* part;        // [strip][ldA][512] partial adjoints of the dense SDF gradient (vertex_bwd), or NULL
     int nstrips, ldA, slot;
+    const int* strip_active;  // [strip][ftiles]
+    int ftiles;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -365,15 +367,16 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
                 float a = 0.f;
                 const float* pp = din.part + (size_t)din.slot * kPartFloats + e;
                 const size_t stride = (size_t)din.ldA * kPartFloats;
+                const int* fl = din.strip_active + din.slot / kTileF;
                 int sidx = 0;
-                for (; sidx + 8 <= din.nstrips; sidx += 8) {
+                for (; sidx + 8 <= din.nstrips; sidx += 8) {       // strips that met no active tile wrote nothing
                     float v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = pp[(size_t)(sidx + u) * stride];
+                    for (int u = 0; u < 8; ++u) v[u] = fl[(sidx + u) * din.ftiles] ? pp[(size_t)(sidx + u) * stride] : 0.f;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) a += v[u];
                 }
-                for (; sidx < din.nstrips; ++sidx) a += pp[(size_t)sidx * stride];
+                for (; sidx < din.nstrips; ++sidx) a += fl[sidx * din.ftiles] ? pp[(size_t)sidx * stride] : 0.f;
                 if (e < kSkinFloats) S.dA[e] += a; else S.dPhi[e - kSkinFloats] += a;
             }
             __syncthreads();
@@ -628,7 +631,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
                   const int* __restrict__ list_n, const float* __restrict__ list_d, const int* __restrict__ list_count,
                   const float* __restrict__ pen_loss, const float* __restrict__ Wd, float* __restrict__ Phi,
                   float* __restrict__ PhiTc, float* __restrict__ At, int ldA, const float* __restrict__ part, int nstrips,
-                  const float* __restrict__ sdf_scal) {
+                  const float* __restrict__ sdf_scal, const int* __restrict__ strip_active, int ftiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     const int slot = blockIdx.x;
@@ -658,6 +661,18 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
         }
         for (int i = t; i < hl; i += kResThreads) S.ro[i] = L.ro[(size_t)b * L.H + i];
         asm volatile("cp.async.commit_group;");
+        // the optimiser's seven 86-vectors: one coalesced read now, one write-back after the step (every dot
+        // product / axpy of the state machine then runs out of shared memory instead of ~30 dependent L2 round trips)
+        for (int i = t; i < kParams; i += kResThreads) {
+            S.lx[i] = params[(size_t)b * kParams + i];
+            S.lg[i] = L.g[(size_t)b * kParams + i];
+            S.ld[i] = L.d[(size_t)b * kParams + i];
+            S.lprev_g[i] = L.prev_g[(size_t)b * kParams + i];
+            S.lx_init[i] = L.x_init[(size_t)b * kParams + i];
+            S.lg_prev[i] = L.g_prev[(size_t)b * kParams + i];
+            S.lbg0[i] = L.bg[(size_t)b * 2 * kParams + i];
+            S.lbg1[i] = L.bg[(size_t)b * 2 * kParams + kParams + i];
+        }
     }
     __syncthreads();
     DenseIn din;
@@ -670,17 +685,28 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     din.Wd = Wd;
     din.part = (part && sdf_scal[4 * slot] != 0.f) ? part : nullptr;      // frames without penetration have no partials
     din.nstrips = nstrips; din.ldA = ldA; din.slot = slot;
+    din.strip_active = strip_active; din.ftiles = ftiles;
     resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
     __syncthreads();
     if (warp == 0) {
         FrameScalars s = L.sc[b];
-        LbfgsPtrs P{params + (size_t)b * kParams, L.g + (size_t)b * kParams, L.d + (size_t)b * kParams,
-                    L.prev_g + (size_t)b * kParams, L.x_init + (size_t)b * kParams, L.g_prev + (size_t)b * kParams,
-                    L.bg + (size_t)b * 2 * kParams, L.bg + (size_t)b * 2 * kParams + kParams,
-                    hy, hs, S.ro, S.al, x_eval, S.lg_new, L.H};
+        LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval,
+                    S.lg_new, L.H};
         lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
+        __syncwarp();
+        VLOOP(i) {
+            params[(size_t)b * kParams + i] = S.lx[i];
+            L.g[(size_t)b * kParams + i] = S.lg[i];
+            L.d[(size_t)b * kParams + i] = S.ld[i];
+            L.prev_g[(size_t)b * kParams + i] = S.lprev_g[i];
+            L.x_init[(size_t)b * kParams + i] = S.lx_init[i];
+            L.g_prev[(size_t)b * kParams + i] = S.lg_prev[i];
+            L.bg[(size_t)b * 2 * kParams + i] = S.lbg0[i];
+            L.bg[(size_t)b * 2 * kParams + kParams + i] = S.lbg1[i];
+            x_eval[i] = S.lx_eval[i];
+        }
         if (s.pushed_slot >= 0) {                       // write the new curvature pair through to global memory
             const int wslot = s.pushed_slot;
             VLOOP(i) {
@@ -694,7 +720,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     __syncthreads();
     if (S.fs.phase == PH_DONE) return;
     // pose forward of the next trial point -> Phi row and skinning transforms for the next vertex launch
-    for (int i = t; i < kParams; i += kResThreads) S.x[i] = x_eval[i];
+    for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
     __syncthreads();
     if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
     else if (t >= 32 && t < 32 + 72) {
@@ -832,7 +858,7 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
                                                                  w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
                                                                  w.verts, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count, w.pen_loss,
                                                                  dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA, nstrips > 0 ? w.part : nullptr, nstrips,
-                                                                 w.sdf_scal));
+                                                                 w.sdf_scal, w.strip_active, (w.B + kTileF - 1) / kTileF));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -583,10 +583,10 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
     __shared__ FrameBox s_box;
     __shared__ float tri0[9];
     __shared__ float cone[12];
-    {
+    if (t < 32) {       // warp 0 folds the per-chunk box partials with shuffles (ties -> lowest vertex index)
         float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
         int ilo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, ihi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-        for (int tl = t; tl < nbox; tl += kSdfPartThreads) {
+        for (int tl = t; tl < nbox; tl += 32) {
             const float* bp = bboxp + ((size_t)slot * nbox + tl) * 12;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -597,19 +597,14 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
             }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { s_f[c][t] = lo[c]; s_f[3 + c][t] = hi[c]; s_i[c][t] = ilo[c]; s_i[3 + c][t] = ihi[c]; }
-        __syncthreads();
-        for (int o = kSdfPartThreads / 2; o > 0; o >>= 1) {
-            if (t < o) {
+        for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float l2 = s_f[c][t + o]; const int il2 = s_i[c][t + o];
-                    if (l2 < s_f[c][t] || (l2 == s_f[c][t] && il2 < s_i[c][t])) { s_f[c][t] = l2; s_i[c][t] = il2; }
-                    const float h2 = s_f[3 + c][t + o]; const int ih2 = s_i[3 + c][t + o];
-                    if (h2 > s_f[3 + c][t] || (h2 == s_f[3 + c][t] && ih2 < s_i[3 + c][t])) { s_f[3 + c][t] = h2; s_i[3 + c][t] = ih2; }
-                }
+            for (int c = 0; c < 3; ++c) {
+                const float l2 = __shfl_xor_sync(0xffffffffu, lo[c], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[c], o);
+                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
+                const float h2 = __shfl_xor_sync(0xffffffffu, hi[c], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[c], o);
+                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
             }
-            __syncthreads();
         }
         if (t == 0) {
             FrameBox fb;
@@ -619,9 +614,9 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
             for (int c = 0; c < 3; ++c) {
                 // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
                 // arg-indices commute with the translation (body_models_scale.py:403)
-                const float lc = s_f[c][0] + tr[c], hc = s_f[3 + c][0] + tr[c];
+                const float lc = lo[c] + tr[c], hc = hi[c] + tr[c];
                 fb.centre[c] = (lc + hc) / 2.f;
-                fb.ilo[c] = s_i[c][0]; fb.ihi[c] = s_i[3 + c][0];
+                fb.ilo[c] = ilo[c]; fb.ihi[c] = ihi[c];
                 const float e = hc - lc;
                 if (e > ext) { ext = e; fb.cmax = c; }
             }
@@ -630,8 +625,8 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
             s_box = fb;
             if (part == 0) boxout[slot] = fb;
         }
-        __syncthreads();
     }
+    __syncthreads();
     const FrameBox fb = s_box;
     if (t < 9) tri0[t] = ((vf[3 * faces[t / 3] + t % 3] + tr[t % 3]) - fb.centre[t % 3]) / fb.scale;
     __syncthreads();

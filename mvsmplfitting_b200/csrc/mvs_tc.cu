@@ -226,7 +226,8 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 constexpr int kSkinV = 64;
 constexpr int kSkinThreads = 256;
 constexpr int kSkinOutLd = 3 * kSkinV + 1;     // 193
-constexpr size_t kSkinSmem = (size_t)(kSkinFloats * 32 + kBetas * 32 + 2 * 32 * kSkinOutLd + 8 * 32 * 6 * 2) * sizeof(float);
+constexpr size_t kSkinSmem =
+    (size_t)(kSkinFloats * 32 + kBetas * 32 + 2 * 32 * kSkinOutLd + 8 * 32 * 6 * 2 + kSkinV * 33) * sizeof(float);
 
 __global__ void __launch_bounds__(kSkinThreads)
 skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const float* __restrict__ Phi,
@@ -239,6 +240,7 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
     float* Ovp = Bs + kBetas * 32;                    // [32][193]
     float* Ov = Ovp + 32 * kSkinOutLd;                // [32][193]
     float* Bb = Ov + 32 * kSkinOutLd;                 // [8 warps][32 lanes][6] values, then [..][6] indices
+    float* Sts = Bb + 8 * 32 * 6 * 2;                 // [64][33] shapedirs rows | template of this CTA's vertices
     const int na = *na_ptr;
     const int f0 = blockIdx.y * 32;
     if (f0 >= na) return;
@@ -248,6 +250,7 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
     for (int e = tid; e < kSkinFloats * 32; e += kSkinThreads) As[e] = At[(size_t)(e >> 5) * ldA + min(f0 + (e & 31), na - 1)];
     for (int e = tid; e < kBetas * 32; e += kSkinThreads)
         Bs[e] = Phi[(size_t)min(f0 + (e & 31), na - 1) * kFeatPad + kPoseBasis + (e >> 5)];
+    for (int e = tid; e < kSkinV * 33; e += kSkinThreads) Sts[e] = (v0 * 33 + e < N * 33) ? ST[(size_t)v0 * 33 + e] : 0.f;
     __syncthreads();
     float beta[kBetas];
 #pragma unroll
@@ -258,7 +261,7 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
         const int li = warp * (kSkinV / 8) + i;
         const int n = v0 + li;
         if (n >= N) break;
-        const float* st = ST + (size_t)n * 33;                       // [3][11]: shapedirs row | template
+        const float* st = Sts + li * 33;                              // [3][11]: shapedirs row | template
         float vp[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

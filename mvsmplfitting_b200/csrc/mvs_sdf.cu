@@ -579,7 +579,6 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
     const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
                          x[(size_t)b * kParams + kOffTransl + 2]};
     __shared__ float s_f[6][kSdfPartThreads];
-    __shared__ int s_i[6][kSdfPartThreads];
     __shared__ FrameBox s_box;
     __shared__ float tri0[9];
     __shared__ float cone[12];

@@ -245,7 +245,9 @@ def run_ours(args):
                 "note": "the path is latency / L2 bound, not HBM bound: constants (20 MB) live in the 126 MB L2 and one "
                         "launch moves a few MB; see DESIGN.md section 5",
                 "kernel_time_share_of_step": {k: round(v[0] / max(sum(x_[0] for x_ in share.values()), 1e-9), 4)
-                                              for k, v in share.items()}}
+                                              for k, v in share.items()},
+                "kernel_avg_us_instrumented_step": {k: round(v[0] * 1e3 / max(v[1], 1), 2) for k, v in share.items()},
+                "kernel_launches_instrumented_step": {k: int(v[1]) for k, v in share.items()}}
         # the tensor-core contraction, from the fully instrumented warm-up step (events around every launch)
         if "posedirs_gemm_tc" in share and share["posedirs_gemm_tc"][1] > 0:
             g_ms, g_n = share["posedirs_gemm_tc"]
@@ -295,7 +297,7 @@ def algorithmic_bytes(kernel: str, na: float, V: int, dense: bool) -> float:
         return N * 33 * 4 + N * 32 + na * (3 * N * 4 + 288 * 4 + 40 + 2 * N * 12)
     if kernel == "vertex_bwd":
         return 3 * N * 218 * 4 + N * 24 * 4 + na * (1152 + 2 * N * 12 + 2048)
-    if kernel in ("sdf_sample", "sdf_finalize", "sdf_frame"):
+    if kernel in ("sdf_sample", "sdf_finalize", "sdf_fused"):
         return na * (N * 12 + N * 12)
     if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance", "frame_step"):
         return na * (344 * 3 + 204 * V + 2048 + 86 * 24)

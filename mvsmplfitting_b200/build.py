@@ -29,6 +29,14 @@ def needs_build() -> bool:
     return os.path.getmtime(OUT) < max(os.path.getmtime(p) for p in deps)
 
 
+def build_debug() -> str:
+    """libmvsmpl_dbg.so with -DMVS_PHASE_DBG (per-phase clock stamps in frame_step_kernel); profiling scripts only"""
+    out = os.path.join(_HERE, "libmvsmpl_dbg.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DMVS_PHASE_DBG", "-o", out] + sources() + ["-lcuda"])
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
@@ -41,4 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -334,10 +334,7 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
                   const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW,
                   const float* __restrict__ Wd, const int* __restrict__ blist_n, const int* __restrict__ blist_pos,
                   int nvb, int nv_fwd, const float* __restrict__ vposed, const float* __restrict__ dv,
-                  const int* __restrict__ na_ptr, int tiles_per_strip, int ntiles, float* __restrict__ part,
-                  const float* __restrict__ slot_scale /* [slot][4]: dv is multiplied by slot_scale[4*slot], or NULL */,
-                  const unsigned char* __restrict__ tileflag /* [slot][ntiles] or NULL */,
-                  int* __restrict__ strip_active /* [strip][gridDim.y] or NULL: 1 iff this CTA wrote partials */) {
+                  const int* __restrict__ na_ptr, int tiles_per_strip, int ntiles, float* __restrict__ part) {
     extern __shared__ __align__(16) float smem[];
     float* DV = smem;                          // [96][65]   upstream d loss / d vertex, column-major
     float* VP = DV + kTileC * kDvLd;           // [96][65]   v_posed
@@ -379,19 +376,12 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
         }
         __syncthreads();
         int any = 0;
-        if (tileflag) {              // SDF gradient: a byte per (frame, tile) says whether anything is there at all
-            int f = 0;
-            if (tid < kTileF && f0 + tid < na)
-                f = tileflag[(size_t)(f0 + tid) * ntiles + tile] && slot_scale[4 * (f0 + tid)] != 0.f;
-            if (!__syncthreads_or(f)) continue;
-        }
         for (int idx = tid; idx < kTileF * kTileC; idx += kVertThreads) {
             const int bb = idx / kTileC, col = idx % kTileC;
             const int slot = f0 + bb, vi = v0 + col / 3;
             float d = 0.f, p = 0.f;
             if (slot < na && vi < nvb) {
                 d = dv[((size_t)slot * nvb + v0) * 3 + col];
-                if (slot_scale) d *= slot_scale[4 * slot];
                 p = vposed[((size_t)slot * nv_fwd + s_pos[col / 3]) * 3 + col % 3];
             }
             DV[col * kDvLd + bb] = d;
@@ -503,11 +493,7 @@ vertex_bwd_kernel(const float* __restrict__ Qk, const float* __restrict__ At, in
             }
         }
     }
-    // per-strip partials: [strip][slot][288 skin | 224 feature]; a CTA that met no active tile only says so
-    if (strip_active) {
-        if (tid == 0) strip_active[strip * gridDim.y + blockIdx.y] = ats_loaded ? 1 : 0;
-        if (!ats_loaded) return;
-    }
+    // per-strip partials: [strip][slot][288 skin | 224 feature]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int slot = f0 + 4 * ty + i;
@@ -812,7 +798,7 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         MVS_LAUNCH(ctx, KID_VERTEX_BWD, st,
                    vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd,
                                                                              blist_n, blist_pos, nvb, nv, w.vposed, w.dv,
-                                                                             w.na, tps, ntiles, w.part, nullptr, nullptr, nullptr));
+                                                                             w.na, tps, ntiles, w.part));
     }
     PriorModel pm{m.M, m.gmm_means, m.gmm_prec, m.gmm_lognllw};
     MVS_LAUNCH(ctx, KID_FRAME_BWD, st,
@@ -834,37 +820,6 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
                frame_fwd_kernel<<<w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt, m.JS, w.Phi, w.PhiTc, w.At,
                                                               w.ldA, w.gchain));
-    MVS_CUDA_OK(ctx, cudaGetLastError());
-    return MVS_OK;
-}
-
-// dense regime: adjoint of the vertex stage for the SDF gradient only (dv = factor[slot] * gcoord), all vertices,
-// tiles without gradient skipped through the flag bytes; per-strip partials for frame_step
-int launch_vertex_bwd_sdf(mvs_ctx* ctx, int* nstrips_out, cudaStream_t st) {
-    DevModel& m = ctx->m;
-    Workspace& w = ctx->ws;
-    if (!ctx->attr_done) {
-        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertFwdSmem));
-        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertBwdSmem));
-        ctx->attr_done = true;
-    }
-    const int ftiles = (w.B + kTileF - 1) / kTileF;
-    const int ntiles = (m.N + kTileV - 1) / kTileV;
-    int want = (ctx->sm_count + ftiles - 1) / ftiles;
-    if (want < 1) want = 1;
-    if (want > w.nstrips_max) want = w.nstrips_max;
-    const int tps = (ntiles + want - 1) / want;
-    const int nstrips = (ntiles + tps - 1) / tps;
-    *nstrips_out = nstrips;
-    if (!w.strip_active) {
-        int rc = dev_alloc(ctx, &w.strip_active, (size_t)w.nstrips_max * ftiles);
-        if (rc) return rc;
-    }
-    dim3 g4(nstrips, ftiles);
-    MVS_LAUNCH(ctx, KID_VERTEX_BWD, st,
-               vertex_bwd_kernel<<<g4, kVertThreads, kVertBwdSmem, st>>>(m.Qk, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.Wd, nullptr,
-                                                                         nullptr, m.N, m.N, w.vposed, w.sdf_gcoord, w.na, tps,
-                                                                         ntiles, w.part, w.sdf_scal, w.sdf_tileflag, w.strip_active));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

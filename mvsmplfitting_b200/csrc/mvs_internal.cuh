@@ -91,7 +91,6 @@ struct Workspace {
     float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
     float* dv = nullptr;              // [B][nsup + N][3]
     float* part = nullptr;            // [nstrips_max][ldA][kPartFloats]
-    int* strip_active = nullptr;      // [nstrips_max][ftiles] which (strip, frame-tile) CTAs wrote partials (dense regime)
     float* data_loss = nullptr;       // [B]
     float* pen_loss = nullptr;        // [B]
     float* dtransl = nullptr;         // [B][3]
@@ -108,15 +107,36 @@ struct Workspace {
     float* sdf_frame = nullptr;       // [B][16]  centre(3) scale(1) argmin/argmax ids etc.
     float* sdf_gcoord = nullptr;      // [B][N][3]
     float* sdf_valpart = nullptr;     // [B][nbt]
-    int* sdf_list_n = nullptr;        // [B][N] vertices with a non-zero penetration gradient (dense regime)
-    float* sdf_list_d = nullptr;      // [B][N][3]
-    int* sdf_list_count = nullptr;    // [B]
-    float* bboxp = nullptr;           // [B][ntiles][12] per-tile bbox partials written by the tensor-core vertex kernel
-    float* sdf_parts = nullptr;       // [B][P][5] partial sums of the SDF sampling kernel
-    float* sdf_scal = nullptr;        // [B][12] per frame: cg/scale, pen, dcentre(3), dscale, centre(3), scale ...
-    unsigned char* sdf_tileflag = nullptr;   // [B][ntiles] tile has a non-zero SDF gradient
-    unsigned char* sdf_box = nullptr;        // [B] FrameBox
+    float* bboxp = nullptr;           // [B][nchunks][12] per-chunk bbox partials written by the skinning kernel
+    // dense regime (sdf_fused_kernel -> frame_step_kernel), P = parts of 1024 vertices per frame
+    float* sdf_parts5 = nullptr;      // [B][P][5] partial sums: value, d value/d local (3), <d value/d local, local>
+    float* sdf_part = nullptr;        // [B][P][512] unit-factor partial adjoints (288 skin | 224 feature)
+    int* sdf_pflag = nullptr;         // [B][P] 1 iff the part has vertices with a non-zero sample gradient
+    unsigned char* sdf_box = nullptr; // [B] FrameBox
 };
+
+struct FrameBox {                     // bounding box of one frame's mesh (fitting.py:352-359)
+    float centre[3];
+    float scale;
+    int ilo[3], ihi[3];
+    int cmax;                         // coordinate with the largest extent
+    float pad;
+};
+
+// sdf_fused_kernel splits a frame's vertices into parts of 256 x passes vertices; few active frames -> more, smaller
+// parts (latency), many -> fewer, larger ones (less per-CTA overhead).  frame_step_kernel derives the same split.
+constexpr int kSdfMaxParts = 32;
+__host__ __device__ inline int sdf_passes_for(int na, int n_verts) {
+    const int p1 = (n_verts + 255) / 256;
+    if (p1 > kSdfMaxParts) return 4;
+    if (na * p1 <= 640) return 1;
+    if (na * ((p1 + 1) / 2) <= 640) return 2;
+    return 4;
+}
+__host__ __device__ inline int sdf_parts_for(int na, int n_verts) {
+    const int per = 256 * sdf_passes_for(na, n_verts);
+    return (n_verts + per - 1) / per;
+}
 
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
@@ -188,20 +208,17 @@ int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, f
 bool resident_lbfgs_available(const mvs_ctx* ctx, int history);
 int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, void* frame_scalars_out,
                           float* last_grad_dev, cudaStream_t st);
-// dense regime (SDF term): per round  vertex_fwd (all vertices, batched GEMM) -> sdf_frame -> frame_step
+// dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
-int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
-int launch_sdf_parts(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
-int launch_vertex_bwd_sdf(mvs_ctx* ctx, int* nstrips_out, cudaStream_t st);                          // mvs_closure.cu
+int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
 // mvs_tc.cu: tcgen05 / TMA dense vertex forward
 int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
 int tc_check_error(mvs_ctx* ctx);
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstrips,
-                      cudaStream_t st);
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st);
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);
 }  // namespace mvs

@@ -19,6 +19,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include "mvs_internal.cuh"
 #include "mvs_lbfgs_core.cuh"
 
@@ -192,22 +194,21 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
     if (!step_mode && hybrid_available(ctx)) {
-        // dense regime (SDF term on): three launches per round -- dense vertices (batched GEMM over the active
-        // frames), the per-frame SDF term, the per-frame fused closure-adjoint + optimiser step + next pose forward.
-        // Finished frames are compacted out of the active list once per chunk.
+        // dense regime (SDF term on): four launches per round -- pose blend shapes of the active frames (tcgen05
+        // GEMM), skinning + box partials, the SDF term with the adjoint of its (short) vertex list, and the per-frame
+        // closure adjoint + optimiser step + next pose forward.  Finished frames are compacted out once per chunk.
         const int chunk = 8;
         const long long max_rounds = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
         long long rounds = 0;
         int na_host = B;
+        static const bool trace_na = getenv("MVS_TRACE_NA") != nullptr;       // debugging aid: active-list size per chunk
         rc = launch_frame_fwd(ctx, S.x_eval, st);
         if (rc) return rc;
         while (na_host > 0 && rounds < max_rounds) {
             for (int r = 0; r < chunk; ++r) {
-                int nstrips = 0;
                 if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;        // tcgen05 GEMM + LBS + bbox partials
-                if ((rc = launch_sdf_parts(ctx, S.x_eval, S.sc, st))) return rc;   // samples, gradients, per-frame scalars
-                if ((rc = launch_vertex_bwd_sdf(ctx, &nstrips, st))) return rc;    // adjoint of the dense SDF gradient
-                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, nstrips, st))) return rc;
+                if ((rc = launch_sdf_fused(ctx, S.x_eval, S.sc, st))) return rc;   // samples + adjoint of the listed vertices
+                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, st))) return rc;
                 ++rounds;
             }
             // compaction changes slot -> frame, so the surviving frames' Phi / transforms are rebuilt for their new slots
@@ -216,6 +217,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
             MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.na_host, w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
             MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
             na_host = *S.na_host;
+            if (trace_na) fprintf(stderr, "[mvs] dense regime: round %lld, active frames %d\n", rounds, na_host);
             if ((rc = tc_check_error(ctx))) return rc;
         }
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));

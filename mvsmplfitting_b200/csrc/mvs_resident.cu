@@ -18,10 +18,29 @@
 
 namespace mvs {
 
+// -DMVS_PHASE_DBG (scripts/phase_times.py builds libmvsmpl_dbg.so with it): thread 0 of CTA 0 stamps clock64() after
+// every barrier of frame_step_kernel, so the serial phases of one frame's round can be timed without a profiler.
+#ifdef MVS_PHASE_DBG
+__device__ long long g_phase_clk[64];
+#define PHASE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PHASE_MARK(i) do {} while (0)
+#endif
+
 constexpr int kResThreads = 256;
 constexpr int kResMaxSup = 96;            // support vertices (SMPL: 86)
 constexpr int kResMaxVK = 272;            // views x keypoints (16 x 17)
 constexpr int kResMaxM = 8;               // GMM components
+
+// Depth-level schedule of the kinematic tree: joints of one level only depend on the level above (forward) / below
+// (adjoint), so a level is processed by parallel lane groups and the 23-step serial chain becomes <= 9 level steps
+// for SMPL.  Children are listed in DESCENDING index order: gathering them in that order reproduces the summation
+// order of the plain "for j = 23 .. 1" reverse sweep bit for bit.
+struct ChainSched {
+    int nlev;
+    unsigned char lev_ptr[kJoints + 1], lev_j[kJoints];
+    unsigned char ch_ptr[kJoints + 1], ch_j[kJoints];
+};
 
 struct ResidentModel {                    // device pointers + sizes, by value
     const float* Qk; const float* Jt; const float* JS;
@@ -33,6 +52,7 @@ struct ResidentModel {                    // device pointers + sizes, by value
     int M; const float* gmm_means; const float* gmm_prec; const float* gmm_lognllw;
     const float* anchor; const float* anchor_w;     // sequence mode (mvs_set_anchor)
     Parents par;
+    ChainSched cs;
 };
 
 struct ResidentSmem {
@@ -52,24 +72,110 @@ struct ResidentSmem {
     // optimiser vectors (lbfgs_resident_kernel only)
     float lx[88], lg[88], ld[88], lprev_g[88], lx_init[88], lg_prev[88], lbg0[88], lbg1[88], lx_eval[88], lg_new[88];
     float ro[128], al[128];
+    // level schedule of the kinematic tree (copy of ResidentModel::cs / par: shared-memory latency instead of
+    // dependent constant-bank loads inside the level loops)
+    int nlev, lev_ptr[kJoints + 1], lev_j[kJoints], ch_ptr[kJoints + 1], ch_j[kJoints], par[kJoints];
+    // dense regime: frame scalars of the SDF term and its box-extreme vertex list (frame_step_kernel)
+    int ext_n[8];
+    float ext_d[24];
+    float sdf_sc[4];                       // [0] cg / scale, [1] pen loss, [2] number of extreme entries
     FrameScalars fs;
 };
 
-// Inputs of the dense regime (SDF term on): the dense vertex kernel already produced every vertex of the frame,
-// and the SDF kernel a compact list of vertices with a non-zero penetration gradient.
+// Inputs of the dense regime (SDF term on): the skinning kernel already produced every vertex of the frame, and
+// sdf_fused_kernel the unit-factor adjoint of the vertices inside the penetration cone (per 1024-vertex part).
 struct DenseIn {
     const float* vposed;      // [N][3] this frame's v_posed (NULL: sparse regime, recompute the support vertices)
     const float* verts;       // [N][3] skinned, pre-transl
-    const int* extra_n;       // [n_extra] vertex ids
+    const int* extra_n;       // [n_extra] box-extreme vertices that carry the gradient through the box centre / scale
     const float* extra_d;     // [n_extra][3] d pen / d vertex
     int n_extra;
     float pen_loss;
     const float* Wd;          // [N][24] dense skinning weights (adjoint of the extra vertices)
-    const float* part;        // [strip][ldA][512] partial adjoints of the dense SDF gradient (vertex_bwd), or NULL
-    int nstrips, ldA, slot;
-    const int* strip_active;  // [strip][ftiles]
-    int ftiles;
+    const float* part;        // [nparts][512] this frame's unit-factor partial adjoints, or NULL (no penetration)
+    const int* pflag;         // [nparts]
+    int nparts;
+    float factor;             // cg / scale: d pen / d (sum of samples) over the box scale
 };
+
+// ------------------------------------------------------------------------------------------------
+// Kinematic chain by depth levels (lbs.py:348-374): 12 lanes per joint, all joints of a level in parallel.
+// All kResThreads threads must call; ends with a barrier.
+__device__ __forceinline__ void chain_fwd_levels(ResidentSmem& S) {
+    const int t = threadIdx.x;
+    if (t < 9) S.Gam[t] = S.x[kOffScale] * S.R[t];                               // lbs.py:348
+    else if (t < 12) S.g[t - 9] = S.J[t - 9];
+    __syncthreads();
+    constexpr int kGroups = kResThreads / 12;
+    const int grp = t / 12, l = t % 12;
+    for (int L = 1; L < S.nlev; ++L) {
+        const int beg = S.lev_ptr[L], cnt = S.lev_ptr[L + 1] - beg;
+        if (grp < kGroups) {
+            for (int q = grp; q < cnt; q += kGroups) {
+                const int j = S.lev_j[beg + q], p = S.par[j];
+                const float* Gp = &S.Gam[9 * p];
+                if (l < 9) {
+                    const int r = l / 3, c = l % 3;
+                    const float* Rj = &S.R[9 * j];
+                    S.Gam[9 * j + l] = Gp[3 * r] * Rj[c] + Gp[3 * r + 1] * Rj[3 + c] + Gp[3 * r + 2] * Rj[6 + c];
+                } else {
+                    const int r = l - 9;
+                    const float r0 = S.J[3 * j] - S.J[3 * p], r1 = S.J[3 * j + 1] - S.J[3 * p + 1], r2 = S.J[3 * j + 2] - S.J[3 * p + 2];
+                    S.g[3 * j + r] = (Gp[3 * r] * r0 + Gp[3 * r + 1] * r1 + Gp[3 * r + 2] * r2) + S.g[3 * p + r];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Adjoint of the chain, deepest level first: the 24 lanes of a PARENT gather its children's contributions
+// (dGam_p += dGam_j R_j^T + dg_j rel^T, dg_p += dg_j, dJ_p -= drel) and emit the children's dR_j, dJ_j.
+__device__ __forceinline__ void chain_bwd_levels(ResidentSmem& S) {
+    const int t = threadIdx.x;
+    constexpr int kGroups = kResThreads / 24;
+    const int grp = t / 24, l = t % 24;
+    for (int L = S.nlev - 2; L >= 0; --L) {
+        const int beg = S.lev_ptr[L], cnt = S.lev_ptr[L + 1] - beg;
+        if (grp < kGroups) {
+            for (int q = grp; q < cnt; q += kGroups) {
+                const int p = S.lev_j[beg + q];
+                const int c0 = S.ch_ptr[p], c1 = S.ch_ptr[p + 1];
+                if (c0 == c1) continue;
+                const float* Gp = &S.Gam[9 * p];
+                float acc = 0.f;
+                if (l < 9) acc = S.dGam[9 * p + l];
+                else if (l >= 18 && l < 21) acc = S.dJ[3 * p + l - 18];
+                else if (l >= 21) acc = S.dg[3 * p + l - 21];
+                for (int ci = c0; ci < c1; ++ci) {
+                    const int j = S.ch_j[ci];
+                    const float* dGj = &S.dGam[9 * j];
+                    const float* dgj = &S.dg[3 * j];
+                    if (l < 9) {                   // dGp += dGam_j R_j^T + dg_j rel^T
+                        const int r = l / 3, c = l % 3;
+                        const float* Rj = &S.R[9 * j];
+                        const float rel = S.J[3 * j + c] - S.J[3 * p + c];
+                        acc += (dGj[3 * r] * Rj[3 * c] + dGj[3 * r + 1] * Rj[3 * c + 1] + dGj[3 * r + 2] * Rj[3 * c + 2]) + dgj[r] * rel;
+                    } else if (l < 18) {           // dR_j = Gp^T dGam_j
+                        const int e = l - 9, r = e / 3, c = e % 3;
+                        S.dR[9 * j + e] = Gp[r] * dGj[c] + Gp[3 + r] * dGj[3 + c] + Gp[6 + r] * dGj[6 + c];
+                    } else if (l < 21) {           // drel = Gp^T dg_j
+                        const int r = l - 18;
+                        const float out = Gp[r] * dgj[0] + Gp[3 + r] * dgj[1] + Gp[6 + r] * dgj[2];
+                        S.dJ[3 * j + r] += out;
+                        acc -= out;
+                    } else {
+                        acc += dgj[l - 21];
+                    }
+                }
+                if (l < 9) S.dGam[9 * p + l] = acc;
+                else if (l >= 18 && l < 21) S.dJ[3 * p + l - 18] = acc;
+                else if (l >= 21) S.dg[3 * p + l - 21] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // One closure evaluation at S.x (already loaded).  Writes S.sc[2] = total loss and S.lg_new = gradient
@@ -94,30 +200,10 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
     for (int i = t; i < kJoints * 3; i += kResThreads) { S.dg[i] = 0.f; S.dJ[i] = 0.f; }
     for (int i = t; i < kParams; i += kResThreads) S.grad[i] = 0.f;
     __syncthreads();
-    // ---- P2 kinematic chain (warp 0, 12 lanes per joint, joints in index order: parents[j] < j)
-    if (warp == 0) {
-        const float sc = S.x[kOffScale];
-        if (lane < 9) S.Gam[lane] = sc * S.R[lane];                               // lbs.py:348
-        if (lane < 3) S.g[lane] = S.J[lane];
-        __syncwarp();
-        for (int j = 1; j < kJoints; ++j) {
-            const int p = m.par.p[j];
-            if (lane < 12) {
-                const float* Gp = &S.Gam[9 * p];
-                if (lane < 9) {
-                    const int r = lane / 3, c = lane % 3;
-                    const float* Rj = &S.R[9 * j];
-                    S.Gam[9 * j + lane] = Gp[3 * r] * Rj[c] + Gp[3 * r + 1] * Rj[3 + c] + Gp[3 * r + 2] * Rj[6 + c];
-                } else {
-                    const int r = lane - 9;
-                    const float r0 = S.J[3 * j] - S.J[3 * p], r1 = S.J[3 * j + 1] - S.J[3 * p + 1], r2 = S.J[3 * j + 2] - S.J[3 * p + 2];
-                    S.g[3 * j + r] = (Gp[3 * r] * r0 + Gp[3 * r + 1] * r1 + Gp[3 * r + 2] * r2) + S.g[3 * p + r];
-                }
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    PHASE_MARK(2);
+    // ---- P2 kinematic chain, level-parallel
+    chain_fwd_levels(S);
+    PHASE_MARK(3);
     // ---- P3 skinning transforms and the feature row
     if (t < kJoints) make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], &S.A[12 * t]);
     else if (t >= 32) {
@@ -129,6 +215,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         S.Phi[k] = v;
     }
     __syncthreads();
+    PHASE_MARK(4);
     // ---- P4 v_posed for the support columns: warp per Qk row, 2 x LDG.128 per lane
     if (din.vposed) {                 // dense regime: the vertex kernel already has them
         for (int col = t; col < ncol; col += kResThreads) {
@@ -162,6 +249,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(5);
     // ---- P5 linear blend skinning of the support vertices
     if (!din.vposed && t < nsup) {
         const int n = m.sup[t];
@@ -181,6 +269,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         for (int r = 0; r < 3; ++r) S.v[3 * t + r] = T[4 * r] * p0 + T[4 * r + 1] * p1 + T[4 * r + 2] * p2 + T[4 * r + 3];
     }
     __syncthreads();
+    PHASE_MARK(6);
     // ---- P6 keypoints, projection, GMoF data term and its adjoint down to the support vertices
     if (t < K) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -198,6 +287,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(7);
     {
         const float rho2 = lp.rho * lp.rho, dw2 = lp.data_weight * lp.data_weight;
         for (int idx = t; idx < V * K; idx += kResThreads) {
@@ -219,6 +309,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             S.contrib[3 * idx] = dqv[0]; S.contrib[3 * idx + 1] = dqv[1]; S.contrib[3 * idx + 2] = dqv[2];
         }
         __syncthreads();
+        PHASE_MARK(8);
         if (t < K) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             for (int v = 0; v < V; ++v) {
@@ -232,6 +323,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             S.vsum[v] = a * dw2;
         }
         __syncthreads();
+        PHASE_MARK(9);
         if (t == 0) {
             float a = 0.f;
             for (int v = 0; v < V; ++v) a += S.vsum[v];
@@ -261,6 +353,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(10);
     if (have_grad) {
         // ---- P7 adjoint of skinning: dvp = T3x3^T dv ; dA_j = sum_i W[i,j] [dv (x) vp | dv]
         if (t < nsup) {
@@ -286,6 +379,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         for (int e = t; e < kSkinFloats; e += kResThreads) {
             const int j = e / 12, r = (e % 12) / 4, c = e % 4;
             float a = 0.f;
+#pragma unroll 4
             for (int q2 = m.supj_ptr[j]; q2 < m.supj_ptr[j + 1]; ++q2) {
                 const int i = m.supj_i[q2];
                 const float wd = m.supj_w[q2] * S.dv[3 * i + r];
@@ -294,22 +388,23 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             S.dA[e] = a;
         }
         __syncthreads();
+        PHASE_MARK(11);
         // ---- P8 dPhi[k] = sum_col dvp[col] Qk[row(col)][k]   (thread per k, coalesced rows)
         if (t < kFeatPad) {
             float a = 0.f;
             int col = 0;
-            for (; col + 4 <= ncol; col += 4) {
-                const float q0 = __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t);
-                const float q1 = __ldg(m.Qk + (size_t)S.rowbase[col + 1] * kFeatPad + t);
-                const float q2 = __ldg(m.Qk + (size_t)S.rowbase[col + 2] * kFeatPad + t);
-                const float q3 = __ldg(m.Qk + (size_t)S.rowbase[col + 3] * kFeatPad + t);
-                a = fmaf(S.dvp[col], q0, a); a = fmaf(S.dvp[col + 1], q1, a);
-                a = fmaf(S.dvp[col + 2], q2, a); a = fmaf(S.dvp[col + 3], q3, a);
+            for (; col + 12 <= ncol; col += 12) {              // 12 independent L2 loads in flight per thread
+                float qv[12];
+#pragma unroll
+                for (int u = 0; u < 12; ++u) qv[u] = __ldg(m.Qk + (size_t)S.rowbase[col + u] * kFeatPad + t);
+#pragma unroll
+                for (int u = 0; u < 12; ++u) a = fmaf(S.dvp[col + u], qv[u], a);
             }
             for (; col < ncol; ++col) a = fmaf(S.dvp[col], __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t), a);
             S.dPhi[t] = a;
         }
         __syncthreads();
+        PHASE_MARK(12);
         // ---- P8b dense regime: vertices with a penetration gradient, in chunks of kResMaxSup (reusing vp/dv/dvp);
         //      same adjoint as P7/P8 with generic (dense-W) joint ownership -- deterministic, no atomics
         for (int e0 = 0; e0 < din.n_extra; e0 += kResMaxSup) {
@@ -361,25 +456,16 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             }
             __syncthreads();
         }
-        if (din.part) {                   // dense SDF gradient: partial adjoints from the batched vertex kernel
+        if (din.part) {                   // penetration gradient: unit-factor partial adjoints of the listed vertices
             for (int e = t; e < kPartFloats; e += kResThreads) {
-                // fixed summation order (strip 0,1,2,...) with 8 loads in flight: the strips are independent L2 reads
-                float a = 0.f;
-                const float* pp = din.part + (size_t)din.slot * kPartFloats + e;
-                const size_t stride = (size_t)din.ldA * kPartFloats;
-                const int* fl = din.strip_active + din.slot / kTileF;
-                int sidx = 0;
-                for (; sidx + 8 <= din.nstrips; sidx += 8) {       // strips that met no active tile wrote nothing
-                    float v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = fl[(sidx + u) * din.ftiles] ? pp[(size_t)(sidx + u) * stride] : 0.f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) a += v[u];
-                }
-                for (; sidx < din.nstrips; ++sidx) a += fl[sidx * din.ftiles] ? pp[(size_t)sidx * stride] : 0.f;
+                float a = 0.f;                // fixed summation order (part 0,1,2,...); parts without vertices wrote nothing
+                for (int p = 0; p < din.nparts; ++p)
+                    if (din.pflag[p]) a += din.part[(size_t)p * kPartFloats + e];
+                a *= din.factor;
                 if (e < kSkinFloats) S.dA[e] += a; else S.dPhi[e - kSkinFloats] += a;
             }
             __syncthreads();
+            PHASE_MARK(13);
         }
         if (din.n_extra > 0) {            // restore the support-list row map for the next evaluation
             for (int col = t; col < ncol; col += kResThreads) S.rowbase[col] = 3 * m.sup[col / 3] + col % 3;
@@ -388,35 +474,10 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         if (t < kJoints)
             skin_transform_bwd(&S.dA[12 * t], &S.Gam[9 * t], &S.J[3 * t], &S.dGam[9 * t], &S.dg[3 * t], &S.dJ[3 * t]);
         __syncthreads();
-        // reverse sweep over the tree: 24 lanes per joint
+        PHASE_MARK(14);
+        // reverse sweep over the tree, level-parallel
+        chain_bwd_levels(S);
         if (warp == 0) {
-            for (int j = kJoints - 1; j >= 1; --j) {
-                const int p = m.par.p[j];
-                const float* Gp = &S.Gam[9 * p];
-                const float* dGj = &S.dGam[9 * j];
-                const float* dgj = &S.dg[3 * j];
-                float out = 0.f;
-                if (lane < 9) {                // dGp += dGam_j R_j^T + dg_j rel^T
-                    const int r = lane / 3, c = lane % 3;
-                    const float* Rj = &S.R[9 * j];
-                    const float rel = S.J[3 * j + c] - S.J[3 * p + c];
-                    out = (dGj[3 * r] * Rj[3 * c] + dGj[3 * r + 1] * Rj[3 * c + 1] + dGj[3 * r + 2] * Rj[3 * c + 2]) + dgj[r] * rel;
-                } else if (lane < 18) {        // dR_j = Gp^T dGam_j
-                    const int e = lane - 9, r = e / 3, c = e % 3;
-                    out = Gp[r] * dGj[c] + Gp[3 + r] * dGj[3 + c] + Gp[6 + r] * dGj[6 + c];
-                } else if (lane < 21) {        // drel = Gp^T dg_j
-                    const int r = lane - 18;
-                    out = Gp[r] * dgj[0] + Gp[3 + r] * dgj[1] + Gp[6 + r] * dgj[2];
-                } else if (lane < 24) {
-                    out = dgj[lane - 21];
-                }
-                __syncwarp();
-                if (lane < 9) S.dGam[9 * p + lane] += out;
-                else if (lane < 18) S.dR[9 * j + lane - 9] = out;
-                else if (lane < 21) { S.dJ[3 * j + lane - 18] += out; S.dJ[3 * p + lane - 18] -= out; }
-                else if (lane < 24) S.dg[3 * p + lane - 21] += out;
-                __syncwarp();
-            }
             const float sc = S.x[kOffScale];
             if (lane < 9) S.dR[lane] = sc * S.dGam[lane];
             if (lane == 0) {
@@ -428,9 +489,11 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             if (lane < 3) S.dJ[lane] += S.dg[lane];
         }
         __syncthreads();
+        PHASE_MARK(15);
         // ---- P10 pose-feature adjoint, Rodrigues adjoint, shape gradient
         if (t < kPoseBasis) S.dR[9 + t] += S.dPhi[t];
         __syncthreads();
+        PHASE_MARK(16);
         if (t < kJoints) {
             float dr[3] = {0.f, 0.f, 0.f};
             rodrigues_bwd(&S.x[kOffOrient + 3 * t], &S.dR[9 * t], dr);
@@ -450,19 +513,21 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         for (int e = t; e < M * 69; e += kResThreads) S.gm_diff[e] = theta[e % 69] - m.gmm_means[e];
     S.red[t] = (t < 69) ? theta[t] * theta[t] : 0.f;
     __syncthreads();
+    PHASE_MARK(17);
     if (!lp.use_vposer && lp.body_prior == MVS_PRIOR_GMM) {
         for (int e = t; e < M * 69; e += kResThreads) {
             const int mm = e / 69, i = e % 69;
             const float* P = m.gmm_prec + (size_t)mm * 69 * 69 + i;
             const float* df = &S.gm_diff[mm * 69];
             float y = 0.f;
-#pragma unroll 3
-            for (int j = 0; j < 69; ++j) y = fmaf(__ldg(P + j * 69), df[j], y);
+#pragma unroll 23
+            for (int j = 0; j < 69; ++j) y = fmaf(__ldg(P + j * 69), df[j], y);       // 23 independent loads in flight
             S.gm_y[e] = y;
         }
     }
     if (t == 0) { float a = 0.f; for (int i = 0; i < 69; ++i) a += S.red[i]; S.sc[1] = a; }
     __syncthreads();
+    PHASE_MARK(18);
     if (!lp.use_vposer && lp.body_prior == MVS_PRIOR_GMM && warp < M) {
         float p = 0.f;
         for (int i = lane; i < 69; i += 32) p = fmaf(S.gm_y[warp * 69 + i], S.gm_diff[warp * 69 + i], p);
@@ -470,6 +535,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         if (lane == 0) S.gm_ll[warp] = 0.5f * p - m.gmm_lognllw[warp];
     }
     __syncthreads();
+    PHASE_MARK(19);
     float pprior = 0.f, l2extra = 0.f;
     if (!lp.use_vposer) {
         float gs = bpw2;
@@ -500,6 +566,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         if (have_grad && t >= 96 && t < 96 + kBetas) S.grad[kOffBetas + t - 96] += 2.f * S.x[t - 96] * sw2;
     }
     __syncthreads();
+    PHASE_MARK(20);
     float angle = 0.f;
     {
         const int idx[4] = {52, 55, 9, 12};
@@ -516,6 +583,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(21);
     float anchor_loss = 0.f;
     if (lp.anchor_on) {                                   // sequence mode: sum_i w_i (x_i - a_i)^2
         float dif = 0.f, wt = 0.f;
@@ -544,10 +612,15 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(22);
 }
 
 __device__ __forceinline__ void resident_setup(ResidentSmem& S, const ResidentModel& m) {
     for (int col = threadIdx.x; col < 3 * m.nsup; col += kResThreads) S.rowbase[col] = 3 * m.sup[col / 3] + col % 3;
+    const int t = threadIdx.x;
+    if (t < kJoints) { S.lev_j[t] = m.cs.lev_j[t]; S.ch_j[t] = m.cs.ch_j[t]; S.par[t] = m.par.p[t]; }
+    else if (t >= 32 && t < 32 + kJoints + 1) { S.lev_ptr[t - 32] = m.cs.lev_ptr[t - 32]; S.ch_ptr[t - 32] = m.cs.ch_ptr[t - 32]; }
+    else if (t == 64) S.nlev = m.cs.nlev;
 }
 
 // ------------------------------------------------------------------------------------------------ single closure
@@ -628,16 +701,19 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
                   const int* __restrict__ fidx, const int* __restrict__ na_ptr, const float* __restrict__ gt_uv,
                   const float* __restrict__ conf, const float* __restrict__ joint_w, int B, int N,
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
-                  const int* __restrict__ list_n, const float* __restrict__ list_d, const int* __restrict__ list_count,
-                  const float* __restrict__ pen_loss, const float* __restrict__ Wd, float* __restrict__ Phi,
-                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA, const float* __restrict__ part, int nstrips,
-                  const float* __restrict__ sdf_scal, const int* __restrict__ strip_active, int ftiles) {
+                  const float* __restrict__ parts5, const float* __restrict__ part, const int* __restrict__ pflag,
+                  const FrameBox* __restrict__ box, const float* __restrict__ Wd, float* __restrict__ Phi,
+                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     const int slot = blockIdx.x;
-    if (slot >= *na_ptr) return;
+    const int na = *na_ptr;
+    if (slot >= na) return;
+    const int nparts = sdf_parts_for(na, N);                    // the split sdf_fused_kernel used for this round
     const int b = fidx[slot], t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (L.sc[b].phase == PH_DONE) return;
+    const FrameScalars fs0 = L.sc[b];
+    if (fs0.phase == PH_DONE) return;
+    PHASE_MARK(0);
     resident_setup(S, m);
     float* x_eval = L.x_eval + (size_t)b * kParams;
     for (int i = t; i < kParams; i += kResThreads) S.x[i] = x_eval[i];
@@ -647,12 +723,12 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     float* hy = reinterpret_cast<float*>(smem_raw + sizeof(ResidentSmem));
     float* hs = hy + (size_t)L.H * kParams;
     {
-        const int hl = L.sc[b].hist_len;
+        const int hl = fs0.hist_len;
         const float* gy = L.hist_y + (size_t)b * L.H * kParams;
         const float* gs = L.hist_s + (size_t)b * L.H * kParams;
-        const int nvec = (hl == L.H ? L.H : hl) * kParams / 2;       // 8-byte packets (rows are 344 B: 8-byte aligned)
-        const int total = (hl == L.H) ? nvec : hl * kParams / 2;
-        // ring buffer: with hl < H the live rows are [0, hl); when full all rows are live
+        // ring buffer: with hl < H the live rows are [0, hl); when full all rows are live.  8-byte packets
+        // (rows are 344 B: 8-byte aligned)
+        const int total = hl * kParams / 2;
         for (int i = t; i < total; i += kResThreads) {
             const unsigned sy = (unsigned)__cvta_generic_to_shared(hy + 2 * i);
             const unsigned ss = (unsigned)__cvta_generic_to_shared(hs + 2 * i);
@@ -674,24 +750,59 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
             S.lbg1[i] = L.bg[(size_t)b * 2 * kParams + kParams + i];
         }
     }
+    if (warp == 7) {
+        // frame scalars of the penetration term (fitting.py:386-392): total of the sampled values -> loss, the
+        // factor of the listed vertices' adjoint, and the <= 6 box-extreme vertices that carry the gradient through
+        // the box centre (mean of min / max vertex) and scale (0.6 x the largest extent)
+        float a = 0.f;
+        if (lane < 5)
+            for (int p = 0; p < nparts; ++p) a += parts5[((size_t)slot * nparts + p) * 5 + lane];
+        float tot[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) tot[q] = __shfl_sync(0xffffffffu, a, q);
+        if (lane == 0) {
+            const FrameBox fb = box[slot];
+            const float coll_w = lp.coll_loss_weight;
+            const float wsum = coll_w * tot[0];                 // coll_loss_weight * cur_loss.sum() / 1
+            const float cg = 2.f * wsum * coll_w;               // d pen / d (sum of samples)
+            const float inv_s = 1.f / fb.scale;
+            int cnt = 0;
+            if (cg != 0.f) {
+                const float dscale = -cg * tot[4] * inv_s;      // local = (v - c) / s  ->  d local / d s = -local / s
+                for (int c = 0; c < 3; ++c) {
+                    const float dcentre = -cg * tot[1 + c] * inv_s;
+                    float dl = 0.5f * dcentre, dh = 0.5f * dcentre;
+                    if (c == fb.cmax) { dh += 0.6f * dscale; dl -= 0.6f * dscale; }
+                    if (dl != 0.f) { S.ext_n[cnt] = fb.ilo[c]; S.ext_d[3 * cnt] = 0.f; S.ext_d[3 * cnt + 1] = 0.f; S.ext_d[3 * cnt + 2] = 0.f; S.ext_d[3 * cnt + c] = dl; ++cnt; }
+                    if (dh != 0.f) { S.ext_n[cnt] = fb.ihi[c]; S.ext_d[3 * cnt] = 0.f; S.ext_d[3 * cnt + 1] = 0.f; S.ext_d[3 * cnt + 2] = 0.f; S.ext_d[3 * cnt + c] = dh; ++cnt; }
+                }
+            }
+            S.sdf_sc[0] = cg * inv_s;
+            S.sdf_sc[1] = wsum * wsum;                          // fitting.py:391-392
+            S.sdf_sc[2] = (float)cnt;
+        }
+    }
     __syncthreads();
+    PHASE_MARK(1);
     DenseIn din;
     din.vposed = vposed_ws + (size_t)slot * N * 3;
     din.verts = verts_ws + (size_t)slot * N * 3;
-    din.extra_n = list_n + (size_t)slot * N;
-    din.extra_d = list_d + (size_t)slot * N * 3;
-    din.n_extra = list_count[slot];
-    din.pen_loss = pen_loss[slot];
+    din.extra_n = S.ext_n;
+    din.extra_d = S.ext_d;
+    din.n_extra = (int)S.sdf_sc[2];
+    din.pen_loss = S.sdf_sc[1];
     din.Wd = Wd;
-    din.part = (part && sdf_scal[4 * slot] != 0.f) ? part : nullptr;      // frames without penetration have no partials
-    din.nstrips = nstrips; din.ldA = ldA; din.slot = slot;
-    din.strip_active = strip_active; din.ftiles = ftiles;
+    din.factor = S.sdf_sc[0];
+    din.part = (din.factor != 0.f) ? part + (size_t)slot * nparts * kPartFloats : nullptr;   // no penetration: nothing to add
+    din.pflag = pflag + (size_t)slot * nparts;
+    din.nparts = nparts;
     resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
     __syncthreads();
+    PHASE_MARK(23);
     if (warp == 0) {
-        FrameScalars s = L.sc[b];
+        FrameScalars s = fs0;
         LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval,
                     S.lg_new, L.H};
         lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
@@ -718,10 +829,12 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
         if (lane == 0) { L.sc[b] = s; S.fs = s; }
     }
     __syncthreads();
+    PHASE_MARK(24);
     if (S.fs.phase == PH_DONE) return;
     // pose forward of the next trial point -> Phi row and skinning transforms for the next vertex launch
     for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
     __syncthreads();
+    PHASE_MARK(25);
     if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
     else if (t >= 32 && t < 32 + 72) {
         const int jc = t - 32;
@@ -731,29 +844,9 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
         S.J[jc] = a;
     }
     __syncthreads();
-    if (warp == 0) {
-        const float sc = S.x[kOffScale];
-        if (lane < 9) S.Gam[lane] = sc * S.R[lane];
-        if (lane < 3) S.g[lane] = S.J[lane];
-        __syncwarp();
-        for (int j = 1; j < kJoints; ++j) {
-            const int p = m.par.p[j];
-            if (lane < 12) {
-                const float* Gp = &S.Gam[9 * p];
-                if (lane < 9) {
-                    const int r = lane / 3, c = lane % 3;
-                    const float* Rj = &S.R[9 * j];
-                    S.Gam[9 * j + lane] = Gp[3 * r] * Rj[c] + Gp[3 * r + 1] * Rj[3 + c] + Gp[3 * r + 2] * Rj[6 + c];
-                } else {
-                    const int r = lane - 9;
-                    const float r0 = S.J[3 * j] - S.J[3 * p], r1 = S.J[3 * j + 1] - S.J[3 * p + 1], r2 = S.J[3 * j + 2] - S.J[3 * p + 2];
-                    S.g[3 * j + r] = (Gp[3 * r] * r0 + Gp[3 * r + 1] * r1 + Gp[3 * r + 2] * r2) + S.g[3 * p + r];
-                }
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    PHASE_MARK(26);
+    chain_fwd_levels(S);
+    PHASE_MARK(27);
     if (t < kJoints) {
         float A[12];
         make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], A);
@@ -772,6 +865,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
             PhiTc[(size_t)slot * kFeatPad + k] = r;
         }
     }
+    PHASE_MARK(28);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -791,6 +885,25 @@ static ResidentModel make_resident_model(const mvs_ctx* ctx) {
     r.M = m.M; r.gmm_means = m.gmm_means; r.gmm_prec = m.gmm_prec; r.gmm_lognllw = m.gmm_lognllw;
     r.anchor = ctx->ws.anchor; r.anchor_w = ctx->ws.anchor_w;
     r.par = ctx->parents;
+    // level schedule of the tree (parents[j] < j is checked in mvs_set_model)
+    int depth[kJoints];
+    depth[0] = 0;
+    int maxd = 0;
+    for (int j = 1; j < kJoints; ++j) { depth[j] = depth[r.par.p[j]] + 1; if (depth[j] > maxd) maxd = depth[j]; }
+    r.cs.nlev = maxd + 1;
+    int o = 0;
+    for (int L = 0; L <= maxd; ++L) {
+        r.cs.lev_ptr[L] = (unsigned char)o;
+        for (int j = 0; j < kJoints; ++j) if (depth[j] == L) r.cs.lev_j[o++] = (unsigned char)j;
+    }
+    for (int L = maxd + 1; L <= kJoints; ++L) r.cs.lev_ptr[L] = (unsigned char)o;
+    o = 0;
+    for (int p = 0; p < kJoints; ++p) {
+        r.cs.ch_ptr[p] = (unsigned char)o;
+        for (int j = kJoints - 1; j >= 1; --j) if (r.par.p[j] == p) r.cs.ch_j[o++] = (unsigned char)j;
+    }
+    r.cs.ch_ptr[kJoints] = (unsigned char)o;
+    for (int q = o; q < kJoints; ++q) r.cs.ch_j[q] = 0;
     return r;
 }
 
@@ -842,8 +955,7 @@ bool hybrid_available(const mvs_ctx* ctx) {
     return resident_supported(ctx) && sdf_on;
 }
 
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstrips,
-                      cudaStream_t st) {
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& dm = ctx->m;
     const LbfgsState& L = *static_cast<const LbfgsState*>(lbfgs_state);
@@ -856,11 +968,20 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
     MVS_LAUNCH(ctx, KID_FRAME_STEP, st,
                frame_step_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, ctx->loss, cfg, L, params_dev,
                                                                  w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
-                                                                 w.verts, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count, w.pen_loss,
-                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA, nstrips > 0 ? w.part : nullptr, nstrips,
-                                                                 w.sdf_scal, w.strip_active, (w.B + kTileF - 1) / kTileF));
+                                                                 w.verts, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
+                                                                 reinterpret_cast<const FrameBox*>(w.sdf_box),
+                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }
 
 }  // namespace mvs
+
+#ifdef MVS_PHASE_DBG
+extern "C" int mvs_debug_clocks(long long* out, int n) {       // debug builds only; not part of the ABI
+    long long h[64];
+    if (cudaMemcpyFromSymbol(h, mvs::g_phase_clk, sizeof(h)) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
+    return 0;
+}
+#endif

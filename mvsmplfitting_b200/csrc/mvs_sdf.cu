@@ -157,14 +157,6 @@ int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, c
 
 // ---------------------------------------------------------------------------------- fused term for the closure
 constexpr int kBoxThreads = 256;
-struct FrameBox {                 // per frame
-    float centre[3];
-    float scale;
-    int ilo[3], ihi[3];
-    int cmax;                     // coordinate with the largest extent
-    float pad;
-};
-
 __global__ void __launch_bounds__(kBoxThreads)
 sdf_bbox_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,
                 const int* __restrict__ na_ptr, int N, FrameBox* __restrict__ box) {
@@ -342,250 +334,74 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
     o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
 }
 
-// ---------------------------------------------------------------------------------- one CTA per frame (dense regime)
-// bbox + sample + gradient of the whole term for ONE frame, then an ordered compaction of the vertices whose
-// penetration gradient is non-zero (with the as-written semantics that is a handful of vertices in the shadow of
-// triangle 0 plus the six box-extreme vertices).  Feeds frame_step_kernel (mvs_resident.cu).
-constexpr int kSdfFrameThreads = 256;
+// ---------------------------------------------------------------------------------- dense regime, v4: fused adjoint
+// sdf_fused_kernel: P CTAs per frame, 1024 vertices each.  Per CTA: fold the skinning kernel's box partials (all
+// threads), sample phi at the <= 8 voxels around each vertex, compact the vertices with a non-zero sample gradient
+// (deterministic order: warp, pass, lane) and -- because with the as-written semantics that list holds a handful of
+// vertices -- run the adjoint of the vertex stage for exactly those vertices right here:
+//     d v_posed = T_3x3^T g,   dA_j += W[n,j] [g (x) v_posed | g],   dPhi += d v_posed . Qk[rows of n]
+// with g = d value / d local (UNIT scale; the frame factor cg/scale is linear and applied by frame_step once the
+// frame's total is known).
+constexpr int kSdfFThreads = 256;
+constexpr int kSdfFMaxPasses = 4;
+constexpr int kSdfFVerts = kSdfFThreads * kSdfFMaxPasses;    // <= 1024 vertices per CTA (sdf_passes_for)
+constexpr int kSdfFChunk = 128;                              // list entries per adjoint pass
 
-__global__ void __launch_bounds__(kSdfFrameThreads)
-sdf_frame_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,
-                 const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc, int N,
-                 const int* __restrict__ faces, int num_faces, int G, float coll_w, float* __restrict__ gcoord,
-                 int* __restrict__ list_n, float* __restrict__ list_d, int* __restrict__ list_count,
-                 float* __restrict__ pen_loss) {
-    const int slot = blockIdx.x;
-    if (slot >= *na_ptr) return;
-    const int b = fidx[slot], t = threadIdx.x;
+__device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, const int* __restrict__ faces,
+                                              const float* __restrict__ vf, const float* tr, const FrameBox& fb,
+                                              const float* tri0) {
+    if (num_faces == 1) {
+        if (!ray_hits(c, tri0, tri0 + 3, tri0 + 6)) return 0.f;
+        return triangle_distance(c, tri0, tri0 + 3, tri0 + 6);
+    }
+    int hits = 0;
+    float min_d = 1000.f;
+    for (int f = 0; f < num_faces; ++f) {
+        float p[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+            p[r] = ((vf[3 * faces[3 * f + r / 3] + r % 3] + tr[r % 3]) - fb.centre[r % 3]) / fb.scale;
+        const float dd = triangle_distance(c, p, p + 3, p + 6);
+        if (dd < min_d) min_d = dd;
+        if (ray_hits(c, p, p + 3, p + 6)) ++hits;
+    }
+    return (hits % 2 == 0) ? 0.f : min_d;
+}
+
+__global__ void __launch_bounds__(kSdfFThreads)
+sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vposed, const float* __restrict__ x,
+                 const int* __restrict__ fidx, const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc,
+                 int N, int nbox, const float* __restrict__ bboxp, const int* __restrict__ faces, int num_faces, int G,
+                 const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w,
+                 int KW, const float* __restrict__ Wd, const float* __restrict__ Qk, float* __restrict__ parts5,
+                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout) {
+    const int slot = blockIdx.y, pidx = blockIdx.x;
+    const int na = *na_ptr;
+    if (slot >= na) return;
+    const int passes = sdf_passes_for(na, N), nparts = (N + kSdfFThreads * passes - 1) / (kSdfFThreads * passes);
+    if (pidx >= nparts) return;
+    const int b = fidx[slot], t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (sc && sc[b].phase == PH_DONE) return;
     const float* vf = verts + (size_t)slot * N * 3;
     const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
                          x[(size_t)b * kParams + kOffTransl + 2]};
-    __shared__ float s_f[6][kSdfFrameThreads];
-    __shared__ int s_i[6][kSdfFrameThreads];
     __shared__ FrameBox s_box;
-    __shared__ float tri0[9];
-    __shared__ float s_tot[8];
-    __shared__ int s_cnt[kSdfFrameThreads + 1];
-    // ---- bounding box with arg-extrema (ties -> lowest vertex index)
+    __shared__ float s_wb[8][6];
+    __shared__ int s_wi[8][6];
+    __shared__ float tri0[9], cone[12], ctab[256];
+    __shared__ float s_red[8][5];
+    __shared__ int s_wcnt[8], s_woff[9];
+    __shared__ int seg_n[kSdfFVerts];                 // per-warp segments: warp w owns [128 w, 128 w + 128)
+    __shared__ float seg_g[kSdfFVerts * 3];
+    __shared__ float sA[kSkinFloats];
+    __shared__ int c_n[kSdfFChunk];
+    __shared__ float c_dv[kSdfFChunk * 3], c_vp[kSdfFChunk * 3], c_dvp[kSdfFChunk * 3];
+    __shared__ float s_dphi[8][kFeatPad];
+    // ---- bounding box: every thread takes one partial, warps fold with shuffles (ties -> lowest vertex index)
     {
         float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-        int ilo[3] = {0, 0, 0}, ihi[3] = {0, 0, 0};
-        for (int n = t; n < N; n += kSdfFrameThreads) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = vf[3 * n + c] + tr[c];
-                if (v < lo[c]) { lo[c] = v; ilo[c] = n; }
-                if (v > hi[c]) { hi[c] = v; ihi[c] = n; }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { s_f[c][t] = lo[c]; s_f[3 + c][t] = hi[c]; s_i[c][t] = ilo[c]; s_i[3 + c][t] = ihi[c]; }
-        __syncthreads();
-        for (int o = kSdfFrameThreads / 2; o > 0; o >>= 1) {
-            if (t < o) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float l2 = s_f[c][t + o]; const int il2 = s_i[c][t + o];
-                    if (l2 < s_f[c][t] || (l2 == s_f[c][t] && il2 < s_i[c][t])) { s_f[c][t] = l2; s_i[c][t] = il2; }
-                    const float h2 = s_f[3 + c][t + o]; const int ih2 = s_i[3 + c][t + o];
-                    if (h2 > s_f[3 + c][t] || (h2 == s_f[3 + c][t] && ih2 < s_i[3 + c][t])) { s_f[3 + c][t] = h2; s_i[3 + c][t] = ih2; }
-                }
-            }
-            __syncthreads();
-        }
-        if (t == 0) {
-            FrameBox fb;
-            float ext = -1.f;
-            fb.cmax = 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                fb.centre[c] = (s_f[c][0] + s_f[3 + c][0]) / 2.f;
-                fb.ilo[c] = s_i[c][0]; fb.ihi[c] = s_i[3 + c][0];
-                const float e = s_f[3 + c][0] - s_f[c][0];
-                if (e > ext) { ext = e; fb.cmax = c; }
-            }
-            fb.scale = 0.6f * ext;
-            fb.pad = 0.f;
-            s_box = fb;
-        }
-        __syncthreads();
-    }
-    const FrameBox fb = s_box;
-    if (t < 9) tri0[t] = ((vf[3 * faces[t / 3] + t % 3] + tr[t % 3]) - fb.centre[t % 3]) / fb.scale;
-    __syncthreads();
-    // Conservative cull for the as-written semantics: a voxel's ray towards q0 = (-1,-1,-1) can only hit triangle 0
-    // if the voxel lies in the (double) cone with apex q0 spanned by the triangle.  w . n_i of the three edge planes
-    // must not have strictly mixed signs; a 1e-4 relative margin keeps every borderline voxel for the exact
-    // Moeller-Trumbore test, so the sampled values are unchanged.
-    __shared__ float cone[12];
-    if (t < 3) {
-        const float* a = &tri0[3 * t];
-        const float* bb = &tri0[3 * ((t + 1) % 3)];
-        const float ea[3] = {a[0] + 1.f, a[1] + 1.f, a[2] + 1.f}, eb[3] = {bb[0] + 1.f, bb[1] + 1.f, bb[2] + 1.f};
-        const float nx = ea[1] * eb[2] - ea[2] * eb[1], ny = ea[2] * eb[0] - ea[0] * eb[2], nz = ea[0] * eb[1] - ea[1] * eb[0];
-        cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
-    }
-    __syncthreads();
-    const bool cull = (num_faces == 1);
-    // ---- trilinear samples and coordinate gradients
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    float* gof = gcoord + (size_t)slot * N * 3;
-    for (int n = t; n < N; n += kSdfFrameThreads) {
-        float loc[3], w1[3];
-        int i0[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            loc[c] = ((vf[3 * n + c] + tr[c]) - fb.centre[c]) / fb.scale;
-            const float ix = ((loc[c] + 1.f) * G - 1.f) / 2.f;
-            const float fl = floorf(ix);
-            i0[c] = (int)fl;
-            w1[c] = ix - fl;
-        }
-        float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int corner = 0; corner < 8; ++corner) {
-            const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
-            const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
-            if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
-            if (cull) {
-                float cc[3];
-                voxel_centre(ii, jj, kk, G, cc);
-                const float wv[3] = {cc[0] + 1.f, cc[1] + 1.f, cc[2] + 1.f};
-                const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) * 1e-4f;
-                const float s1 = wv[0] * cone[0] + wv[1] * cone[1] + wv[2] * cone[2];
-                const float s2 = wv[0] * cone[4] + wv[1] * cone[5] + wv[2] * cone[6];
-                const float s3 = wv[0] * cone[8] + wv[1] * cone[9] + wv[2] * cone[10];
-                const float m1 = wn * cone[3], m2 = wn * cone[7], m3 = wn * cone[11];
-                const bool neg = (s1 < -m1) || (s2 < -m2) || (s3 < -m3);
-                const bool pos = (s1 > m1) || (s2 > m2) || (s3 > m3);
-                if (neg && pos) continue;                    // strictly outside the cone: phi == 0 exactly
-            }
-            const float p = voxel_phi_frame(ii, jj, kk, G, num_faces, faces, vf, tr, fb, tri0);
-            if (p == 0.f) continue;
-            const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
-            val += p * wx * wy * wz;
-            dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
-            dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
-            dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
-        }
-        float gdl = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { const float gcv = dix[c] * (0.5f * G); gof[3 * n + c] = gcv; acc[1 + c] += gcv; gdl += gcv * loc[c]; }
-        acc[0] += val;
-        acc[4] += gdl;
-    }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) s_f[q][t] = acc[q];
-    __syncthreads();
-    for (int o = kSdfFrameThreads / 2; o > 0; o >>= 1) {
-        if (t < o) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) s_f[q][t] += s_f[q][t + o];
-        }
-        __syncthreads();
-    }
-    if (t < 5) s_tot[t] = s_f[t][0];
-    __syncthreads();
-    const float wsum = coll_w * s_tot[0];
-    if (t == 0) pen_loss[slot] = wsum * wsum;
-    const float cg = 2.f * wsum * coll_w;
-    const float inv_s = 1.f / fb.scale;
-    const float dscale = -cg * s_tot[4] * inv_s;
-    // ---- d pen / d vertex, ordered compaction of the non-zeros (count pass, exclusive scan, write pass)
-    auto grad_of = [&](int n, float* d) {
-        d[0] = cg * gof[3 * n] * inv_s; d[1] = cg * gof[3 * n + 1] * inv_s; d[2] = cg * gof[3 * n + 2] * inv_s;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float dcentre = -cg * s_tot[1 + c] * inv_s;
-            if (n == fb.ilo[c]) d[c] += 0.5f * dcentre;
-            if (n == fb.ihi[c]) d[c] += 0.5f * dcentre;
-            if (c == fb.cmax) {
-                if (n == fb.ihi[c]) d[c] += 0.6f * dscale;
-                if (n == fb.ilo[c]) d[c] -= 0.6f * dscale;
-            }
-        }
-    };
-    int cnt = 0;
-    if (cg != 0.f) {
-        for (int n = t; n < N; n += kSdfFrameThreads) {
-            float d[3];
-            grad_of(n, d);
-            cnt += (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f);
-        }
-    }
-    s_cnt[t + 1] = cnt;
-    if (t == 0) s_cnt[0] = 0;
-    __syncthreads();
-    if (t == 0) for (int i = 1; i <= kSdfFrameThreads; ++i) s_cnt[i] += s_cnt[i - 1];
-    __syncthreads();
-    if (t == 0) list_count[slot] = s_cnt[kSdfFrameThreads];
-    if (cnt > 0) {
-        int o = s_cnt[t];
-        int* ln = list_n + (size_t)slot * N;
-        float* ld = list_d + (size_t)slot * N * 3;
-        for (int n = t; n < N; n += kSdfFrameThreads) {
-            float d[3];
-            grad_of(n, d);
-            if (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f) { ln[o] = n; ld[3 * o] = d[0]; ld[3 * o + 1] = d[1]; ld[3 * o + 2] = d[2]; ++o; }
-        }
-    }
-}
-
-int launch_sdf_frame(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
-    Workspace& w = ctx->ws;
-    const DevModel& m = ctx->m;
-    const LossParams& lp = ctx->loss;
-    const int B = w.B, N = m.N;
-    if (!w.sdf_gcoord) {
-        int rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
-    }
-    if (!w.sdf_list_n) {
-        int rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_list_n, (size_t)B * N))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_list_d, (size_t)B * N * 3))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_list_count, (size_t)B))) return rc;
-    }
-    MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
-               sdf_frame_kernel<<<B, kSdfFrameThreads, 0, st>>>(w.verts, x_dev, w.fidx, w.na,
-                                                                static_cast<const FrameScalars*>(frame_scalars), N, m.faces,
-                                                                lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, lp.coll_loss_weight,
-                                                                w.sdf_gcoord, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count,
-                                                                w.pen_loss));
-    MVS_CUDA_OK(ctx, cudaGetLastError());
-    return MVS_OK;
-}
-
-// ---------------------------------------------------------------------------------- dense regime, v3: P CTAs per frame
-// sdf_part_kernel: bounding box from the per-tile partials the tensor-core vertex kernel wrote, then trilinear
-// samples + coordinate gradients for this CTA's slice of the vertices, per-part sums and per-tile activity flags.
-// sdf_reduce_kernel: one warp per frame folds the parts into loss, d pen/d sample, the factor of the dense vertex
-// gradient, and the (<= 6) box-extreme vertices that carry the gradient through the box centre / scale.
-constexpr int kSdfPartThreads = 256;
-constexpr int kSdfTilesPerPart = 7;           // 224 vertices per CTA (one pass of 256 threads)
-
-__global__ void __launch_bounds__(kSdfPartThreads)
-sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, const int* __restrict__ fidx,
-                const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc, int N, int ntiles, int nbox,
-                const float* __restrict__ bboxp, const int* __restrict__ faces, int num_faces, int G,
-                float* __restrict__ gcoord, float* __restrict__ parts, int nparts, FrameBox* __restrict__ boxout,
-                unsigned char* __restrict__ tileflag) {
-    const int slot = blockIdx.y, part = blockIdx.x;
-    if (slot >= *na_ptr) return;
-    const int b = fidx[slot], t = threadIdx.x, lane = t & 31;
-    if (sc && sc[b].phase == PH_DONE) return;
-    const float* vf = verts + (size_t)slot * N * 3;
-    const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
-                         x[(size_t)b * kParams + kOffTransl + 2]};
-    __shared__ float s_f[6][kSdfPartThreads];
-    __shared__ FrameBox s_box;
-    __shared__ float tri0[9];
-    __shared__ float cone[12];
-    if (t < 32) {       // warp 0 folds the per-chunk box partials with shuffles (ties -> lowest vertex index)
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
         int ilo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, ihi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-        for (int tl = t; tl < nbox; tl += 32) {
+        for (int tl = t; tl < nbox; tl += kSdfFThreads) {
             const float* bp = bboxp + ((size_t)slot * nbox + tl) * 12;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -605,25 +421,39 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
                 if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
             }
         }
-        if (t == 0) {
-            FrameBox fb;
-            float ext = -1.f;
-            fb.cmax = 0;
+        if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
-                // arg-indices commute with the translation (body_models_scale.py:403)
-                const float lc = lo[c] + tr[c], hc = hi[c] + tr[c];
-                fb.centre[c] = (lc + hc) / 2.f;
-                fb.ilo[c] = ilo[c]; fb.ihi[c] = ihi[c];
-                const float e = hc - lc;
-                if (e > ext) { ext = e; fb.cmax = c; }
-            }
-            fb.scale = 0.6f * ext;
-            fb.pad = 0.f;
-            s_box = fb;
-            if (part == 0) boxout[slot] = fb;
+            for (int c = 0; c < 3; ++c) { s_wb[warp][c] = lo[c]; s_wb[warp][3 + c] = hi[c]; s_wi[warp][c] = ilo[c]; s_wi[warp][3 + c] = ihi[c]; }
         }
+        if (t < G && t < 256) ctab[t] = (float)(-1 + (t + 0.5) * (double)(float)(2. / (G - 1)));   // voxel_centre, tabulated
+    }
+    __syncthreads();
+    if (t == 0) {
+        FrameBox fb;
+        float ext = -1.f;
+        fb.cmax = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float lo = s_wb[0][c], hi = s_wb[0][3 + c];
+            int ilo = s_wi[0][c], ihi = s_wi[0][3 + c];
+            for (int w2 = 1; w2 < 8; ++w2) {
+                const float l2 = s_wb[w2][c], h2 = s_wb[w2][3 + c];
+                const int il2 = s_wi[w2][c], ih2 = s_wi[w2][3 + c];
+                if (l2 < lo || (l2 == lo && il2 < ilo)) { lo = l2; ilo = il2; }
+                if (h2 > hi || (h2 == hi && ih2 < ihi)) { hi = h2; ihi = ih2; }
+            }
+            // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
+            // arg-indices commute with the translation (body_models_scale.py:403)
+            const float lc = lo + tr[c], hc = hi + tr[c];
+            fb.centre[c] = (lc + hc) / 2.f;
+            fb.ilo[c] = ilo; fb.ihi[c] = ihi;
+            const float e = hc - lc;
+            if (e > ext) { ext = e; fb.cmax = c; }
+        }
+        fb.scale = 0.6f * ext;
+        fb.pad = 0.f;
+        s_box = fb;
+        if (pidx == 0) boxout[slot] = fb;
     }
     __syncthreads();
     const FrameBox fb = s_box;
@@ -637,15 +467,16 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
         cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
     }
     __syncthreads();
+    // ---- samples
     const bool cull = (num_faces == 1);
+    const bool tab = (G <= 256);
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    float* gof = gcoord + (size_t)slot * N * 3;
-    const int n_begin = part * kSdfTilesPerPart * kTileV;
-    const int n_end = min(N, n_begin + kSdfTilesPerPart * kTileV);
-    for (int n0 = n_begin; n0 < n_end; n0 += kSdfPartThreads) {        // a warp covers one 32-vertex tile per pass
-        const int n = n0 + t;
-        bool nz = false;
-        if (n < n_end) {
+    int wcnt = 0;
+    const int n_base = pidx * (kSdfFThreads * passes) + warp * (32 * passes);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int n = n_base + pass * 32 + lane;
+        float gcv[3] = {0.f, 0.f, 0.f};
+        if (n < N) {
             float loc[3], w1[3];
             int i0[3];
 #pragma unroll
@@ -662,9 +493,10 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
                 const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
                 const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
                 if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+                float cc[3];
+                if (tab) { cc[0] = ctab[ii]; cc[1] = ctab[jj]; cc[2] = ctab[kk]; }
+                else voxel_centre(ii, jj, kk, G, cc);
                 if (cull) {
-                    float cc[3];
-                    voxel_centre(ii, jj, kk, G, cc);
                     const float wv[3] = {cc[0] + 1.f, cc[1] + 1.f, cc[2] + 1.f};
                     const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) * 1e-4f;
                     const float s1 = wv[0] * cone[0] + wv[1] * cone[1] + wv[2] * cone[2];
@@ -675,7 +507,7 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
                     const bool pos = (s1 > m1) || (s2 > m2) || (s3 > m3);
                     if (neg && pos) continue;
                 }
-                const float p = voxel_phi_frame(ii, jj, kk, G, num_faces, faces, vf, tr, fb, tri0);
+                const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri0);
                 if (p == 0.f) continue;
                 const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
                 val += p * wx * wy * wz;
@@ -686,104 +518,153 @@ sdf_part_kernel(const float* __restrict__ verts, const float* __restrict__ x, co
             float gdl = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float gcv = dix[c] * (0.5f * G);
-                gof[3 * n + c] = gcv; acc[1 + c] += gcv; gdl += gcv * loc[c];
-                nz = nz || (gcv != 0.f);
+                gcv[c] = dix[c] * (0.5f * G);
+                acc[1 + c] += gcv[c]; gdl += gcv[c] * loc[c];
             }
             acc[0] += val;
             acc[4] += gdl;
         }
-        const unsigned any = __ballot_sync(0xffffffffu, nz);
-        const int tile = (n0 + (t & ~31)) / kTileV;
-        if (lane == 0 && tile < ntiles && n0 + (t & ~31) < n_end) tileflag[(size_t)slot * ntiles + tile] = any ? 1 : 0;
-    }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) s_f[q][t] = acc[q];
-    __syncthreads();
-    for (int o = kSdfPartThreads / 2; o > 0; o >>= 1) {
-        if (t < o) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) s_f[q][t] += s_f[q][t + o];
+        const bool nz = (gcv[0] != 0.f) || (gcv[1] != 0.f) || (gcv[2] != 0.f);
+        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        if (nz) {
+            const int pos = warp * (32 * kSdfFMaxPasses) + wcnt + __popc(mask & ((1u << lane) - 1u));
+            seg_n[pos] = n; seg_g[3 * pos] = gcv[0]; seg_g[3 * pos + 1] = gcv[1]; seg_g[3 * pos + 2] = gcv[2];
         }
-        __syncthreads();
+        wcnt += __popc(mask);
     }
-    if (t < 5) parts[((size_t)slot * nparts + part) * 5 + t] = s_f[t][0];
-}
-
-// scal[slot] = {cg / scale (factor of the dense vertex gradient), pen loss, ...}; box-extreme list (<= 6 entries)
-__global__ void __launch_bounds__(32)
-sdf_reduce_kernel(const int* __restrict__ fidx, const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc,
-                  const float* __restrict__ parts, int nparts, const FrameBox* __restrict__ box, float coll_w, int N,
-                  float* __restrict__ scal, float* __restrict__ pen_loss, int* __restrict__ list_n,
-                  float* __restrict__ list_d, int* __restrict__ list_count) {
-    const int slot = blockIdx.x;
-    if (slot >= *na_ptr) return;
-    const int b = fidx[slot], lane = threadIdx.x;
-    if (sc && sc[b].phase == PH_DONE) return;
-    float tot[5];
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-        float a = 0.f;
-        for (int p = lane; p < nparts; p += 32) a += parts[((size_t)slot * nparts + p) * 5 + q];
+        float a = acc[q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        tot[q] = a;
+        if (lane == 0) s_red[warp][q] = a;
     }
-    if (lane != 0) return;
-    const FrameBox fb = box[slot];
-    const float wsum = coll_w * tot[0];
-    const float cg = 2.f * wsum * coll_w;
-    const float inv_s = 1.f / fb.scale;
-    pen_loss[slot] = wsum * wsum;
-    scal[(size_t)slot * 4] = cg * inv_s;
-    int cnt = 0;
-    if (cg != 0.f) {
-        const float dscale = -cg * tot[4] * inv_s;
-        int* ln = list_n + (size_t)slot * N;
-        float* ld = list_d + (size_t)slot * N * 3;
-        for (int c = 0; c < 3; ++c) {
-            const float dcentre = -cg * tot[1 + c] * inv_s;
-            float dl = 0.5f * dcentre, dh = 0.5f * dcentre;
-            if (c == fb.cmax) { dh += 0.6f * dscale; dl -= 0.6f * dscale; }
-            if (dl != 0.f) { ln[cnt] = fb.ilo[c]; ld[3 * cnt] = 0.f; ld[3 * cnt + 1] = 0.f; ld[3 * cnt + 2] = 0.f; ld[3 * cnt + c] = dl; ++cnt; }
-            if (dh != 0.f) { ln[cnt] = fb.ihi[c]; ld[3 * cnt] = 0.f; ld[3 * cnt + 1] = 0.f; ld[3 * cnt + 2] = 0.f; ld[3 * cnt + c] = dh; ++cnt; }
+    if (lane == 0) s_wcnt[warp] = wcnt;
+    __syncthreads();
+    if (t < 5) {
+        float a = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) a += s_red[w2][t];
+        parts5[((size_t)slot * nparts + pidx) * 5 + t] = a;
+    }
+    if (t == 0) {
+        int o = 0;
+        for (int w2 = 0; w2 < 8; ++w2) { s_woff[w2] = o; o += s_wcnt[w2]; }
+        s_woff[8] = o;
+        pflag[(size_t)slot * nparts + pidx] = o > 0 ? 1 : 0;
+    }
+    __syncthreads();
+    const int total = s_woff[8];
+    if (total == 0) return;
+    // ---- adjoint of the vertex stage for the listed vertices (unit frame factor)
+    for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
+    float accA0 = 0.f, accA1 = 0.f;
+    float accP[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // d Phi[lane + 32 i], this warp's share of the columns
+    for (int e0 = 0; e0 < total; e0 += kSdfFChunk) {
+        const int cnt = min(kSdfFChunk, total - e0);
+        __syncthreads();
+        if (t < cnt) {
+            // entry (e0 + t) of the concatenated list -> (warp segment, offset)
+            const int ge = e0 + t;
+            int w2 = 0;
+#pragma unroll
+            for (int q = 1; q < 8; ++q) w2 += (ge >= s_woff[q]) ? 1 : 0;
+            const int src = w2 * (32 * kSdfFMaxPasses) + (ge - s_woff[w2]);
+            const int n = seg_n[src];
+            c_n[t] = n;
+            const float d0 = seg_g[3 * src], d1 = seg_g[3 * src + 1], d2 = seg_g[3 * src + 2];
+            float Gm[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) Gm[c] = 0.f;
+            for (int e = 0; e < KW; ++e) {
+                const float w = ell_w[(size_t)n * KW + e];
+                if (w != 0.f) {
+                    const float* Aj = &sA[12 * ell_j[(size_t)n * KW + e]];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Gm[3 * r + c] = fmaf(w, Aj[4 * r + c], Gm[3 * r + c]);
+                }
+            }
+            c_dv[3 * t] = d0; c_dv[3 * t + 1] = d1; c_dv[3 * t + 2] = d2;
+            c_dvp[3 * t] = Gm[0] * d0 + Gm[3] * d1 + Gm[6] * d2;
+            c_dvp[3 * t + 1] = Gm[1] * d0 + Gm[4] * d1 + Gm[7] * d2;
+            c_dvp[3 * t + 2] = Gm[2] * d0 + Gm[5] * d1 + Gm[8] * d2;
+            const float* vpn = vposed + ((size_t)slot * N + n) * 3;
+            c_vp[3 * t] = vpn[0]; c_vp[3 * t + 1] = vpn[1]; c_vp[3 * t + 2] = vpn[2];
+        }
+        __syncthreads();
+        {   // dA: thread t owns entry t (and 256 + t for t < 32)
+            const int j0 = t / 12, r0 = (t % 12) / 4, cc0 = t % 4;
+            const int e1 = t + kSdfFThreads, j1 = e1 / 12, r1 = (e1 % 12) / 4, cc1 = e1 % 4;
+            const bool two = t < kSkinFloats - kSdfFThreads;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float* wrow = Wd + (size_t)c_n[i] * kJoints;
+                const float w0 = __ldg(wrow + j0);
+                const float w1v = two ? __ldg(wrow + j1) : 0.f;
+                if (w0 != 0.f) {
+                    const float wd = w0 * c_dv[3 * i + r0];
+                    accA0 = (cc0 < 3) ? fmaf(wd, c_vp[3 * i + cc0], accA0) : accA0 + wd;
+                }
+                if (w1v != 0.f) {
+                    const float wd = w1v * c_dv[3 * i + r1];
+                    accA1 = (cc1 < 3) ? fmaf(wd, c_vp[3 * i + cc1], accA1) : accA1 + wd;
+                }
+            }
+        }
+        // d Phi: a warp takes every 8th column and reads its whole Qk row (7 coalesced loads per lane, two columns =
+        // 14 independent loads in flight); the eight warps' shares are folded in a fixed order below
+        for (int col = warp; col < 3 * cnt; col += 16) {
+            const int colb = col + 8;
+            const bool hb = colb < 3 * cnt;
+            const float* ra = Qk + (size_t)(3 * c_n[col / 3] + col % 3) * kFeatPad + lane;
+            const float* rb = Qk + (size_t)(3 * c_n[(hb ? colb : col) / 3] + (hb ? colb : col) % 3) * kFeatPad + lane;
+            float qa[7], qb[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { qa[i] = __ldg(ra + 32 * i); qb[i] = __ldg(rb + 32 * i); }
+            const float da = c_dvp[col], db = hb ? c_dvp[colb] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { accP[i] = fmaf(da, qa[i], accP[i]); accP[i] = fmaf(db, qb[i], accP[i]); }
         }
     }
-    list_count[slot] = cnt;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) s_dphi[warp][lane + 32 * i] = accP[i];
+    __syncthreads();
+    float* o = part + ((size_t)slot * nparts + pidx) * kPartFloats;
+    o[t] = accA0;
+    if (t < kSkinFloats - kSdfFThreads) o[kSdfFThreads + t] = accA1;
+    if (t < kFeatPad) {
+        float a = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) a += s_dphi[w2][t];
+        o[kSkinFloats + t] = a;
+    }
 }
 
-int launch_sdf_parts(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
+int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;
     const LossParams& lp = ctx->loss;
     const int B = w.B, N = m.N;
-    const int ntiles = (N + kTileV - 1) / kTileV;
-    const int nparts = (ntiles + kSdfTilesPerPart - 1) / kSdfTilesPerPart;
+    const int nparts = sdf_parts_for(1, N);           // the finest split (buffers, grid); the kernel picks by *na_ptr
     int rc;
-    if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
-    if (!w.sdf_list_n) {
-        if ((rc = dev_alloc(ctx, &w.sdf_list_n, (size_t)B * N))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_list_d, (size_t)B * N * 3))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_list_count, (size_t)B))) return rc;
+    if (!w.sdf_parts5) {
+        if ((rc = dev_alloc(ctx, &w.sdf_parts5, (size_t)B * nparts * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_part, (size_t)B * nparts * kPartFloats))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_pflag, (size_t)B * nparts))) return rc;
     }
-    if (!w.sdf_parts) {
-        if ((rc = dev_alloc(ctx, &w.sdf_parts, (size_t)B * nparts * 5))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_scal, (size_t)B * 4))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_tileflag, (size_t)B * ntiles))) return rc;
+    if (!w.sdf_box) {
         unsigned char* raw = nullptr;
         if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
         w.sdf_box = raw;
     }
-    const FrameScalars* sc = static_cast<const FrameScalars*>(frame_scalars);
     dim3 g(nparts, B);
     MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
-               sdf_part_kernel<<<g, kSdfPartThreads, 0, st>>>(w.verts, x_dev, w.fidx, w.na, sc, N, ntiles, (N + 63) / 64, w.bboxp, m.faces,
-                                                              lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, w.sdf_gcoord, w.sdf_parts,
-                                                              nparts, reinterpret_cast<FrameBox*>(w.sdf_box), w.sdf_tileflag));
-    MVS_LAUNCH(ctx, KID_SDF_FINALIZE, st,
-               sdf_reduce_kernel<<<B, 32, 0, st>>>(w.fidx, w.na, sc, w.sdf_parts, nparts,
-                                                   reinterpret_cast<const FrameBox*>(w.sdf_box), lp.coll_loss_weight, N,
-                                                   w.sdf_scal, w.pen_loss, w.sdf_list_n, w.sdf_list_d, w.sdf_list_count));
+               sdf_fused_kernel<<<g, kSdfFThreads, 0, st>>>(w.verts, w.vposed, x_dev, w.fidx, w.na,
+                                                            static_cast<const FrameScalars*>(frame_scalars), N, (N + 63) / 64,
+                                                            w.bboxp, m.faces, lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, w.At, w.ldA,
+                                                            m.ell_j, m.ell_w, m.KW, m.Wd, m.Qk, w.sdf_parts5, w.sdf_part,
+                                                            w.sdf_pflag, reinterpret_cast<FrameBox*>(w.sdf_box)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

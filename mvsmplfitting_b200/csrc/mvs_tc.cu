@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include "mvs_internal.cuh"
 
 namespace mvs {
@@ -104,7 +105,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
-                        const int* __restrict__ na_ptr, int tiles_per_cta, int ntiles, float* __restrict__ poffT,
+                        const int* __restrict__ na_ptr, int cta_slots, int ntiles, float* __restrict__ poffT,
                         int* __restrict__ err_flag) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,6 +122,12 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int na = *na_ptr;
     const int m0 = blockIdx.y * kTcBM;
     if (m0 >= na) return;
+    // the launch provides cta_slots CTAs per M tile of the FULL batch; with fewer active M tiles the survivors
+    // spread the vertex tiles over all of them (the tail of a stage runs one M tile on every SM)
+    const int active_m = (na + kTcBM - 1) / kTcBM;
+    const int ctas_n = max(1, min((int)gridDim.x, cta_slots / active_m));
+    if ((int)blockIdx.x >= ctas_n) return;
+    const int tiles_per_cta = (ntiles + ctas_n - 1) / ctas_n;
     const int tile_begin = blockIdx.x * tiles_per_cta;
     const int tile_end = min(tile_begin + tiles_per_cta, ntiles);
     if (tile_begin >= tile_end) return;
@@ -232,7 +239,7 @@ constexpr size_t kSkinSmem =
 __global__ void __launch_bounds__(kSkinThreads)
 skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const float* __restrict__ Phi,
             const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW,
-            int N, const int* __restrict__ na_ptr, float* __restrict__ vposed, float* __restrict__ verts,
+            int N, const int* __restrict__ na_ptr, int cta_slots, float* __restrict__ vposed, float* __restrict__ verts,
             float* __restrict__ bboxp) {
     extern __shared__ __align__(16) float sk[];
     float* As = sk;                                   // [288][32]
@@ -244,83 +251,109 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
     const int na = *na_ptr;
     const int f0 = blockIdx.y * 32;
     if (f0 >= na) return;
-    const int v0 = blockIdx.x * kSkinV;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slotc = min(f0 + lane, na - 1);
+    // chunks per CTA from the number of ACTIVE frame groups: one chunk each while the active CTAs fit in one wave
+    // (latency at the tail of a stage), several once they do not (the 36 KB of transforms are then loaded once)
+    const int nchunks = (N + kSkinV - 1) / kSkinV;
+    const int per_cta = (nchunks * ((na + 31) / 32) + cta_slots - 1) / cta_slots;
+    const int nx = (nchunks + per_cta - 1) / per_cta;
+    if ((int)blockIdx.x >= nx) return;
+    // the 32 frames' transforms and shape coefficients are loaded once and reused for every vertex chunk of this CTA
     for (int e = tid; e < kSkinFloats * 32; e += kSkinThreads) As[e] = At[(size_t)(e >> 5) * ldA + min(f0 + (e & 31), na - 1)];
     for (int e = tid; e < kBetas * 32; e += kSkinThreads)
         Bs[e] = Phi[(size_t)min(f0 + (e & 31), na - 1) * kFeatPad + kPoseBasis + (e >> 5)];
-    for (int e = tid; e < kSkinV * 33; e += kSkinThreads) Sts[e] = (v0 * 33 + e < N * 33) ? ST[(size_t)v0 * 33 + e] : 0.f;
-    __syncthreads();
+    constexpr int kVw = kSkinV / 8;                                       // vertices per warp and chunk
     float beta[kBetas];
+    bool have_beta = false;
+    for (int ch = blockIdx.x; ch < nchunks; ch += nx) {
+        const int v0 = ch * kSkinV;
+        // pose offsets of this warp's vertices: 24 independent coalesced loads in flight before anything waits
+        float pf[kVw][3];
 #pragma unroll
-    for (int l = 0; l < kBetas; ++l) beta[l] = Bs[l * 32 + lane];
-    float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
-    int bilo[3] = {0, 0, 0}, bihi[3] = {0, 0, 0};
-    for (int i = 0; i < kSkinV / 8; ++i) {
-        const int li = warp * (kSkinV / 8) + i;
-        const int n = v0 + li;
-        if (n >= N) break;
-        const float* st = Sts + li * 33;                              // [3][11]: shapedirs row | template
-        float vp[3];
+        for (int i = 0; i < kVw; ++i) {
+            const int n = v0 + warp * kVw + i;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = st[11 * c + kBetas];
-#pragma unroll
-            for (int l = 0; l < kBetas; ++l) a = fmaf(st[11 * c + l], beta[l], a);
-            vp[c] = a + poffT[(size_t)(3 * n + c) * ldA + slotc];
+            for (int c = 0; c < 3; ++c) pf[i][c] = n < N ? poffT[(size_t)(3 * n + c) * ldA + slotc] : 0.f;
         }
-        float T[12];
+        __syncthreads();                                                  // previous chunk's staging buffers are free
+        for (int e = tid; e < kSkinV * 33; e += kSkinThreads) Sts[e] = (v0 * 33 + e < N * 33) ? ST[(size_t)v0 * 33 + e] : 0.f;
+        __syncthreads();
+        if (!have_beta) {
 #pragma unroll
-        for (int c = 0; c < 12; ++c) T[c] = 0.f;
-        for (int e = 0; e < KW; ++e) {
-            const float w = ell_w[(size_t)n * KW + e];
-            if (w != 0.f) {
-                const float* Aj = As + (size_t)ell_j[(size_t)n * KW + e] * 12 * 32 + lane;
+            for (int l = 0; l < kBetas; ++l) beta[l] = Bs[l * 32 + lane];
+            have_beta = true;
+        }
+        float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+        int bilo[3] = {0, 0, 0}, bihi[3] = {0, 0, 0};
 #pragma unroll
-                for (int c = 0; c < 12; ++c) T[c] = fmaf(w, Aj[c * 32], T[c]);
+        for (int i = 0; i < kVw; ++i) {
+            const int li = warp * kVw + i;
+            const int n = v0 + li;
+            if (n < N) {
+                const float* st = Sts + li * 33;                          // [3][11]: shapedirs row | template
+                float vp[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float a = st[11 * c + kBetas];
+#pragma unroll
+                    for (int l = 0; l < kBetas; ++l) a = fmaf(st[11 * c + l], beta[l], a);
+                    vp[c] = a + pf[i][c];
+                }
+                float T[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) T[c] = 0.f;
+                for (int e = 0; e < KW; ++e) {
+                    const float w = ell_w[(size_t)n * KW + e];
+                    if (w != 0.f) {
+                        const float* Aj = As + (size_t)ell_j[(size_t)n * KW + e] * 12 * 32 + lane;
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) T[c] = fmaf(w, Aj[c * 32], T[c]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float vv = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
+                    Ovp[lane * kSkinOutLd + 3 * li + r] = vp[r];
+                    Ov[lane * kSkinOutLd + 3 * li + r] = vv;
+                    if (vv < blo[r]) { blo[r] = vv; bilo[r] = n; }       // strict: ties keep the lowest vertex index
+                    if (vv > bhi[r]) { bhi[r] = vv; bihi[r] = n; }
+                }
             }
         }
+        int* Bi = reinterpret_cast<int*>(Bb + 8 * 32 * 6);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const float vv = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
-            Ovp[lane * kSkinOutLd + 3 * li + r] = vp[r];
-            Ov[lane * kSkinOutLd + 3 * li + r] = vv;
-            if (vv < blo[r]) { blo[r] = vv; bilo[r] = n; }       // strict: ties keep the lowest vertex index
-            if (vv > bhi[r]) { bhi[r] = vv; bihi[r] = n; }
+            Bb[(warp * 32 + lane) * 6 + r] = blo[r]; Bb[(warp * 32 + lane) * 6 + 3 + r] = bhi[r];
+            Bi[(warp * 32 + lane) * 6 + r] = bilo[r]; Bi[(warp * 32 + lane) * 6 + 3 + r] = bihi[r];
         }
-    }
-    int* Bi = reinterpret_cast<int*>(Bb + 8 * 32 * 6);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        Bb[(warp * 32 + lane) * 6 + r] = blo[r]; Bb[(warp * 32 + lane) * 6 + 3 + r] = bhi[r];
-        Bi[(warp * 32 + lane) * 6 + r] = bilo[r]; Bi[(warp * 32 + lane) * 6 + 3 + r] = bihi[r];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 32 * 3 * kSkinV; idx += kSkinThreads) {
-        const int fl = idx / (3 * kSkinV), col = idx % (3 * kSkinV);
-        const int slot = f0 + fl, n = v0 + col / 3;
-        if (slot < na && n < N) {
-            const size_t off = ((size_t)slot * N + v0) * 3 + col;
-            vposed[off] = Ovp[fl * kSkinOutLd + col];
-            verts[off] = Ov[fl * kSkinOutLd + col];
-        }
-    }
-    if (bboxp && warp == 0 && f0 + lane < na) {       // fold the 8 warps' vertex groups (ascending vertex index)
-        float lo[3], hi[3];
-        int ilo[3], ihi[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { lo[r] = Bb[lane * 6 + r]; hi[r] = Bb[lane * 6 + 3 + r]; ilo[r] = Bi[lane * 6 + r]; ihi[r] = Bi[lane * 6 + 3 + r]; }
-        for (int w2 = 1; w2 < 8; ++w2)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float l2 = Bb[(w2 * 32 + lane) * 6 + r], h2 = Bb[(w2 * 32 + lane) * 6 + 3 + r];
-                if (l2 < lo[r]) { lo[r] = l2; ilo[r] = Bi[(w2 * 32 + lane) * 6 + r]; }
-                if (h2 > hi[r]) { hi[r] = h2; ihi[r] = Bi[(w2 * 32 + lane) * 6 + 3 + r]; }
+        __syncthreads();
+        const int ncol = 3 * min(kSkinV, N - v0);                         // contiguous floats of this chunk per frame
+        for (int fl = warp; fl < 32; fl += 8) {                           // a warp stores one frame's row segment at a time
+            const int slot = f0 + fl;
+            if (slot >= na) break;
+            const size_t off = ((size_t)slot * N + v0) * 3;
+            for (int col = lane; col < ncol; col += 32) {
+                vposed[off + col] = Ovp[fl * kSkinOutLd + col];
+                verts[off + col] = Ov[fl * kSkinOutLd + col];
             }
-        float* bp = bboxp + ((size_t)(f0 + lane) * gridDim.x + blockIdx.x) * 12;
+        }
+        if (bboxp && warp == 0 && f0 + lane < na) {       // fold the 8 warps' vertex groups (ascending vertex index)
+            float lo[3], hi[3];
+            int ilo[3], ihi[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { bp[r] = lo[r]; bp[3 + r] = hi[r]; bp[6 + r] = __int_as_float(ilo[r]); bp[9 + r] = __int_as_float(ihi[r]); }
+            for (int r = 0; r < 3; ++r) { lo[r] = Bb[lane * 6 + r]; hi[r] = Bb[lane * 6 + 3 + r]; ilo[r] = Bi[lane * 6 + r]; ihi[r] = Bi[lane * 6 + 3 + r]; }
+            for (int w2 = 1; w2 < 8; ++w2)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float l2 = Bb[(w2 * 32 + lane) * 6 + r], h2 = Bb[(w2 * 32 + lane) * 6 + 3 + r];
+                    if (l2 < lo[r]) { lo[r] = l2; ilo[r] = Bi[(w2 * 32 + lane) * 6 + r]; }
+                    if (h2 > hi[r]) { hi[r] = h2; ihi[r] = Bi[(w2 * 32 + lane) * 6 + 3 + r]; }
+                }
+            float* bp = bboxp + ((size_t)(f0 + lane) * nchunks + ch) * 12;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { bp[r] = lo[r]; bp[3 + r] = hi[r]; bp[6 + r] = __int_as_float(ilo[r]); bp[9 + r] = __int_as_float(ihi[r]); }
+        }
     }
 }
 
@@ -396,17 +429,16 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
     }
     const int ntiles = (m.N + kTileV - 1) / kTileV;
     const int mtiles = (w.B + kTcBM - 1) / kTcBM;
-    int ctas_n = ctx->sm_count / mtiles;
-    if (ctas_n < 1) ctas_n = 1;
-    const int tiles_per_cta = (ntiles + ctas_n - 1) / ctas_n;
-    dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, mtiles);
+    dim3 grid(std::min(ctx->sm_count, ntiles), mtiles);          // surplus CTAs exit: the kernel splits the tiles from *na
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
-               posedirs_gemm_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, w.ldA, 3 * m.N, w.na, tiles_per_cta,
+               posedirs_gemm_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, w.ldA, 3 * m.N, w.na, ctx->sm_count,
                                                                           ntiles, T->poffT, T->err));
-    dim3 g2((m.N + kSkinV - 1) / kSkinV, (w.B + 31) / 32);
+    // one wave of CTAs (two per SM): each CTA keeps its 32 frames' transforms in shared memory and walks several chunks
+    const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (w.B + 31) / 32;
+    dim3 g2(nchunks, fgroups);                          // surplus CTAs exit: the kernel sizes its chunk loop from *na
     MVS_LAUNCH(ctx, KID_SKIN, st,
                skin_kernel<<<g2, kSkinThreads, kSkinSmem, st>>>(T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N,
-                                                                w.na, w.vposed, w.verts, w.bboxp));
+                                                                w.na, 2 * ctx->sm_count, w.vposed, w.verts, w.bboxp));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

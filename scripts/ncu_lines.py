@@ -7,7 +7,7 @@ agg = collections.Counter(); text = {}; cur_file = ""
 stall = collections.Counter()
 hdr = None
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         cur_file = r[1].split("/")[-1]; continue
     if r and r[0] == "Line No":
         hdr = r; continue
@@ -15,6 +15,7 @@ for r in rows:
     si = hdr.index("# Samples")
     try: n = int(r[si])
     except ValueError: continue
+    if r[0] == "": continue          # SASS rows repeat the samples of their source line
     key = (cur_file, r[0])
     agg[key] += n; text[key] = r[1].strip()[:100]
     for i, h in enumerate(hdr):

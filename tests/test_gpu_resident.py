@@ -73,7 +73,7 @@ def test_resident_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
 
 
 def test_dense_regime_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
-    """SDF term on: vertex_fwd -> sdf_frame -> frame_step rounds against the batched kernel chain"""
+    """SDF term on: posedirs_gemm_tc -> skin -> sdf_fused -> frame_step rounds against the batched kernel chain"""
     cams = S.make_cameras(4)
     B = 70
     fr = S.make_frames(syn_model, cams, B, seed=2)

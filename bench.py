@@ -135,17 +135,11 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step_resident():
+        # inputs already in HBM; mvs_fit runs the whole stage schedule (frames change stage on their own)
         nonlocal stages
         x.copy_(x0_dev)
-        tot = dict(frame_iterations=0, frame_evals=0, rounds=0, frames_nan=0)
-        per_stage = []
-        for cfg in stages:
-            ctx.set_loss(config=cfg)
-            _, st = ctx.lbfgs_run(x, opt)
-            per_stage.append(st)
-            for k in tot:
-                tot[k] += st[k]
-        return tot, per_stage
+        _, tot = ctx.fit(x, stages, opt)
+        return tot, [tot]
 
     def step_host():
         X_pin.copy_(torch.from_numpy(X0))

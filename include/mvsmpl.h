@@ -156,10 +156,20 @@ int mvs_lbfgs_run(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const 
 int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last_grad_dev, const mvs_lbfgs_config* cfg,
                    int reset, mvs_lbfgs_stats* stats, void* stream);
 
+/* ---- all stages of one fit, device buffers: what code/utils/non_linear_solver.py:109-203 does per frame (for every
+ *      stage: new loss weights, new optimiser, run_fitting) for all B frames at once.  Consecutive stages that run in
+ *      the same execution regime are merged into one run in which every frame moves to its next stage as soon as ITS
+ *      current stage stops -- frames are independent problems, so the per-frame schedule is the reference's, but no
+ *      frame waits at a stage boundary for the slowest one.  params_dev [B,86] is updated in place, final_loss_dev [B]
+ *      (may be NULL) receives each frame's last-stage result of run_fitting.  Leaves the last stage's loss
+ *      configuration set.  Synchronises. */
+int mvs_fit(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
+            float* final_loss_dev, mvs_lbfgs_stats* stats, void* stream);
+
 /* ---- host-buffer entry point (what a caller without device memory uses): copies keypoints and
  *      parameters host->device, runs `n_stages` optimisation stages (one mvs_loss_config each, the weight
  *      schedule of code/utils/non_linear_solver.py:109-203), copies parameters and losses back.
- *      All pointers are HOST pointers; synchronises. */
+ *      Stages are scheduled as in mvs_fit.  All pointers are HOST pointers; synchronises. */
 int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, const float* conf_host,
                  const float* joint_weights_host, int n_stages, const mvs_loss_config* stage_cfgs,
                  const mvs_lbfgs_config* opt_cfg, float* final_loss_host, mvs_lbfgs_stats* stats, void* stream);
@@ -173,7 +183,8 @@ int mvs_sdf_grid(mvs_ctx* ctx, float* phi_dev, const int* faces_dev, int num_fac
 
 /* Execution mode: 0 (default) = frame-resident kernels wherever they apply (sparse regime: no vertices requested,
  * no SDF term): one CTA per frame runs the closure -- and in mvs_lbfgs_run / mvs_fit_host the frame's whole
- * L-BFGS stage -- out of shared memory;  1 = always the batched multi-kernel path (used by tests to cross-check). */
+ * L-BFGS stage -- out of shared memory;  1 = always the batched multi-kernel path (used by tests to cross-check);
+ * 2 = like 0, but mvs_fit / mvs_fit_host keep a barrier between stages (one run per stage, as mvs_lbfgs_run). */
 int mvs_set_exec_mode(mvs_ctx* ctx, int mode);
 
 /* ---- measurement support (bench.py): per-kernel device time with CUDA events recorded on the launching

@@ -215,6 +215,19 @@ class FittingContext:
         return loss, grad, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
                                 frames_nan=st.frames_nan)
 
+    def fit(self, params: torch.Tensor, stage_cfgs, opt_cfg=None):
+        """All stages of a fit on device buffers (mvs_fit): params [B,86] CUDA float32, updated in place.  Frames move
+        from stage to stage on their own; returns (final_loss [B], stats)."""
+        assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
+        arr = (_lib.LossConfig * len(stage_cfgs))(*stage_cfgs)
+        cfg = opt_cfg or self.make_lbfgs_config()
+        final = torch.empty(self.B, dtype=torch.float32, device=self.device)
+        st = _lib.LbfgsStats()
+        _lib.check(self.h, self.lib.mvs_fit(self.h, _ptr(params), len(stage_cfgs), arr, ctypes.byref(cfg), _ptr(final),
+                                            ctypes.byref(st), self._stream()), "mvs_fit")
+        return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
+                           frames_nan=st.frames_nan)
+
     def fit_host(self, params_host: np.ndarray, gt_uv: np.ndarray, conf: np.ndarray, joint_weights: np.ndarray,
                  stage_cfgs, opt_cfg=None):
         """Host-buffer entry point (mvs_fit_host): params_host [B,86] float32 updated in place."""

@@ -67,6 +67,26 @@ using namespace mvs;
 #define MVS_REQUIRE(ctx, cond, ...) \
     do { if (!(cond)) return set_error(ctx, MVS_ERR_INVALID, __VA_ARGS__); } while (0)
 
+namespace mvs {
+int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out) {
+    MVS_REQUIRE(ctx, c, "mvs_set_loss_config: NULL config");
+    MVS_REQUIRE(ctx, c->body_prior >= 0 && c->body_prior <= 2, "mvs_set_loss_config: bad body_prior");
+    MVS_REQUIRE(ctx, c->body_prior != MVS_PRIOR_GMM || c->use_vposer || ctx->m.M > 0,
+                "mvs_set_loss_config: GMM prior selected but mvs_set_gmm_prior was not called");
+    MVS_REQUIRE(ctx, !c->interpenetration || ctx->m.faces, "mvs_set_loss_config: interpenetration needs faces");
+    LossParams l{};
+    l.data_weight = c->data_weight; l.body_pose_weight = c->body_pose_weight; l.shape_weight = c->shape_weight;
+    l.bending_prior_weight = c->bending_prior_weight; l.coll_loss_weight = c->coll_loss_weight; l.rho = c->rho;
+    l.body_prior = c->body_prior; l.use_joints_conf = c->use_joints_conf; l.use_vposer = c->use_vposer;
+    l.fix_shape = c->fix_shape; l.interpenetration = c->interpenetration;
+    l.sdf_grid = c->sdf_grid > 0 ? c->sdf_grid : 128; l.sdf_all_faces = c->sdf_all_faces;
+    l.frozen_mask = c->frozen_mask; l.num_gaussians = ctx->m.M;
+    l.anchor_on = ctx->anchor_enabled ? 1 : 0;
+    *out = l;
+    return MVS_OK;
+}
+}  // namespace mvs
+
 extern "C" {
 
 int mvs_version(void) { return 100; }
@@ -105,7 +125,7 @@ const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelN
 
 int mvs_set_exec_mode(mvs_ctx* ctx, int mode) {
     if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
-    MVS_REQUIRE(ctx, mode == 0 || mode == 1, "mvs_set_exec_mode: mode must be 0 or 1");
+    MVS_REQUIRE(ctx, mode >= 0 && mode <= 2, "mvs_set_exec_mode: mode must be 0, 1 or 2");
     ctx->exec_mode = mode;
     return MVS_OK;
 }
@@ -358,6 +378,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;
     w.B = B;
+    w.na_bound = B;
     w.ldA = (B + kTileF - 1) / kTileF * kTileF;
     const int ftiles = w.ldA / kTileF;
     w.nstrips_max = std::min((m.N + kTileV - 1) / kTileV, (ctx->sm_count + ftiles - 1) / ftiles + 1);
@@ -413,19 +434,10 @@ int mvs_set_keypoints(mvs_ctx* ctx, const float* gt_uv, const float* conf, const
 
 int mvs_set_loss_config(mvs_ctx* ctx, const mvs_loss_config* c) {
     if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
-    MVS_REQUIRE(ctx, c, "mvs_set_loss_config: NULL config");
-    MVS_REQUIRE(ctx, c->body_prior >= 0 && c->body_prior <= 2, "mvs_set_loss_config: bad body_prior");
-    MVS_REQUIRE(ctx, c->body_prior != MVS_PRIOR_GMM || c->use_vposer || ctx->m.M > 0,
-                "mvs_set_loss_config: GMM prior selected but mvs_set_gmm_prior was not called");
-    MVS_REQUIRE(ctx, !c->interpenetration || ctx->m.faces, "mvs_set_loss_config: interpenetration needs faces");
-    LossParams& l = ctx->loss;
-    l.data_weight = c->data_weight; l.body_pose_weight = c->body_pose_weight; l.shape_weight = c->shape_weight;
-    l.bending_prior_weight = c->bending_prior_weight; l.coll_loss_weight = c->coll_loss_weight; l.rho = c->rho;
-    l.body_prior = c->body_prior; l.use_joints_conf = c->use_joints_conf; l.use_vposer = c->use_vposer;
-    l.fix_shape = c->fix_shape; l.interpenetration = c->interpenetration;
-    l.sdf_grid = c->sdf_grid > 0 ? c->sdf_grid : 128; l.sdf_all_faces = c->sdf_all_faces;
-    l.frozen_mask = c->frozen_mask; l.num_gaussians = ctx->m.M;
-    l.anchor_on = ctx->anchor_enabled ? 1 : 0;
+    LossParams l;
+    const int rc = make_loss_params(ctx, c, &l);
+    if (rc) return rc;
+    ctx->loss = l;
     ctx->have_loss = true;
     return MVS_OK;
 }

@@ -818,8 +818,8 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     DevModel& m = ctx->m;
     Workspace& w = ctx->ws;
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
-               frame_fwd_kernel<<<w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt, m.JS, w.Phi, w.PhiTc, w.At,
-                                                              w.ldA, w.gchain));
+               frame_fwd_kernel<<<w.na_bound > 0 ? w.na_bound : w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt,
+                                                              m.JS, w.Phi, w.PhiTc, w.At, w.ldA, w.gchain));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

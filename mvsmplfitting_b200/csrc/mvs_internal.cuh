@@ -80,6 +80,8 @@ struct DevModel {
 // Per-batch workspace (slot-indexed: slot = position in the active-frame list)
 struct Workspace {
     int B = 0, ldA = 0;               // ldA = B rounded up to kTileF
+    int na_bound = 0;                 // host-side upper bound of *na (grids of the dense-regime rounds are sized by it;
+                                      // equals B outside mvs_lbfgs_run / while the active list is full)
     int nstrips_max = 0;
     int* fidx = nullptr;              // [B] active list: slot -> frame
     int* na = nullptr;                // [1] number of active slots
@@ -108,10 +110,10 @@ struct Workspace {
     float* sdf_gcoord = nullptr;      // [B][N][3]
     float* sdf_valpart = nullptr;     // [B][nbt]
     float* bboxp = nullptr;           // [B][nchunks][12] per-chunk bbox partials written by the skinning kernel
-    // dense regime (sdf_fused_kernel -> frame_step_kernel), P = parts of 1024 vertices per frame
-    float* sdf_parts5 = nullptr;      // [B][P][5] partial sums: value, d value/d local (3), <d value/d local, local>
+    // dense regime (sdf_fused_kernel -> frame_step_kernel), P = 256-vertex blocks per frame
+    float* sdf_parts5 = nullptr;      // [B][P][5] per 256-vertex block: value, d value/d local (3), <d value/d local, local>
     float* sdf_part = nullptr;        // [B][P][512] unit-factor partial adjoints (288 skin | 224 feature)
-    int* sdf_pflag = nullptr;         // [B][P] 1 iff the part has vertices with a non-zero sample gradient
+    int* sdf_pflag = nullptr;         // [B][P] 1 iff the block has vertices with a non-zero sample gradient
     unsigned char* sdf_box = nullptr; // [B] FrameBox
 };
 
@@ -123,8 +125,8 @@ struct FrameBox {                     // bounding box of one frame's mesh (fitti
     float pad;
 };
 
-// sdf_fused_kernel splits a frame's vertices into parts of 256 x passes vertices; few active frames -> more, smaller
-// parts (latency), many -> fewer, larger ones (less per-CTA overhead).  frame_step_kernel derives the same split.
+// sdf_fused_kernel gives a CTA 1, 2 or 4 blocks of 256 vertices: few active frames -> more, smaller CTAs (latency),
+// many -> fewer, larger ones (less per-CTA overhead).  Results are emitted per block, so they do not depend on it.
 constexpr int kSdfMaxParts = 32;
 __host__ __device__ inline int sdf_passes_for(int na, int n_verts) {
     const int p1 = (n_verts + 255) / 256;
@@ -206,8 +208,8 @@ bool resident_closure_available(const mvs_ctx* ctx);
 int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
                             float* proj_dev, cudaStream_t st);
 bool resident_lbfgs_available(const mvs_ctx* ctx, int history);
-int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, void* frame_scalars_out,
-                          float* last_grad_dev, cudaStream_t st);
+int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, const void* lp_tab_dev,
+                          int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st);
 // dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
@@ -218,7 +220,11 @@ int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
 int tc_check_error(mvs_ctx* ctx);
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st);
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
+                      cudaStream_t st);
+bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
+bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
+int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);
 }  // namespace mvs

@@ -20,6 +20,7 @@
 #include <stdio.h>
 
 #include <cstdio>
+#include <vector>
 #include <cstdlib>
 #include "mvs_internal.cuh"
 #include "mvs_lbfgs_core.cuh"
@@ -110,7 +111,7 @@ __global__ void lbfgs_finalize_kernel(LbfgsState S, int B, float* __restrict__ f
     if (final_loss) final_loss[b] = s.final_loss;
     atomicAdd((unsigned long long*)&totals[0], (unsigned long long)s.iters);
     atomicAdd((unsigned long long*)&totals[1], (unsigned long long)s.evals);
-    atomicAdd((unsigned long long*)&totals[2], (unsigned long long)s.nan_flag);
+    atomicAdd((unsigned long long*)&totals[2], (unsigned long long)(s.nan_flag + s.nan_acc));
     if (max_evals_as_rounds) atomicMax((unsigned long long*)&totals[3], (unsigned long long)s.evals);
 }
 
@@ -150,13 +151,19 @@ static int ensure_state(mvs_ctx* ctx, int H) {
     if ((rc = dev_alloc(ctx, &raw2, 4 * sizeof(long long)))) return rc;
     S->totals = reinterpret_cast<long long*>(raw2);
     MVS_CUDA_OK(ctx, cudaMallocHost(&S->na_host, 8 * sizeof(long long)));
+    MVS_CUDA_OK(ctx, cudaMallocHost(&S->lp_tab_host, kMaxStages * sizeof(LossParams)));
+    unsigned char* raw3 = nullptr;
+    if ((rc = dev_alloc(ctx, &raw3, kMaxStages * sizeof(LossParams)))) return rc;
+    S->lp_tab = reinterpret_cast<LossParams*>(raw3);
     ctx->lbfgs = S;
     return MVS_OK;
 }
 
+// Runs the stages lps[0 .. nst) (nst == 1: ctx->loss).  nst > 1 requires that all of them run in the same regime
+// (frame-resident or dense rounds, see run_fit): every frame then walks through the stages at its own pace.
 static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const mvs_lbfgs_config* c,
                      mvs_lbfgs_stats* stats, cudaStream_t st, int step_mode = 0, int reset = 1,
-                     float* last_grad_dev = nullptr) {
+                     float* last_grad_dev = nullptr, const LossParams* lps = nullptr, int nst = 1) {
     const int B = ctx->ws.B;
     const int H = c->history_size > 0 ? c->history_size : 100;
     if (H > 128) return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_run: history_size must be <= 128");
@@ -176,9 +183,15 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
 
     Workspace& w = ctx->ws;
     MVS_CUDA_OK(ctx, cudaMemsetAsync(S.totals, 0, 4 * sizeof(long long), st));
+    if (!lps) { lps = &ctx->loss; nst = 1; }
+    if (nst > kMaxStages) return set_error(ctx, MVS_ERR_INVALID, "at most %d stages per run", kMaxStages);
+    // stage table for the multi-stage kernels (the previous run ended with a stream synchronisation, so the pinned
+    // staging copy is free)
+    for (int i = 0; i < nst; ++i) S.lp_tab_host[i] = lps[i];
+    MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.lp_tab, S.lp_tab_host, (size_t)nst * sizeof(LossParams), cudaMemcpyHostToDevice, st));
     if (!step_mode && resident_lbfgs_available(ctx, H)) {
         // sparse regime: every frame runs its whole stage inside one CTA (mvs_resident.cu): one launch, no rounds
-        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.sc, last_grad_dev, st);
+        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.lp_tab, nst, S.sc, last_grad_dev, st);
         if (rc) return rc;
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
         long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
@@ -198,28 +211,48 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         // GEMM), skinning + box partials, the SDF term with the adjoint of its (short) vertex list, and the per-frame
         // closure adjoint + optimiser step + next pose forward.  Finished frames are compacted out once per chunk.
         const int chunk = 8;
-        const long long max_rounds = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
+        const long long max_rounds = ((long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8) * nst;
         long long rounds = 0;
         int na_host = B;
         static const bool trace_na = getenv("MVS_TRACE_NA") != nullptr;       // debugging aid: active-list size per chunk
         rc = launch_frame_fwd(ctx, S.x_eval, st);
         if (rc) return rc;
-        while (na_host > 0 && rounds < max_rounds) {
+        // The host only needs the active count to know when to stop, so chunk k+1 is enqueued BEFORE the count of
+        // chunk k is awaited (kernels exit at once when the list is empty): the GPU never idles on the host round trip.
+        if (!S.na_event[0]) {
+            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[0], cudaEventDisableTiming));
+            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[1], cudaEventDisableTiming));
+        }
+        int* na_slots = reinterpret_cast<int*>(S.na_host);           // [0], [1]: two chunks in flight
+        int pending = -1;                                             // chunk whose count has not been read yet
+        long long chunk_idx = 0;
+        w.na_bound = B;                                               // grids shrink with the (lagging) host view of the count
+        while (rounds < max_rounds) {
             for (int r = 0; r < chunk; ++r) {
                 if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;        // tcgen05 GEMM + LBS + bbox partials
                 if ((rc = launch_sdf_fused(ctx, S.x_eval, S.sc, st))) return rc;   // samples + adjoint of the listed vertices
-                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, st))) return rc;
+                if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, nst, st))) return rc;
                 ++rounds;
             }
             // compaction changes slot -> frame, so the surviving frames' Phi / transforms are rebuilt for their new slots
             MVS_LAUNCH(ctx, KID_LBFGS_COMPACT, st, lbfgs_compact_kernel<<<1, 1024, 0, st>>>(S, B, w.fidx, w.na));
             if ((rc = launch_frame_fwd(ctx, S.x_eval, st))) return rc;
-            MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.na_host, w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
-            MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
-            na_host = *S.na_host;
-            if (trace_na) fprintf(stderr, "[mvs] dense regime: round %lld, active frames %d\n", rounds, na_host);
-            if ((rc = tc_check_error(ctx))) return rc;
+            const int cur = (int)(chunk_idx & 1);
+            MVS_CUDA_OK(ctx, cudaMemcpyAsync(&na_slots[cur], w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MVS_CUDA_OK(ctx, cudaEventRecord(S.na_event[cur], st));
+            if (pending >= 0) {
+                MVS_CUDA_OK(ctx, cudaEventSynchronize(S.na_event[pending]));
+                na_host = na_slots[pending];
+                if (trace_na) fprintf(stderr, "[mvs] dense regime: chunk %lld, active frames %d\n", chunk_idx - 1, na_host);
+                if (na_host <= 0) break;
+                w.na_bound = na_host;                                 // the list only shrinks: still an upper bound
+            }
+            pending = cur;
+            ++chunk_idx;
         }
+        w.na_bound = B;
+        MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if ((rc = tc_check_error(ctx))) return rc;
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
         if (last_grad_dev)
             MVS_CUDA_OK(ctx, cudaMemcpyAsync(last_grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -268,6 +301,41 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     return MVS_OK;
 }
 
+// All stages of a fit.  Consecutive stages that run in the same regime are handed to ONE multi-stage run in which
+// every frame changes stage on its own (frames are independent problems, so a frame that converged need not wait at
+// the stage boundary for the slowest one; the per-frame arithmetic is the sequential schedule's).  exec_mode 2 keeps
+// the stage barrier (one run per stage).
+static int run_fit(mvs_ctx* ctx, float* x_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
+                   float* final_loss_dev, mvs_lbfgs_stats* stats, cudaStream_t st) {
+    if (n_stages > 64) return set_error(ctx, MVS_ERR_INVALID, "mvs_fit: at most 64 stages");
+    std::vector<LossParams> lps(n_stages);
+    for (int i = 0; i < n_stages; ++i) {
+        const int rc = make_loss_params(ctx, &stage_cfgs[i], &lps[i]);
+        if (rc) return rc;
+    }
+    const int H = opt_cfg->history_size > 0 ? opt_cfg->history_size : 100;
+    auto regime = [&](const LossParams& lp) {
+        if (resident_lbfgs_available_for(ctx, lp, H)) return 0;
+        if (hybrid_available_for(ctx, lp)) return 1;
+        return 2;
+    };
+    int i = 0;
+    while (i < n_stages) {
+        const int rg = regime(lps[i]);
+        int j = i + 1;
+        while (ctx->exec_mode != 2 && rg != 2 && j < n_stages && j - i < kMaxStages && regime(lps[j]) == rg &&
+               lps[j].sdf_grid == lps[i].sdf_grid && lps[j].sdf_all_faces == lps[i].sdf_all_faces)
+            ++j;
+        ctx->loss = lps[i];
+        ctx->have_loss = true;
+        const int rc = run_stage(ctx, x_dev, final_loss_dev, opt_cfg, stats, st, 0, 1, nullptr, &lps[i], j - i);
+        if (rc) return rc;
+        i = j;
+    }
+    ctx->loss = lps[n_stages - 1];
+    return MVS_OK;
+}
+
 }  // namespace mvs
 
 using namespace mvs;
@@ -297,6 +365,17 @@ int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last
     return run_stage(ctx, params_dev, loss_dev, cfg, stats, (cudaStream_t)stream, 1, reset ? 1 : 0, last_grad_dev);
 }
 
+int mvs_fit(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
+            float* final_loss_dev, mvs_lbfgs_stats* stats, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    if (!(ctx->have_model && ctx->have_cams && ctx->have_kp && ctx->ws.B > 0))
+        return set_error(ctx, MVS_ERR_INVALID, "mvs_fit: model, cameras, batch and keypoints must be set first");
+    if (!params_dev || n_stages <= 0 || !stage_cfgs || !opt_cfg) return set_error(ctx, MVS_ERR_INVALID, "mvs_fit: NULL / empty argument");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    return run_fit(ctx, params_dev, n_stages, stage_cfgs, opt_cfg, final_loss_dev, stats, (cudaStream_t)stream);
+}
+
 int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, const float* conf_host,
                  const float* joint_weights_host, int n_stages, const mvs_loss_config* stage_cfgs,
                  const mvs_lbfgs_config* opt_cfg, float* final_loss_host, mvs_lbfgs_stats* stats, void* stream) {
@@ -320,12 +399,8 @@ int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, cons
     float* x = S.x_fit;                              // [B][86] device copy of the parameters
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(x, params_host, (size_t)B * kParams * sizeof(float), cudaMemcpyHostToDevice, st));
     if (stats) memset(stats, 0, sizeof(*stats));
-    for (int sidx = 0; sidx < n_stages; ++sidx) {
-        rc = mvs_set_loss_config(ctx, &stage_cfgs[sidx]);
-        if (rc) return rc;
-        rc = run_stage(ctx, x, S.final_fit, opt_cfg, stats, st);
-        if (rc) return rc;
-    }
+    rc = run_fit(ctx, x, n_stages, stage_cfgs, opt_cfg, S.final_fit, stats, st);
+    if (rc) return rc;
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(params_host, x, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (final_loss_host)
         MVS_CUDA_OK(ctx, cudaMemcpyAsync(final_loss_host, S.final_fit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -5,6 +5,8 @@
 
 namespace mvs {
 
+constexpr int kMaxStages = 16;
+
 enum Phase { PH_STEP_ENTRY = 0, PH_LS_BRACKET = 1, PH_LS_ZOOM = 2, PH_DONE = 3 };
 
 struct FrameScalars {
@@ -12,6 +14,8 @@ struct FrameScalars {
     int ls_iter, ls_evals, ls_first, low, high, done, insuf, have_prev;
     int hist_len, hist_head, nan_flag;
     int pushed_slot;                 // ring slot written by the last advance call (-1: none)
+    int stage;                       // index into the stage table of a multi-stage run (frames change stage on their own)
+    int nan_acc;                     // NaN / Inf stops of the stages this frame already left
     float t, H_diag, gtd0, t_prev, gtd_prev, d_norm;
     float bt[2], bgtd[2], bf[2];
     float loss, prev_loss, orig_loss, f_prev, mon_prev_loss, final_loss;
@@ -27,6 +31,9 @@ struct LbfgsState {
     long long* totals = nullptr;     // [4] iters, evals, nan frames, real rounds
     float *x_fit = nullptr, *final_fit = nullptr;   // mvs_fit_host staging
     int* na_host = nullptr;          // pinned
+    cudaEvent_t na_event[2] = {nullptr, nullptr};   // host side: active-count readback of the two chunks in flight
+    LossParams* lp_tab = nullptr;    // [kMaxStages] loss parameters of the stages of the current run (device)
+    LossParams* lp_tab_host = nullptr;   // pinned staging copy
 };
 
 struct LbfgsCfg {

@@ -21,8 +21,22 @@ namespace mvs {
 // -DMVS_PHASE_DBG (scripts/phase_times.py builds libmvsmpl_dbg.so with it): thread 0 of CTA 0 stamps clock64() after
 // every barrier of frame_step_kernel, so the serial phases of one frame's round can be timed without a profiler.
 #ifdef MVS_PHASE_DBG
-__device__ long long g_phase_clk[64];
-#define PHASE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+__device__ long long g_phase_clk[64];       // [0..31] stamps of CTA 0; [32..39] max over CTAs of coarse segment times
+__device__ __forceinline__ void phase_mark(int i) {
+    if (threadIdx.x != 0) return;
+    const long long c = clock64();
+    if (blockIdx.x == 0) g_phase_clk[i] = c;
+    // coarse segments of every CTA: start -> closure done (22) -> history ready (23) -> advanced (24) -> next pose (28)
+    __shared__ long long seg_t0, seg_prev;
+    if (i == 0) { seg_t0 = c; seg_prev = c; }
+    const int k = (i == 22) ? 0 : (i == 23) ? 1 : (i == 24) ? 2 : (i == 28) ? 3 : -1;
+    if (k >= 0) {
+        atomicMax(reinterpret_cast<unsigned long long*>(&g_phase_clk[32 + k]), (unsigned long long)(c - seg_prev));
+        seg_prev = c;
+        if (i == 24 || i == 28) atomicMax(reinterpret_cast<unsigned long long*>(&g_phase_clk[36 + (i == 28)]), (unsigned long long)(c - seg_t0));
+    }
+}
+#define PHASE_MARK(i) phase_mark(i)
 #else
 #define PHASE_MARK(i) do {} while (0)
 #endif
@@ -79,6 +93,7 @@ struct ResidentSmem {
     int ext_n[8];
     float ext_d[24];
     float sdf_sc[4];                       // [0] cg / scale, [1] pen loss, [2] number of extreme entries
+    LossParams lp;                         // this frame's CURRENT stage (multi-stage kernels)
     FrameScalars fs;
 };
 
@@ -99,78 +114,99 @@ struct DenseIn {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Kinematic chain by depth levels (lbs.py:348-374): 12 lanes per joint, all joints of a level in parallel.
+// Kinematic chain by depth levels (lbs.py:348-374).  Every ROLE (rotation part, translation part, ...) has its own
+// warps so that no warp executes more than one branch body: a level costs one short dependent chain plus a barrier.
 // All kResThreads threads must call; ends with a barrier.
 __device__ __forceinline__ void chain_fwd_levels(ResidentSmem& S) {
     const int t = threadIdx.x;
     if (t < 9) S.Gam[t] = S.x[kOffScale] * S.R[t];                               // lbs.py:348
-    else if (t < 12) S.g[t - 9] = S.J[t - 9];
+    else if (t >= 64 && t < 67) S.g[t - 64] = S.J[t - 64];
     __syncthreads();
-    constexpr int kGroups = kResThreads / 12;
-    const int grp = t / 12, l = t % 12;
     for (int L = 1; L < S.nlev; ++L) {
         const int beg = S.lev_ptr[L], cnt = S.lev_ptr[L + 1] - beg;
-        if (grp < kGroups) {
-            for (int q = grp; q < cnt; q += kGroups) {
+        if (t < 63) {                                        // threads 0..62: Gam_j = Gam_p R_j, 9 lanes per joint
+            const int l = t % 9;
+            for (int q = t / 9; q < cnt; q += 7) {
                 const int j = S.lev_j[beg + q], p = S.par[j];
                 const float* Gp = &S.Gam[9 * p];
-                if (l < 9) {
-                    const int r = l / 3, c = l % 3;
-                    const float* Rj = &S.R[9 * j];
-                    S.Gam[9 * j + l] = Gp[3 * r] * Rj[c] + Gp[3 * r + 1] * Rj[3 + c] + Gp[3 * r + 2] * Rj[6 + c];
-                } else {
-                    const int r = l - 9;
-                    const float r0 = S.J[3 * j] - S.J[3 * p], r1 = S.J[3 * j + 1] - S.J[3 * p + 1], r2 = S.J[3 * j + 2] - S.J[3 * p + 2];
-                    S.g[3 * j + r] = (Gp[3 * r] * r0 + Gp[3 * r + 1] * r1 + Gp[3 * r + 2] * r2) + S.g[3 * p + r];
-                }
+                const float* Rj = &S.R[9 * j];
+                const int r = l / 3, c = l % 3;
+                S.Gam[9 * j + l] = Gp[3 * r] * Rj[c] + Gp[3 * r + 1] * Rj[3 + c] + Gp[3 * r + 2] * Rj[6 + c];
+            }
+        } else if (t >= 64 && t < 64 + 30) {                 // threads 64..93: g_j = Gam_p (J_j - J_p) + g_p, 3 lanes per joint
+            const int u = t - 64, r = u % 3;
+            for (int q = u / 3; q < cnt; q += 10) {
+                const int j = S.lev_j[beg + q], p = S.par[j];
+                const float* Gp = &S.Gam[9 * p];
+                const float r0 = S.J[3 * j] - S.J[3 * p], r1 = S.J[3 * j + 1] - S.J[3 * p + 1], r2 = S.J[3 * j + 2] - S.J[3 * p + 2];
+                S.g[3 * j + r] = (Gp[3 * r] * r0 + Gp[3 * r + 1] * r1 + Gp[3 * r + 2] * r2) + S.g[3 * p + r];
             }
         }
         __syncthreads();
     }
 }
 
-// Adjoint of the chain, deepest level first: the 24 lanes of a PARENT gather its children's contributions
-// (dGam_p += dGam_j R_j^T + dg_j rel^T, dg_p += dg_j, dJ_p -= drel) and emit the children's dR_j, dJ_j.
+// Adjoint of the chain, deepest level first.  Per level L (parents p with children j at level L + 1, already final):
+//   role A (threads 0..62)     dGam_p += sum_j dGam_j R_j^T + dg_j rel_j^T      9 lanes per parent
+//   role B (threads 64..126)   dR_j = Gam_p^T dGam_j                             9 lanes per child
+//   role C (threads 128..157)  drel_j = Gam_p^T dg_j;  dJ_j += drel_j, dJ_p -= sum_j drel_j     3 lanes per parent
+//   role D (threads 160..189)  dg_p += sum_j dg_j                                3 lanes per parent
+// Children are gathered in descending index order = the summation order of the plain j = 23..1 sweep.
 __device__ __forceinline__ void chain_bwd_levels(ResidentSmem& S) {
     const int t = threadIdx.x;
-    constexpr int kGroups = kResThreads / 24;
-    const int grp = t / 24, l = t % 24;
     for (int L = S.nlev - 2; L >= 0; --L) {
         const int beg = S.lev_ptr[L], cnt = S.lev_ptr[L + 1] - beg;
-        if (grp < kGroups) {
-            for (int q = grp; q < cnt; q += kGroups) {
+        if (t < 63) {
+            const int l = t % 9, r = l / 3, c = l % 3;
+            for (int q = t / 9; q < cnt; q += 7) {
+                const int p = S.lev_j[beg + q];
+                const int c0 = S.ch_ptr[p], c1 = S.ch_ptr[p + 1];
+                if (c0 == c1) continue;
+                float acc = S.dGam[9 * p + l];
+                for (int ci = c0; ci < c1; ++ci) {
+                    const int j = S.ch_j[ci];
+                    const float* dGj = &S.dGam[9 * j];
+                    const float* Rj = &S.R[9 * j];
+                    const float rel = S.J[3 * j + c] - S.J[3 * p + c];
+                    acc += (dGj[3 * r] * Rj[3 * c] + dGj[3 * r + 1] * Rj[3 * c + 1] + dGj[3 * r + 2] * Rj[3 * c + 2]) + S.dg[3 * j + r] * rel;
+                }
+                S.dGam[9 * p + l] = acc;
+            }
+        } else if (t >= 64 && t < 64 + 63) {
+            const int u = t - 64, e = u % 9, r = e / 3, c = e % 3;
+            const int cbeg = S.lev_ptr[L + 1], ccnt = S.lev_ptr[L + 2] - cbeg;
+            for (int q = u / 9; q < ccnt; q += 7) {
+                const int j = S.lev_j[cbeg + q], p = S.par[j];
+                const float* Gp = &S.Gam[9 * p];
+                const float* dGj = &S.dGam[9 * j];
+                S.dR[9 * j + e] = Gp[r] * dGj[c] + Gp[3 + r] * dGj[3 + c] + Gp[6 + r] * dGj[6 + c];
+            }
+        } else if (t >= 128 && t < 128 + 30) {
+            const int u = t - 128, r = u % 3;
+            for (int q = u / 3; q < cnt; q += 10) {
                 const int p = S.lev_j[beg + q];
                 const int c0 = S.ch_ptr[p], c1 = S.ch_ptr[p + 1];
                 if (c0 == c1) continue;
                 const float* Gp = &S.Gam[9 * p];
-                float acc = 0.f;
-                if (l < 9) acc = S.dGam[9 * p + l];
-                else if (l >= 18 && l < 21) acc = S.dJ[3 * p + l - 18];
-                else if (l >= 21) acc = S.dg[3 * p + l - 21];
+                float acc = S.dJ[3 * p + r];
                 for (int ci = c0; ci < c1; ++ci) {
                     const int j = S.ch_j[ci];
-                    const float* dGj = &S.dGam[9 * j];
                     const float* dgj = &S.dg[3 * j];
-                    if (l < 9) {                   // dGp += dGam_j R_j^T + dg_j rel^T
-                        const int r = l / 3, c = l % 3;
-                        const float* Rj = &S.R[9 * j];
-                        const float rel = S.J[3 * j + c] - S.J[3 * p + c];
-                        acc += (dGj[3 * r] * Rj[3 * c] + dGj[3 * r + 1] * Rj[3 * c + 1] + dGj[3 * r + 2] * Rj[3 * c + 2]) + dgj[r] * rel;
-                    } else if (l < 18) {           // dR_j = Gp^T dGam_j
-                        const int e = l - 9, r = e / 3, c = e % 3;
-                        S.dR[9 * j + e] = Gp[r] * dGj[c] + Gp[3 + r] * dGj[3 + c] + Gp[6 + r] * dGj[6 + c];
-                    } else if (l < 21) {           // drel = Gp^T dg_j
-                        const int r = l - 18;
-                        const float out = Gp[r] * dgj[0] + Gp[3 + r] * dgj[1] + Gp[6 + r] * dgj[2];
-                        S.dJ[3 * j + r] += out;
-                        acc -= out;
-                    } else {
-                        acc += dgj[l - 21];
-                    }
+                    const float out = Gp[r] * dgj[0] + Gp[3 + r] * dgj[1] + Gp[6 + r] * dgj[2];
+                    S.dJ[3 * j + r] += out;
+                    acc -= out;
                 }
-                if (l < 9) S.dGam[9 * p + l] = acc;
-                else if (l >= 18 && l < 21) S.dJ[3 * p + l - 18] = acc;
-                else if (l >= 21) S.dg[3 * p + l - 21] = acc;
+                S.dJ[3 * p + r] = acc;
+            }
+        } else if (t >= 160 && t < 160 + 30) {
+            const int u = t - 160, r = u % 3;
+            for (int q = u / 3; q < cnt; q += 10) {
+                const int p = S.lev_j[beg + q];
+                const int c0 = S.ch_ptr[p], c1 = S.ch_ptr[p + 1];
+                if (c0 == c1) continue;
+                float acc = S.dg[3 * p + r];
+                for (int ci = c0; ci < c1; ++ci) acc += S.dg[3 * S.ch_j[ci] + r];
+                S.dg[3 * p + r] = acc;
             }
         }
         __syncthreads();
@@ -623,6 +659,19 @@ __device__ __forceinline__ void resident_setup(ResidentSmem& S, const ResidentMo
     else if (t == 64) S.nlev = m.cs.nlev;
 }
 
+// A frame that finished stage k of a multi-stage run starts stage k + 1 at once, with a fresh optimiser (the reference
+// builds one optimiser per stage, fitting.py / fit_single_frame) and the parameters it has: frames are independent
+// problems, so nothing makes a fast frame wait for the slowest one at a stage boundary.
+__device__ __forceinline__ void next_stage_scalars(FrameScalars& s) {
+    const long long it = s.iters, ev = s.evals;
+    const int st = s.stage + 1, nacc = s.nan_acc + s.nan_flag;
+    memset(&s, 0, sizeof(s));
+    s.H_diag = 1.f;
+    s.phase = PH_STEP_ENTRY;
+    s.final_loss = __int_as_float(0x7fc00000);
+    s.iters = it; s.evals = ev; s.stage = st; s.nan_acc = nacc;
+}
+
 // ------------------------------------------------------------------------------------------------ single closure
 __global__ void __launch_bounds__(kResThreads, 2)
 closure_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, const float* __restrict__ x,
@@ -646,8 +695,8 @@ closure_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, const float
 
 // ------------------------------------------------------------------------------------------------ whole stage
 __global__ void __launch_bounds__(kResThreads, 2)
-lbfgs_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, float* __restrict__ params,
-                      const float* __restrict__ gt_uv, const float* __restrict__ conf,
+lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ lp_tab, int nstages, LbfgsCfg cfg,
+                      float* __restrict__ params, const float* __restrict__ gt_uv, const float* __restrict__ conf,
                       const float* __restrict__ joint_w, int B, int H, FrameScalars* __restrict__ sc_out,
                       float* __restrict__ last_grad_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -666,23 +715,37 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg,
         s.final_loss = __int_as_float(0x7fc00000);
         S.fs = s;
     }
+    if (t < (int)(sizeof(LossParams) / 4)) reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[0])[t];
     __syncthreads();
     LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval, S.lg_new, H};
-    // hard bound on closure evaluations per frame (never reached by a terminating line search; a guard against
-    // hanging the GPU): every outer step costs at most 1 + max_eval + max_iter evaluations
+    // hard bound on closure evaluations per frame and stage (never reached by a terminating line search; a guard
+    // against hanging the GPU): every outer step costs at most 1 + max_eval + max_iter evaluations
     const long long eval_cap = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
+    long long stage_ev0 = 0;
+    int cur_stage = 0;
     while (true) {
         for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
         __syncthreads();
-        resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, DenseIn{});
+        resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, DenseIn{});
         if (warp == 0) {
             FrameScalars s = S.fs;
             lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
-            if (s.evals >= eval_cap && s.phase != PH_DONE) { s.phase = PH_DONE; s.nan_flag = 1; }
+            if (s.evals - stage_ev0 >= eval_cap && s.phase != PH_DONE) { s.phase = PH_DONE; s.nan_flag = 1; }
+            if (s.phase == PH_DONE && s.stage + 1 < nstages) {          // this frame moves on to its next stage
+                next_stage_scalars(s);
+                VLOOP(i) S.lx_eval[i] = S.lx[i];
+            }
             if (lane == 0) S.fs = s;
         }
         __syncthreads();
         if (S.fs.phase == PH_DONE) break;
+        if (S.fs.stage != cur_stage) {                                   // a stage just started: its loss parameters
+            cur_stage = S.fs.stage;
+            stage_ev0 = S.fs.evals;
+            if (t < (int)(sizeof(LossParams) / 4))
+                reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[cur_stage])[t];
+            __syncthreads();
+        }
     }
     for (int i = t; i < kParams; i += kResThreads) {
         params[(size_t)b * kParams + i] = S.lx[i];
@@ -697,7 +760,8 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg,
 // machine and -- if the frame needs another evaluation -- runs the pose forward of the NEXT trial point and
 // writes its feature row / skinning transforms for the next dense vertex launch.
 __global__ void __launch_bounds__(kResThreads, 2)
-frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, LbfgsState L, float* __restrict__ params,
+frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ lp_tab, int nstages, LbfgsCfg cfg,
+                  LbfgsState L, float* __restrict__ params,
                   const int* __restrict__ fidx, const int* __restrict__ na_ptr, const float* __restrict__ gt_uv,
                   const float* __restrict__ conf, const float* __restrict__ joint_w, int B, int N,
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
@@ -709,12 +773,15 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     const int slot = blockIdx.x;
     const int na = *na_ptr;
     if (slot >= na) return;
-    const int nparts = sdf_parts_for(na, N);                    // the split sdf_fused_kernel used for this round
+    const int nparts = (N + 255) / 256;                         // sdf_fused_kernel emits per 256-vertex block
+    (void)na;
     const int b = fidx[slot], t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const FrameScalars fs0 = L.sc[b];
     if (fs0.phase == PH_DONE) return;
     PHASE_MARK(0);
     resident_setup(S, m);
+    if (t < (int)(sizeof(LossParams) / 4))          // the loss parameters of the stage THIS frame is in
+        reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[fs0.stage])[t];
     float* x_eval = L.x_eval + (size_t)b * kParams;
     for (int i = t; i < kParams; i += kResThreads) S.x[i] = x_eval[i];
     // Stage this frame's curvature history (<= 2 x 100 x 86 floats) into shared memory with cp.async while the
@@ -762,7 +829,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
         for (int q = 0; q < 5; ++q) tot[q] = __shfl_sync(0xffffffffu, a, q);
         if (lane == 0) {
             const FrameBox fb = box[slot];
-            const float coll_w = lp.coll_loss_weight;
+            const float coll_w = lp_tab[fs0.stage].coll_loss_weight;
             const float wsum = coll_w * tot[0];                 // coll_loss_weight * cur_loss.sum() / 1
             const float cg = 2.f * wsum * coll_w;               // d pen / d (sum of samples)
             const float inv_s = 1.f / fb.scale;
@@ -796,7 +863,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
     din.part = (din.factor != 0.f) ? part + (size_t)slot * nparts * kPartFloats : nullptr;   // no penetration: nothing to add
     din.pflag = pflag + (size_t)slot * nparts;
     din.nparts = nparts;
-    resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
+    resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
     __syncthreads();
@@ -807,6 +874,11 @@ frame_step_kernel(ResidentModel m, CamSet cams, LossParams lp, LbfgsCfg cfg, Lbf
                     S.lg_new, L.H};
         lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
         __syncwarp();
+        if (s.phase == PH_DONE && s.stage + 1 < nstages) {      // this frame moves on to its next stage
+            next_stage_scalars(s);
+            VLOOP(i) S.lx_eval[i] = S.lx[i];
+            __syncwarp();
+        }
         VLOOP(i) {
             params[(size_t)b * kParams + i] = S.lx[i];
             L.g[(size_t)b * kParams + i] = S.lg[i];
@@ -926,14 +998,14 @@ int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, f
     return MVS_OK;
 }
 
-bool resident_lbfgs_available(const mvs_ctx* ctx, int H) {
-    const LossParams& lp = ctx->loss;
+bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int H) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
     return resident_supported(ctx) && !sdf_on && H <= 100;
 }
+bool resident_lbfgs_available(const mvs_ctx* ctx, int H) { return resident_lbfgs_available_for(ctx, ctx->loss, H); }
 
-int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, int H, void* sc_out, float* last_grad_dev,
-                          cudaStream_t st) {
+int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, int H, const void* lp_tab_dev, int nstages,
+                          void* sc_out, float* last_grad_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const LbfgsCfg& cfg = *static_cast<const LbfgsCfg*>(cfg_ptr);
     const size_t smem = sizeof(ResidentSmem) + (size_t)2 * H * kParams * sizeof(float);
@@ -942,20 +1014,22 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, 
         ctx->attr_res_lbfgs_smem = (int)smem;
     }
     MVS_LAUNCH(ctx, KID_RESIDENT_LBFGS, st,
-               lbfgs_resident_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, ctx->loss, cfg,
+               lbfgs_resident_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams,
+                                                                     static_cast<const LossParams*>(lp_tab_dev), nstages, cfg,
                                                                      params_dev, w.gt_uv, w.conf, w.joint_w, w.B, H,
                                                                      static_cast<FrameScalars*>(sc_out), last_grad_dev));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }
 
-bool hybrid_available(const mvs_ctx* ctx) {
-    const LossParams& lp = ctx->loss;
+bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
     return resident_supported(ctx) && sdf_on;
 }
+bool hybrid_available(const mvs_ctx* ctx) { return hybrid_available_for(ctx, ctx->loss); }
 
-int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, cudaStream_t st) {
+int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
+                      cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& dm = ctx->m;
     const LbfgsState& L = *static_cast<const LbfgsState*>(lbfgs_state);
@@ -966,7 +1040,7 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
         ctx->attr_done_step = true;
     }
     MVS_LAUNCH(ctx, KID_FRAME_STEP, st,
-               frame_step_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, ctx->loss, cfg, L, params_dev,
+               frame_step_kernel<<<w.na_bound > 0 ? w.na_bound : w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, L.lp_tab, nstages, cfg, L, params_dev,
                                                                  w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
                                                                  w.verts, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
                                                                  reinterpret_cast<const FrameBox*>(w.sdf_box),

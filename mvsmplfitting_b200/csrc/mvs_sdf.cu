@@ -335,7 +335,7 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
 }
 
 // ---------------------------------------------------------------------------------- dense regime, v4: fused adjoint
-// sdf_fused_kernel: P CTAs per frame, 1024 vertices each.  Per CTA: fold the skinning kernel's box partials (all
+// sdf_fused_kernel: P CTAs per frame, 1, 2 or 4 blocks of 256 vertices each.  Per CTA: fold the skinning kernel's box partials (all
 // threads), sample phi at the <= 8 voxels around each vertex, compact the vertices with a non-zero sample gradient
 // (deterministic order: warp, pass, lane) and -- because with the as-written semantics that list holds a handful of
 // vertices -- run the adjoint of the vertex stage for exactly those vertices right here:
@@ -343,8 +343,6 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
 // with g = d value / d local (UNIT scale; the frame factor cg/scale is linear and applied by frame_step once the
 // frame's total is known).
 constexpr int kSdfFThreads = 256;
-constexpr int kSdfFMaxPasses = 4;
-constexpr int kSdfFVerts = kSdfFThreads * kSdfFMaxPasses;    // <= 1024 vertices per CTA (sdf_passes_for)
 constexpr int kSdfFChunk = 128;                              // list entries per adjoint pass
 
 __device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, const int* __restrict__ faces,
@@ -378,8 +376,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
     const int slot = blockIdx.y, pidx = blockIdx.x;
     const int na = *na_ptr;
     if (slot >= na) return;
-    const int passes = sdf_passes_for(na, N), nparts = (N + kSdfFThreads * passes - 1) / (kSdfFThreads * passes);
-    if (pidx >= nparts) return;
+    const int passes = sdf_passes_for(na, N);         // 256-vertex blocks per CTA
+    if (pidx * passes * kSdfFThreads >= N) return;
     const int b = fidx[slot], t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (sc && sc[b].phase == PH_DONE) return;
     const float* vf = verts + (size_t)slot * N * 3;
@@ -391,8 +389,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
     __shared__ float tri0[9], cone[12], ctab[256];
     __shared__ float s_red[8][5];
     __shared__ int s_wcnt[8], s_woff[9];
-    __shared__ int seg_n[kSdfFVerts];                 // per-warp segments: warp w owns [128 w, 128 w + 128)
-    __shared__ float seg_g[kSdfFVerts * 3];
+    __shared__ int seg_n[kSdfFThreads];               // this block's vertices with a non-zero sample gradient
+    __shared__ float seg_g[kSdfFThreads * 3];
     __shared__ float sA[kSkinFloats];
     __shared__ int c_n[kSdfFChunk];
     __shared__ float c_dv[kSdfFChunk * 3], c_vp[kSdfFChunk * 3], c_dvp[kSdfFChunk * 3];
@@ -467,14 +465,18 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
     }
     __syncthreads();
-    // ---- samples
+    // ---- one 256-vertex block per pass.  Sums, vertex lists and adjoint partials are emitted PER BLOCK, so the
+    //      arithmetic of a frame does not depend on how many blocks this launch gave to one CTA (i.e. not on how
+    //      many other frames are still active): frames stay bit-for-bit independent problems.
     const bool cull = (num_faces == 1);
     const bool tab = (G <= 256);
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    int wcnt = 0;
-    const int n_base = pidx * (kSdfFThreads * passes) + warp * (32 * passes);
+    const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
+    bool have_A = false;
     for (int pass = 0; pass < passes; ++pass) {
-        const int n = n_base + pass * 32 + lane;
+        const int blk = pidx * passes + pass;
+        if (blk >= nblocks) break;
+        const int n = blk * kSdfFThreads + t;
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float gcv[3] = {0.f, 0.f, 0.f};
         if (n < N) {
             float loc[3], w1[3];
@@ -519,125 +521,122 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 gcv[c] = dix[c] * (0.5f * G);
-                acc[1 + c] += gcv[c]; gdl += gcv[c] * loc[c];
+                acc[1 + c] = gcv[c]; gdl += gcv[c] * loc[c];
             }
-            acc[0] += val;
-            acc[4] += gdl;
+            acc[0] = val;
+            acc[4] = gdl;
         }
         const bool nz = (gcv[0] != 0.f) || (gcv[1] != 0.f) || (gcv[2] != 0.f);
         const unsigned mask = __ballot_sync(0xffffffffu, nz);
-        if (nz) {
-            const int pos = warp * (32 * kSdfFMaxPasses) + wcnt + __popc(mask & ((1u << lane) - 1u));
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float a = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) s_red[warp][q] = a;
+        }
+        if (lane == 0) s_wcnt[warp] = __popc(mask);
+        __syncthreads();                                   // also: the previous block's adjoint is done with c_* / seg_*
+        if (t < 5) {
+            float a = 0.f;
+            for (int w2 = 0; w2 < 8; ++w2) a += s_red[w2][t];
+            parts5[((size_t)slot * nblocks + blk) * 5 + t] = a;
+        }
+        if (t == 0) {
+            int o = 0;
+            for (int w2 = 0; w2 < 8; ++w2) { s_woff[w2] = o; o += s_wcnt[w2]; }
+            s_woff[8] = o;
+            pflag[(size_t)slot * nblocks + blk] = o > 0 ? 1 : 0;
+        }
+        __syncthreads();
+        const int total = s_woff[8];
+        if (total == 0) continue;
+        if (nz) {                                          // ascending vertex order: (warp, lane)
+            const int pos = s_woff[warp] + __popc(mask & ((1u << lane) - 1u));
             seg_n[pos] = n; seg_g[3 * pos] = gcv[0]; seg_g[3 * pos + 1] = gcv[1]; seg_g[3 * pos + 2] = gcv[2];
         }
-        wcnt += __popc(mask);
-    }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        float a = acc[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s_red[warp][q] = a;
-    }
-    if (lane == 0) s_wcnt[warp] = wcnt;
-    __syncthreads();
-    if (t < 5) {
-        float a = 0.f;
-        for (int w2 = 0; w2 < 8; ++w2) a += s_red[w2][t];
-        parts5[((size_t)slot * nparts + pidx) * 5 + t] = a;
-    }
-    if (t == 0) {
-        int o = 0;
-        for (int w2 = 0; w2 < 8; ++w2) { s_woff[w2] = o; o += s_wcnt[w2]; }
-        s_woff[8] = o;
-        pflag[(size_t)slot * nparts + pidx] = o > 0 ? 1 : 0;
-    }
-    __syncthreads();
-    const int total = s_woff[8];
-    if (total == 0) return;
-    // ---- adjoint of the vertex stage for the listed vertices (unit frame factor)
-    for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
-    float accA0 = 0.f, accA1 = 0.f;
-    float accP[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // d Phi[lane + 32 i], this warp's share of the columns
-    for (int e0 = 0; e0 < total; e0 += kSdfFChunk) {
-        const int cnt = min(kSdfFChunk, total - e0);
-        __syncthreads();
-        if (t < cnt) {
-            // entry (e0 + t) of the concatenated list -> (warp segment, offset)
-            const int ge = e0 + t;
-            int w2 = 0;
-#pragma unroll
-            for (int q = 1; q < 8; ++q) w2 += (ge >= s_woff[q]) ? 1 : 0;
-            const int src = w2 * (32 * kSdfFMaxPasses) + (ge - s_woff[w2]);
-            const int n = seg_n[src];
-            c_n[t] = n;
-            const float d0 = seg_g[3 * src], d1 = seg_g[3 * src + 1], d2 = seg_g[3 * src + 2];
-            float Gm[9];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) Gm[c] = 0.f;
-            for (int e = 0; e < KW; ++e) {
-                const float w = ell_w[(size_t)n * KW + e];
-                if (w != 0.f) {
-                    const float* Aj = &sA[12 * ell_j[(size_t)n * KW + e]];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) Gm[3 * r + c] = fmaf(w, Aj[4 * r + c], Gm[3 * r + c]);
-                }
-            }
-            c_dv[3 * t] = d0; c_dv[3 * t + 1] = d1; c_dv[3 * t + 2] = d2;
-            c_dvp[3 * t] = Gm[0] * d0 + Gm[3] * d1 + Gm[6] * d2;
-            c_dvp[3 * t + 1] = Gm[1] * d0 + Gm[4] * d1 + Gm[7] * d2;
-            c_dvp[3 * t + 2] = Gm[2] * d0 + Gm[5] * d1 + Gm[8] * d2;
-            const float* vpn = vposed + ((size_t)slot * N + n) * 3;
-            c_vp[3 * t] = vpn[0]; c_vp[3 * t + 1] = vpn[1]; c_vp[3 * t + 2] = vpn[2];
+        if (!have_A) {
+            for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
+            have_A = true;
         }
-        __syncthreads();
-        {   // dA: thread t owns entry t (and 256 + t for t < 32)
-            const int j0 = t / 12, r0 = (t % 12) / 4, cc0 = t % 4;
-            const int e1 = t + kSdfFThreads, j1 = e1 / 12, r1 = (e1 % 12) / 4, cc1 = e1 % 4;
-            const bool two = t < kSkinFloats - kSdfFThreads;
+        // ---- adjoint of the vertex stage for the listed vertices of this block (unit frame factor)
+        float accA0 = 0.f, accA1 = 0.f;
+        float accP[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // d Phi[lane + 32 i], this warp's share of the columns
+        for (int e0 = 0; e0 < total; e0 += kSdfFChunk) {
+            const int cnt = min(kSdfFChunk, total - e0);
+            __syncthreads();
+            if (t < cnt) {
+                const int src = e0 + t;
+                const int nn = seg_n[src];
+                c_n[t] = nn;
+                const float d0 = seg_g[3 * src], d1 = seg_g[3 * src + 1], d2 = seg_g[3 * src + 2];
+                float Gm[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) Gm[c] = 0.f;
+                for (int e = 0; e < KW; ++e) {
+                    const float w = ell_w[(size_t)nn * KW + e];
+                    if (w != 0.f) {
+                        const float* Aj = &sA[12 * ell_j[(size_t)nn * KW + e]];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) Gm[3 * r + c] = fmaf(w, Aj[4 * r + c], Gm[3 * r + c]);
+                    }
+                }
+                c_dv[3 * t] = d0; c_dv[3 * t + 1] = d1; c_dv[3 * t + 2] = d2;
+                c_dvp[3 * t] = Gm[0] * d0 + Gm[3] * d1 + Gm[6] * d2;
+                c_dvp[3 * t + 1] = Gm[1] * d0 + Gm[4] * d1 + Gm[7] * d2;
+                c_dvp[3 * t + 2] = Gm[2] * d0 + Gm[5] * d1 + Gm[8] * d2;
+                const float* vpn = vposed + ((size_t)slot * N + nn) * 3;
+                c_vp[3 * t] = vpn[0]; c_vp[3 * t + 1] = vpn[1]; c_vp[3 * t + 2] = vpn[2];
+            }
+            __syncthreads();
+            {   // dA: thread t owns entry t (and 256 + t for t < 32)
+                const int j0 = t / 12, r0 = (t % 12) / 4, cc0 = t % 4;
+                const int e1 = t + kSdfFThreads, j1 = e1 / 12, r1 = (e1 % 12) / 4, cc1 = e1 % 4;
+                const bool two = t < kSkinFloats - kSdfFThreads;
 #pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-                const float* wrow = Wd + (size_t)c_n[i] * kJoints;
-                const float w0 = __ldg(wrow + j0);
-                const float w1v = two ? __ldg(wrow + j1) : 0.f;
-                if (w0 != 0.f) {
-                    const float wd = w0 * c_dv[3 * i + r0];
-                    accA0 = (cc0 < 3) ? fmaf(wd, c_vp[3 * i + cc0], accA0) : accA0 + wd;
-                }
-                if (w1v != 0.f) {
-                    const float wd = w1v * c_dv[3 * i + r1];
-                    accA1 = (cc1 < 3) ? fmaf(wd, c_vp[3 * i + cc1], accA1) : accA1 + wd;
+                for (int i = 0; i < cnt; ++i) {
+                    const float* wrow = Wd + (size_t)c_n[i] * kJoints;
+                    const float w0 = __ldg(wrow + j0);
+                    const float w1v = two ? __ldg(wrow + j1) : 0.f;
+                    if (w0 != 0.f) {
+                        const float wd = w0 * c_dv[3 * i + r0];
+                        accA0 = (cc0 < 3) ? fmaf(wd, c_vp[3 * i + cc0], accA0) : accA0 + wd;
+                    }
+                    if (w1v != 0.f) {
+                        const float wd = w1v * c_dv[3 * i + r1];
+                        accA1 = (cc1 < 3) ? fmaf(wd, c_vp[3 * i + cc1], accA1) : accA1 + wd;
+                    }
                 }
             }
+            // d Phi: a warp takes every 8th column and reads its whole Qk row (7 coalesced loads per lane, two columns
+            // = 14 independent loads in flight); the eight warps' shares are folded in a fixed order below
+            for (int col = warp; col < 3 * cnt; col += 16) {
+                const int colb = col + 8;
+                const bool hb = colb < 3 * cnt;
+                const float* ra = Qk + (size_t)(3 * c_n[col / 3] + col % 3) * kFeatPad + lane;
+                const float* rb = Qk + (size_t)(3 * c_n[(hb ? colb : col) / 3] + (hb ? colb : col) % 3) * kFeatPad + lane;
+                float qa[7], qb[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { qa[i] = __ldg(ra + 32 * i); qb[i] = __ldg(rb + 32 * i); }
+                const float da = c_dvp[col], db = hb ? c_dvp[colb] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { accP[i] = fmaf(da, qa[i], accP[i]); accP[i] = fmaf(db, qb[i], accP[i]); }
+            }
         }
-        // d Phi: a warp takes every 8th column and reads its whole Qk row (7 coalesced loads per lane, two columns =
-        // 14 independent loads in flight); the eight warps' shares are folded in a fixed order below
-        for (int col = warp; col < 3 * cnt; col += 16) {
-            const int colb = col + 8;
-            const bool hb = colb < 3 * cnt;
-            const float* ra = Qk + (size_t)(3 * c_n[col / 3] + col % 3) * kFeatPad + lane;
-            const float* rb = Qk + (size_t)(3 * c_n[(hb ? colb : col) / 3] + (hb ? colb : col) % 3) * kFeatPad + lane;
-            float qa[7], qb[7];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) { qa[i] = __ldg(ra + 32 * i); qb[i] = __ldg(rb + 32 * i); }
-            const float da = c_dvp[col], db = hb ? c_dvp[colb] : 0.f;
+        for (int i = 0; i < 7; ++i) s_dphi[warp][lane + 32 * i] = accP[i];
+        __syncthreads();
+        float* o = part + ((size_t)slot * nblocks + blk) * kPartFloats;
+        o[t] = accA0;
+        if (t < kSkinFloats - kSdfFThreads) o[kSdfFThreads + t] = accA1;
+        if (t < kFeatPad) {
+            float a = 0.f;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) { accP[i] = fmaf(da, qa[i], accP[i]); accP[i] = fmaf(db, qb[i], accP[i]); }
+            for (int w2 = 0; w2 < 8; ++w2) a += s_dphi[w2][t];
+            o[kSkinFloats + t] = a;
         }
-    }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) s_dphi[warp][lane + 32 * i] = accP[i];
-    __syncthreads();
-    float* o = part + ((size_t)slot * nparts + pidx) * kPartFloats;
-    o[t] = accA0;
-    if (t < kSkinFloats - kSdfFThreads) o[kSdfFThreads + t] = accA1;
-    if (t < kFeatPad) {
-        float a = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) a += s_dphi[w2][t];
-        o[kSkinFloats + t] = a;
     }
 }
 
@@ -646,19 +645,20 @@ int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars
     const DevModel& m = ctx->m;
     const LossParams& lp = ctx->loss;
     const int B = w.B, N = m.N;
-    const int nparts = sdf_parts_for(1, N);           // the finest split (buffers, grid); the kernel picks by *na_ptr
+    const int nparts = sdf_parts_for(1, N);           // the finest split (grid); the kernel picks by *na_ptr
+    const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
     int rc;
     if (!w.sdf_parts5) {
-        if ((rc = dev_alloc(ctx, &w.sdf_parts5, (size_t)B * nparts * 5))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_part, (size_t)B * nparts * kPartFloats))) return rc;
-        if ((rc = dev_alloc(ctx, &w.sdf_pflag, (size_t)B * nparts))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_parts5, (size_t)B * nblocks * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_part, (size_t)B * nblocks * kPartFloats))) return rc;
+        if ((rc = dev_alloc(ctx, &w.sdf_pflag, (size_t)B * nblocks))) return rc;
     }
     if (!w.sdf_box) {
         unsigned char* raw = nullptr;
         if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
         w.sdf_box = raw;
     }
-    dim3 g(nparts, B);
+    dim3 g(nparts, w.na_bound > 0 ? w.na_bound : B);
     MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
                sdf_fused_kernel<<<g, kSdfFThreads, 0, st>>>(w.verts, w.vposed, x_dev, w.fidx, w.na,
                                                             static_cast<const FrameScalars*>(frame_scalars), N, (N + 63) / 64,

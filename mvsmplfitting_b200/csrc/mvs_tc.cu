@@ -411,7 +411,7 @@ int tc_upload_model(mvs_ctx* ctx, const float* Qk_host) {
 }
 
 bool tc_available(const mvs_ctx* ctx) {
-    return ctx->exec_mode == 0 && ctx->tc != nullptr && ctx->ws.PhiTc != nullptr;
+    return ctx->exec_mode != 1 && ctx->tc != nullptr && ctx->ws.PhiTc != nullptr;
 }
 
 int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
@@ -428,13 +428,14 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
         T->ready = true;
     }
     const int ntiles = (m.N + kTileV - 1) / kTileV;
-    const int mtiles = (w.B + kTcBM - 1) / kTcBM;
+    const int nb = w.na_bound > 0 ? w.na_bound : w.B;             // upper bound of the active-frame count
+    const int mtiles = (nb + kTcBM - 1) / kTcBM;
     dim3 grid(std::min(ctx->sm_count, ntiles), mtiles);          // surplus CTAs exit: the kernel splits the tiles from *na
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
                posedirs_gemm_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, w.ldA, 3 * m.N, w.na, ctx->sm_count,
                                                                           ntiles, T->poffT, T->err));
     // one wave of CTAs (two per SM): each CTA keeps its 32 frames' transforms in shared memory and walks several chunks
-    const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (w.B + 31) / 32;
+    const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (nb + 31) / 32;
     dim3 g2(nchunks, fgroups);                          // surplus CTAs exit: the kernel sizes its chunk loop from *na
     MVS_LAUNCH(ctx, KID_SKIN, st,
                skin_kernel<<<g2, kSkinThreads, kSkinSmem, st>>>(T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N,

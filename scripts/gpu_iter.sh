@@ -2,6 +2,6 @@
 # one development iteration on the GPU box: tests, per-phase timing of frame_step, bench line
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/i_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/i_pytest.txt
-tail -5 gpurun_out/i_pytest.txt
-timeout 120 python scripts/phase_times.py > gpurun_out/i_phase.txt 2>&1; tail -32 gpurun_out/i_phase.txt
-timeout 600 python bench.py --steps 3 --warmup 2 > gpurun_out/i_bench.txt 2> gpurun_out/i_bench.err; tail -c 1500 gpurun_out/i_bench.txt; tail -3 gpurun_out/i_bench.err
+tail -3 gpurun_out/i_pytest.txt
+timeout 120 python scripts/phase_times.py > gpurun_out/i_phase.txt 2>&1; tail -3 gpurun_out/i_phase.txt
+timeout 600 python bench.py --steps 3 --warmup 2 > gpurun_out/i_bench.txt 2> gpurun_out/i_bench.err; tail -c 600 gpurun_out/i_bench.txt; tail -3 gpurun_out/i_bench.err

@@ -38,3 +38,5 @@ for i in range(1, 29):
     print("%2d %-56s %8d %8.2f" % (i, NAMES.get(i, ""), d, d / ghz / 1e3))
     prev = buf[i]
 print("total %.2f us" % ((prev - buf[0]) / ghz / 1e3))
+print("max over all CTAs and launches (us): closure %.2f | history wait %.2f | advance+write-back %.2f | next pose %.2f | "
+      "start->advanced %.2f | start->end %.2f" % tuple(buf[32 + k] / ghz / 1e3 for k in range(6)))

@@ -251,6 +251,7 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* d) {
         if (rc) return rc;
     }
     if (d->faces && d->n_faces > 0) {
+        for (int c = 0; c < 3; ++c) m.tri0[c] = d->faces[c];
         int rc = dev_upload(ctx, &m.faces, d->faces, (size_t)d->n_faces * 3);
         if (rc) return rc;
     }
@@ -390,6 +391,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.bboxp, (size_t)B * ((m.N + 63) / 64) * 12))) return rc;
     if ((rc = dev_alloc(ctx, &w.At, (size_t)kSkinFloats * w.ldA))) return rc;
     if ((rc = dev_alloc(ctx, &w.gchain, (size_t)B * kJoints * 3))) return rc;
+    if ((rc = dev_alloc(ctx, &w.slot_tr, (size_t)B * 4))) return rc;
     if ((rc = dev_alloc(ctx, &w.vposed, (size_t)B * m.N * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.verts, (size_t)B * m.N * 3))) return rc;
     if ((rc = dev_alloc(ctx, &w.dv, (size_t)B * (m.nsup + m.N) * 3))) return rc;

@@ -68,13 +68,15 @@ __global__ void __launch_bounds__(kFrameThreads)
 frame_fwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, const int* __restrict__ na_ptr,
                  Parents par, const float* __restrict__ Jt, const float* __restrict__ JS,
                  float* __restrict__ Phi, float* __restrict__ PhiTc, float* __restrict__ At, int ldA,
-                 float* __restrict__ gchain) {
+                 float* __restrict__ gchain, float* __restrict__ slot_tr) {
+    pdl_wait();
     const int slot = blockIdx.x;
     if (slot >= *na_ptr) return;
     const int b = fidx[slot];
     __shared__ PoseSmem s;
     pose_forward_block(x + (size_t)b * kParams, par, Jt, JS, s);
     const int t = threadIdx.x;
+    if (slot_tr && t < 3) slot_tr[4 * slot + t] = x[(size_t)b * kParams + kOffTransl + t];
     for (int k = t; k < kFeatPad; k += blockDim.x) {
         float v;
         if (k < kPoseBasis) v = s.R[9 + k] - (((k % 9) % 4 == 0) ? 1.0f : 0.0f);   // lbs.py:192
@@ -751,7 +753,7 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
 
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
                frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.PhiTc, w.At, w.ldA,
-                                                             w.gchain));
+                                                             w.gchain, w.slot_tr));
     if (dense) {
         int rc = launch_vertex_fwd_dense(ctx, st);
         if (rc) return rc;
@@ -819,7 +821,7 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
     MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
                frame_fwd_kernel<<<w.na_bound > 0 ? w.na_bound : w.B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, ctx->parents, m.Jt,
-                                                              m.JS, w.Phi, w.PhiTc, w.At, w.ldA, w.gchain));
+                                                              m.JS, w.Phi, w.PhiTc, w.At, w.ldA, w.gchain, w.slot_tr));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -1,5 +1,6 @@
 // Internal types of libmvsmpl.so (not part of the ABI).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -55,6 +56,7 @@ struct DevModel {
     float* Wd = nullptr;
     float* ST = nullptr;      // [N][3][11] shapedirs row | template, fp32 (skinning kernel of the tensor-core path)
     int* faces = nullptr;
+    int tri0[3] = {0, 0, 0};          // vertex ids of face 0 (the triangle the as-written SDF term sees)
     // keypoints: k-th keypoint = sum_e kp_w[e] * v[kp_vidx[e]]  (+ posed chain joint kp_chain[k] if >= 0) + transl
     int K = 0, n_kp_entries = 0, nsup = 0;
     int* kp_ptr = nullptr;    // [K+1]
@@ -89,6 +91,7 @@ struct Workspace {
     float* PhiTc = nullptr;           // [ldA][224] pose feature rounded to TF32 (A operand of the tensor-core contraction)
     float* At = nullptr;              // [288][ldA]   skinning transforms, frame fastest
     float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
+    float* slot_tr = nullptr;         // [B][4] translation of the frame in each slot (dense-regime kernels index by slot only)
     float* vposed = nullptr;          // [B][nvmax][3]
     float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
     float* dv = nullptr;              // [B][nsup + N][3]
@@ -195,6 +198,27 @@ void prof_mark(mvs_ctx* ctx, int kid, cudaStream_t st);   // records one event o
         if ((ctx)->prof.mask >> (kid) & 1u) mvs::prof_mark(ctx, kid, st); \
         (ctx)->launches++;                                                \
     } while (0)
+
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the stream is still
+// draining; it must execute pdl_wait() before touching anything the predecessor wrote (here: first statement).  The
+// dense-regime rounds are chains of short dependent kernels, so this takes the launch latency of every link off the
+// critical path.  Expands to a plain launch when the attribute is not supported.
+// pdl_wait(): predecessor complete and its writes visible; then let OUR successor be scheduled as soon as all of our
+// CTAs have started (its CTAs park in their own pdl_wait, prologue done, until this grid has drained).
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 template <class T> int dev_alloc(mvs_ctx* ctx, T** p, size_t count);
 template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t count);

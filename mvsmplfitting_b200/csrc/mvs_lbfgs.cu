@@ -80,6 +80,7 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
 
 // Ordered compaction of the frames that still need closure evaluations.
 __global__ void __launch_bounds__(1024) lbfgs_compact_kernel(LbfgsState S, int B, int* __restrict__ fidx, int* __restrict__ na) {
+    pdl_wait();
     if (threadIdx.x == 0 && *na > 0) S.totals[3] += 1;     // rounds that actually evaluated something
     __shared__ int wsum[32];
     __shared__ int base;

@@ -101,7 +101,7 @@ __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsP
                                                    const LbfgsCfg& cfg, const int lane) {
     float* const x = P.x; float* const g = P.g; float* const d = P.d; float* const prev_g = P.prev_g;
     float* const x_init = P.x_init; float* const g_prev = P.g_prev; float* const bg0 = P.bg0; float* const bg1 = P.bg1;
-    float* const hy = P.hy; float* const hs = P.hs; float* const ro = P.ro; float* const al = P.al;
+    float* const hy = P.hy; float* const hs = P.hs; float* const ro = P.ro;
     float* const x_eval = P.x_eval; const float* const g_new = P.g_new;
     const float c1 = 1e-4f, c2 = 0.9f;
     s.pushed_slot = -1;
@@ -154,27 +154,57 @@ __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsP
                     s.H_diag = ys / yy;
                 }
                 __syncwarp();
-                // two-loop recursion (collapsed to one buffer like the reference), q lives in registers
+                // two-loop recursion (collapsed to one buffer like the reference), q lives in registers.  The chain
+                // dot -> shuffle tree -> axpy is strictly serial in the history index, so everything that does not
+                // depend on q is taken off it: the NEXT pair's rows are loaded before the current reduction starts,
+                // the ring index is stepped incrementally and alpha stays in registers (lane k % 32, no shared-memory
+                // store that the loads would have to be ordered against).
                 float q[3] = {0.f, 0.f, 0.f};
                 VL(c, i) q[c] = -g[i];
-                for (int k = s.hist_len - 1; k >= 0; --k) {
-                    const int w = (s.hist_head + k) % P.H;
-                    float p = 0.f;
-                    VL(c, i) p = fmaf(hs[(size_t)w * kParams + i], q[c], p);
-                    const float a = warp_sum(p) * ro[w];
-                    if (lane == 0) al[k] = a;
-                    VL(c, i) q[c] = fmaf(-a, hy[(size_t)w * kParams + i], q[c]);
+                float al_r[4] = {0.f, 0.f, 0.f, 0.f};            // alpha[k] lives in lane k & 31, register k >> 5
+                const int hl = s.hist_len;
+                {
+                    int w = (s.hist_head + hl - 1) % P.H;
+                    float sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f}, rw = 0.f;
+                    if (hl > 0) { VL(c, i) { sv[c] = hs[(size_t)w * kParams + i]; yv[c] = hy[(size_t)w * kParams + i]; } rw = ro[w]; }
+                    for (int k = hl - 1; k >= 0; --k) {
+                        const int wn = (w == 0) ? P.H - 1 : w - 1;
+                        float sn[3] = {0.f, 0.f, 0.f}, yn[3] = {0.f, 0.f, 0.f}, rn = 0.f;
+                        if (k > 0) { VL(c, i) { sn[c] = hs[(size_t)wn * kParams + i]; yn[c] = hy[(size_t)wn * kParams + i]; } rn = ro[wn]; }
+                        float p = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) p = fmaf(sv[c], q[c], p);
+                        const float a = warp_sum(p) * rw;
+                        if (lane == (k & 31)) {
+                            const int r = k >> 5;
+                            if (r == 0) al_r[0] = a; else if (r == 1) al_r[1] = a; else if (r == 2) al_r[2] = a; else al_r[3] = a;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { q[c] = fmaf(-a, yv[c], q[c]); sv[c] = sn[c]; yv[c] = yn[c]; }
+                        rw = rn; w = wn;
+                    }
                 }
-                __syncwarp();
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) q[cc] *= s.H_diag;
-                for (int k = 0; k < s.hist_len; ++k) {
-                    const int w = (s.hist_head + k) % P.H;
-                    float p = 0.f;
-                    VL(c, i) p = fmaf(hy[(size_t)w * kParams + i], q[c], p);
-                    const float be = warp_sum(p) * ro[w];
-                    const float coef = al[k] - be;
-                    VL(c, i) q[c] = fmaf(coef, hs[(size_t)w * kParams + i], q[c]);
+                {
+                    int w = s.hist_head % P.H;
+                    float sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f}, rw = 0.f;
+                    if (hl > 0) { VL(c, i) { sv[c] = hs[(size_t)w * kParams + i]; yv[c] = hy[(size_t)w * kParams + i]; } rw = ro[w]; }
+                    for (int k = 0; k < hl; ++k) {
+                        const int wn = (w + 1 == P.H) ? 0 : w + 1;
+                        float sn[3] = {0.f, 0.f, 0.f}, yn[3] = {0.f, 0.f, 0.f}, rn = 0.f;
+                        if (k + 1 < hl) { VL(c, i) { sn[c] = hs[(size_t)wn * kParams + i]; yn[c] = hy[(size_t)wn * kParams + i]; } rn = ro[wn]; }
+                        const int r = k >> 5;
+                        const float alk = __shfl_sync(0xffffffffu, r == 0 ? al_r[0] : r == 1 ? al_r[1] : r == 2 ? al_r[2] : al_r[3], k & 31);
+                        float p = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) p = fmaf(yv[c], q[c], p);
+                        const float be = warp_sum(p) * rw;
+                        const float coef = alk - be;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { q[c] = fmaf(coef, sv[c], q[c]); sv[c] = sn[c]; yv[c] = yn[c]; }
+                        rw = rn; w = wn;
+                    }
                 }
                 VL(c, i) d[i] = q[c];
             }

@@ -43,6 +43,7 @@ __device__ __forceinline__ void phase_mark(int i) {
 
 constexpr int kResThreads = 256;
 constexpr int kResMaxSup = 96;            // support vertices (SMPL: 86)
+constexpr int kResMaxSupJ = 512;          // (support vertex, joint) pairs with a non-zero skinning weight (SMPL: <= 344)
 constexpr int kResMaxVK = 272;            // views x keypoints (16 x 17)
 constexpr int kResMaxM = 8;               // GMM components
 
@@ -89,10 +90,14 @@ struct ResidentSmem {
     // level schedule of the kinematic tree (copy of ResidentModel::cs / par: shared-memory latency instead of
     // dependent constant-bank loads inside the level loops)
     int nlev, lev_ptr[kJoints + 1], lev_j[kJoints], ch_ptr[kJoints + 1], ch_j[kJoints], par[kJoints];
+    // per joint: the support vertices it skins (copy of supj_*: the dA loop of P7 is a chain of dependent list reads)
+    int sj_ptr[kJoints + 1], sj_i[kResMaxSupJ], sj_on;
+    float sj_w[kResMaxSupJ];
     // dense regime: frame scalars of the SDF term and its box-extreme vertex list (frame_step_kernel)
     int ext_n[8];
     float ext_d[24];
     float sdf_sc[4];                       // [0] cg / scale, [1] pen loss, [2] number of extreme entries
+    int fl[64], nfl;                       // 256-vertex blocks with a penetration adjoint partial
     LossParams lp;                         // this frame's CURRENT stage (multi-stage kernels)
     FrameScalars fs;
 };
@@ -107,9 +112,9 @@ struct DenseIn {
     int n_extra;
     float pen_loss;
     const float* Wd;          // [N][24] dense skinning weights (adjoint of the extra vertices)
-    const float* part;        // [nparts][512] this frame's unit-factor partial adjoints, or NULL (no penetration)
-    const int* pflag;         // [nparts]
-    int nparts;
+    const float* part;        // [nblocks][512] this frame's unit-factor partial adjoints, or NULL (no penetration)
+    const int* fl;            // [nfl] blocks that wrote partials, ascending
+    int nfl;
     float factor;             // cg / scale: d pen / d (sum of samples) over the box scale
 };
 
@@ -259,6 +264,13 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             S.vp[col] = din.vposed[3 * n + col % 3];
             S.v[col] = din.verts[3 * n + col % 3];
         }
+        // the box-extreme vertices of the penetration term ride along as support entries nsup .. nsup + n_extra - 1
+        if (t < 3 * din.n_extra) {
+            const int n = din.extra_n[t / 3];
+            S.vp[ncol + t] = din.vposed[3 * n + t % 3];
+            S.dv[ncol + t] = din.extra_d[t];
+            S.rowbase[ncol + t] = 3 * n + t % 3;
+        }
     } else {
         const float4 ph0 = *reinterpret_cast<const float4*>(&S.Phi[4 * lane]);
         const float4 ph1 = lane < 24 ? *reinterpret_cast<const float4*>(&S.Phi[128 + 4 * lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -392,8 +404,9 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
     PHASE_MARK(10);
     if (have_grad) {
         // ---- P7 adjoint of skinning: dvp = T3x3^T dv ; dA_j = sum_i W[i,j] [dv (x) vp | dv]
-        if (t < nsup) {
-            const int n = m.sup[t];
+        const int nx = din.n_extra, ncol_all = ncol + 3 * nx;
+        if (t < nsup + nx) {
+            const int n = t < nsup ? m.sup[t] : din.extra_n[t - nsup];
             float G[9];
 #pragma unroll
             for (int c = 0; c < 9; ++c) G[c] = 0.f;
@@ -415,11 +428,32 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         for (int e = t; e < kSkinFloats; e += kResThreads) {
             const int j = e / 12, r = (e % 12) / 4, c = e % 4;
             float a = 0.f;
+            if (S.sj_on) {
 #pragma unroll 4
-            for (int q2 = m.supj_ptr[j]; q2 < m.supj_ptr[j + 1]; ++q2) {
-                const int i = m.supj_i[q2];
-                const float wd = m.supj_w[q2] * S.dv[3 * i + r];
-                a = (c < 3) ? fmaf(wd, S.vp[3 * i + c], a) : a + wd;
+                for (int q2 = S.sj_ptr[j]; q2 < S.sj_ptr[j + 1]; ++q2) {
+                    const int i = S.sj_i[q2];
+                    const float wd = S.sj_w[q2] * S.dv[3 * i + r];
+                    a = (c < 3) ? fmaf(wd, S.vp[3 * i + c], a) : a + wd;
+                }
+            } else {
+#pragma unroll 4
+                for (int q2 = m.supj_ptr[j]; q2 < m.supj_ptr[j + 1]; ++q2) {
+                    const int i = m.supj_i[q2];
+                    const float wd = m.supj_w[q2] * S.dv[3 * i + r];
+                    a = (c < 3) ? fmaf(wd, S.vp[3 * i + c], a) : a + wd;
+                }
+            }
+            for (int k = 0; k < nx; ++k) {                     // box-extreme vertices: generic (dense-W) joint ownership
+                const float w = __ldg(din.Wd + (size_t)din.extra_n[k] * kJoints + j);
+                if (w != 0.f) {
+                    const float wd = w * S.dv[3 * (nsup + k) + r];
+                    a = (c < 3) ? fmaf(wd, S.vp[3 * (nsup + k) + c], a) : a + wd;
+                }
+            }
+            if (din.part) {                                    // penetration gradient: unit-factor block partials
+                float pa = 0.f;                                // fixed summation order (ascending block index)
+                for (int q = 0; q < din.nfl; ++q) pa += din.part[(size_t)din.fl[q] * kPartFloats + e];
+                a = fmaf(pa, din.factor, a);
             }
             S.dA[e] = a;
         }
@@ -429,83 +463,23 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         if (t < kFeatPad) {
             float a = 0.f;
             int col = 0;
-            for (; col + 12 <= ncol; col += 12) {              // 12 independent L2 loads in flight per thread
+            for (; col + 12 <= ncol_all; col += 12) {          // 12 independent L2 loads in flight per thread
                 float qv[12];
 #pragma unroll
                 for (int u = 0; u < 12; ++u) qv[u] = __ldg(m.Qk + (size_t)S.rowbase[col + u] * kFeatPad + t);
 #pragma unroll
                 for (int u = 0; u < 12; ++u) a = fmaf(S.dvp[col + u], qv[u], a);
             }
-            for (; col < ncol; ++col) a = fmaf(S.dvp[col], __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t), a);
+            for (; col < ncol_all; ++col) a = fmaf(S.dvp[col], __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t), a);
+            if (din.part) {
+                float pa = 0.f;
+                for (int q = 0; q < din.nfl; ++q) pa += din.part[(size_t)din.fl[q] * kPartFloats + kSkinFloats + t];
+                a = fmaf(pa, din.factor, a);
+            }
             S.dPhi[t] = a;
         }
         __syncthreads();
         PHASE_MARK(12);
-        // ---- P8b dense regime: vertices with a penetration gradient, in chunks of kResMaxSup (reusing vp/dv/dvp);
-        //      same adjoint as P7/P8 with generic (dense-W) joint ownership -- deterministic, no atomics
-        for (int e0 = 0; e0 < din.n_extra; e0 += kResMaxSup) {
-            const int cnt = min(kResMaxSup, din.n_extra - e0);
-            for (int col = t; col < 3 * cnt; col += kResThreads) {
-                const int n = din.extra_n[e0 + col / 3];
-                S.rowbase[col] = 3 * n + col % 3;
-                S.vp[col] = din.vposed[3 * n + col % 3];
-                S.dv[col] = din.extra_d[(size_t)(e0 + col / 3) * 3 + col % 3];
-            }
-            __syncthreads();
-            if (t < cnt) {
-                const int n = din.extra_n[e0 + t];
-                float G[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) G[c] = 0.f;
-                for (int e = 0; e < m.KW; ++e) {
-                    const float w = m.ell_w[(size_t)n * m.KW + e];
-                    if (w != 0.f) {
-                        const float* Aj = &S.A[12 * m.ell_j[(size_t)n * m.KW + e]];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) G[3 * r + c] = fmaf(w, Aj[4 * r + c], G[3 * r + c]);
-                    }
-                }
-                const float d0 = S.dv[3 * t], d1 = S.dv[3 * t + 1], d2 = S.dv[3 * t + 2];
-                S.dvp[3 * t] = G[0] * d0 + G[3] * d1 + G[6] * d2;
-                S.dvp[3 * t + 1] = G[1] * d0 + G[4] * d1 + G[7] * d2;
-                S.dvp[3 * t + 2] = G[2] * d0 + G[5] * d1 + G[8] * d2;
-            }
-            for (int e = t; e < kSkinFloats; e += kResThreads) {
-                const int j = e / 12, r = (e % 12) / 4, c = e % 4;
-                float a = 0.f;
-                for (int i = 0; i < cnt; ++i) {
-                    const float w = __ldg(din.Wd + (size_t)din.extra_n[e0 + i] * kJoints + j);
-                    if (w != 0.f) {
-                        const float wd = w * S.dv[3 * i + r];
-                        a = (c < 3) ? fmaf(wd, S.vp[3 * i + c], a) : a + wd;
-                    }
-                }
-                S.dA[e] += a;
-            }
-            __syncthreads();
-            if (t < kFeatPad) {
-                float a = 0.f;
-                for (int col = 0; col < 3 * cnt; ++col) a = fmaf(S.dvp[col], __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t), a);
-                S.dPhi[t] += a;
-            }
-            __syncthreads();
-        }
-        if (din.part) {                   // penetration gradient: unit-factor partial adjoints of the listed vertices
-            for (int e = t; e < kPartFloats; e += kResThreads) {
-                float a = 0.f;                // fixed summation order (part 0,1,2,...); parts without vertices wrote nothing
-                for (int p = 0; p < din.nparts; ++p)
-                    if (din.pflag[p]) a += din.part[(size_t)p * kPartFloats + e];
-                a *= din.factor;
-                if (e < kSkinFloats) S.dA[e] += a; else S.dPhi[e - kSkinFloats] += a;
-            }
-            __syncthreads();
-            PHASE_MARK(13);
-        }
-        if (din.n_extra > 0) {            // restore the support-list row map for the next evaluation
-            for (int col = t; col < ncol; col += kResThreads) S.rowbase[col] = 3 * m.sup[col / 3] + col % 3;
-        }
         // ---- P9 adjoint of the skinning transforms
         if (t < kJoints)
             skin_transform_bwd(&S.dA[12 * t], &S.Gam[9 * t], &S.J[3 * t], &S.dGam[9 * t], &S.dg[3 * t], &S.dJ[3 * t]);
@@ -657,6 +631,12 @@ __device__ __forceinline__ void resident_setup(ResidentSmem& S, const ResidentMo
     if (t < kJoints) { S.lev_j[t] = m.cs.lev_j[t]; S.ch_j[t] = m.cs.ch_j[t]; S.par[t] = m.par.p[t]; }
     else if (t >= 32 && t < 32 + kJoints + 1) { S.lev_ptr[t - 32] = m.cs.lev_ptr[t - 32]; S.ch_ptr[t - 32] = m.cs.ch_ptr[t - 32]; }
     else if (t == 64) S.nlev = m.cs.nlev;
+    const int nsj = m.supj_ptr[kJoints];
+    if (t == 65) S.sj_on = nsj <= kResMaxSupJ ? 1 : 0;
+    if (nsj <= kResMaxSupJ) {
+        if (t >= 96 && t < 96 + kJoints + 1) S.sj_ptr[t - 96] = m.supj_ptr[t - 96];
+        for (int q = t; q < nsj; q += kResThreads) { S.sj_i[q] = m.supj_i[q]; S.sj_w[q] = m.supj_w[q]; }
+    }
 }
 
 // A frame that finished stage k of a multi-stage run starts stage k + 1 at once, with a fresh optimiser (the reference
@@ -724,9 +704,12 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
     long long stage_ev0 = 0;
     int cur_stage = 0;
     while (true) {
+        PHASE_MARK(0);
         for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
         __syncthreads();
+        PHASE_MARK(1);
         resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, DenseIn{});
+        PHASE_MARK(23);
         if (warp == 0) {
             FrameScalars s = S.fs;
             lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
@@ -738,6 +721,7 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
             if (lane == 0) S.fs = s;
         }
         __syncthreads();
+        PHASE_MARK(24);
         if (S.fs.phase == PH_DONE) break;
         if (S.fs.stage != cur_stage) {                                   // a stage just started: its loss parameters
             cur_stage = S.fs.stage;
@@ -767,7 +751,8 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
                   const float* __restrict__ parts5, const float* __restrict__ part, const int* __restrict__ pflag,
                   const FrameBox* __restrict__ box, const float* __restrict__ Wd, float* __restrict__ Phi,
-                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA) {
+                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA, float* __restrict__ slot_tr) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     const int slot = blockIdx.x;
@@ -848,6 +833,16 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
             S.sdf_sc[1] = wsum * wsum;                          // fitting.py:391-392
             S.sdf_sc[2] = (float)cnt;
         }
+        // blocks whose vertices carry a sample gradient (ascending), so the adjoint phases loop over those only
+        int nfl = 0;
+        for (int p0 = 0; p0 < nparts; p0 += 32) {
+            const int p = p0 + lane;
+            const bool f = p < nparts && pflag[(size_t)slot * nparts + p] != 0;
+            const unsigned mk = __ballot_sync(0xffffffffu, f);
+            if (f) { const int pos = nfl + __popc(mk & ((1u << lane) - 1u)); if (pos < 64) S.fl[pos] = p; }
+            nfl += __popc(mk);
+        }
+        if (lane == 0) S.nfl = nfl < 64 ? nfl : 64;
     }
     __syncthreads();
     PHASE_MARK(1);
@@ -860,9 +855,9 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     din.pen_loss = S.sdf_sc[1];
     din.Wd = Wd;
     din.factor = S.sdf_sc[0];
-    din.part = (din.factor != 0.f) ? part + (size_t)slot * nparts * kPartFloats : nullptr;   // no penetration: nothing to add
-    din.pflag = pflag + (size_t)slot * nparts;
-    din.nparts = nparts;
+    din.part = (din.factor != 0.f && S.nfl > 0) ? part + (size_t)slot * nparts * kPartFloats : nullptr;
+    din.fl = S.fl;
+    din.nfl = S.nfl;
     resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
@@ -924,6 +919,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
         make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], A);
 #pragma unroll
         for (int c = 0; c < 12; ++c) At[(size_t)(t * 12 + c) * ldA + slot] = A[c];
+        if (t < 3) slot_tr[4 * slot + t] = S.x[kOffTransl + t];
     } else if (t >= 32) {
         const int k = t - 32;
         float v;
@@ -943,7 +939,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
 // ------------------------------------------------------------------------------------------------ host side
 static bool resident_supported(const mvs_ctx* ctx) {
     const DevModel& m = ctx->m;
-    return ctx->exec_mode != 1 && m.supj_ptr != nullptr && m.nsup <= kResMaxSup && m.K <= kMaxKeypoints &&
+    return ctx->exec_mode != 1 && m.supj_ptr != nullptr && m.nsup + 6 <= kResMaxSup && m.K <= kMaxKeypoints &&
            ctx->cams.num_views * m.K <= kResMaxVK && m.M <= kResMaxM;
 }
 
@@ -1024,7 +1020,7 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, 
 
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
-    return resident_supported(ctx) && sdf_on;
+    return resident_supported(ctx) && sdf_on && (ctx->m.N + 255) / 256 <= 64;      // frame_step's block list holds 64 entries
 }
 bool hybrid_available(const mvs_ctx* ctx) { return hybrid_available_for(ctx, ctx->loss); }
 
@@ -1040,11 +1036,13 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
         ctx->attr_done_step = true;
     }
     MVS_LAUNCH(ctx, KID_FRAME_STEP, st,
-               frame_step_kernel<<<w.na_bound > 0 ? w.na_bound : w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams, L.lp_tab, nstages, cfg, L, params_dev,
-                                                                 w.fidx, w.na, w.gt_uv, w.conf, w.joint_w, w.B, dm.N, w.vposed,
-                                                                 w.verts, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
-                                                                 reinterpret_cast<const FrameBox*>(w.sdf_box),
-                                                                 dm.Wd, w.Phi, w.PhiTc, w.At, w.ldA));
+               MVS_CUDA_OK(ctx, launch_pdl(frame_step_kernel, dim3(w.na_bound > 0 ? w.na_bound : w.B), dim3(kResThreads), smem, st,
+                                           make_resident_model(ctx), ctx->cams, (const LossParams*)L.lp_tab, nstages, cfg, L, params_dev,
+                                           (const int*)w.fidx, (const int*)w.na, (const float*)w.gt_uv, (const float*)w.conf,
+                                           (const float*)w.joint_w, w.B, dm.N, (const float*)w.vposed, (const float*)w.verts,
+                                           (const float*)w.sdf_parts5, (const float*)w.sdf_part, (const int*)w.sdf_pflag,
+                                           reinterpret_cast<const FrameBox*>(w.sdf_box), (const float*)dm.Wd, w.Phi, w.PhiTc, w.At,
+                                           w.ldA, w.slot_tr)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

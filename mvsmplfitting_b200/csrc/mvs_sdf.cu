@@ -366,35 +366,43 @@ __device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, con
     return (hits % 2 == 0) ? 0.f : min_d;
 }
 
-__global__ void __launch_bounds__(kSdfFThreads)
-sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vposed, const float* __restrict__ x,
-                 const int* __restrict__ fidx, const int* __restrict__ na_ptr, const FrameScalars* __restrict__ sc,
-                 int N, int nbox, const float* __restrict__ bboxp, const int* __restrict__ faces, int num_faces, int G,
+__global__ void __launch_bounds__(kSdfFThreads, 3)
+sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vposed, const float* __restrict__ slot_tr,
+                 const int* __restrict__ na_ptr, int N, int nbox, const float* __restrict__ bboxp,
+                 const int* __restrict__ faces, int num_faces, int f0, int f1, int f2, int G,
                  const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w,
                  int KW, const float* __restrict__ Wd, const float* __restrict__ Qk, float* __restrict__ parts5,
-                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout) {
+                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout, int passes) {
+    pdl_wait();
     const int slot = blockIdx.y, pidx = blockIdx.x;
-    const int na = *na_ptr;
-    if (slot >= na) return;
-    const int passes = sdf_passes_for(na, N);         // 256-vertex blocks per CTA
-    if (pidx * passes * kSdfFThreads >= N) return;
-    const int b = fidx[slot], t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (sc && sc[b].phase == PH_DONE) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // every load of the prologue is addressed by the slot alone (no slot -> frame -> state chain): one round trip
     const float* vf = verts + (size_t)slot * N * 3;
-    const float tr[3] = {x[(size_t)b * kParams + kOffTransl], x[(size_t)b * kParams + kOffTransl + 1],
-                         x[(size_t)b * kParams + kOffTransl + 2]};
-    __shared__ FrameBox s_box;
+    const int na = *na_ptr;
+    const float4 tr4 = *reinterpret_cast<const float4*>(slot_tr + 4 * slot);
+    float traw[9];
+    {
+        const int fid[3] = {f0, f1, f2};
+#pragma unroll
+        for (int q = 0; q < 9; ++q) traw[q] = vf[3 * fid[q / 3] + q % 3];
+    }
+    if (slot >= na) return;
+    if (pidx * passes * kSdfFThreads >= N) return;
+    const float tr[3] = {tr4.x, tr4.y, tr4.z};
     __shared__ float s_wb[8][6];
     __shared__ int s_wi[8][6];
-    __shared__ float tri0[9], cone[12], ctab[256];
-    __shared__ float s_red[8][5];
-    __shared__ int s_wcnt[8], s_woff[9];
-    __shared__ int seg_n[kSdfFThreads];               // this block's vertices with a non-zero sample gradient
+    __shared__ float ctab[256];
+    __shared__ float s_red[4][8][5];
+    __shared__ int s_wcnt[4][8], s_woff[4][9];
+    __shared__ unsigned s_mask[4][8];
+    __shared__ float s_gc[4][3][kSdfFThreads];         // sample gradients of the vertices that have one
+    __shared__ int seg_n[kSdfFThreads];               // one block's vertices with a non-zero sample gradient
     __shared__ float seg_g[kSdfFThreads * 3];
     __shared__ float sA[kSkinFloats];
     __shared__ int c_n[kSdfFChunk];
     __shared__ float c_dv[kSdfFChunk * 3], c_vp[kSdfFChunk * 3], c_dvp[kSdfFChunk * 3];
     __shared__ float s_dphi[8][kFeatPad];
+    __shared__ float s_ch[256][6];                    // the skinning kernel's per-64-vertex boxes (pre-transl lo | hi)
     // ---- bounding box: every thread takes one partial, warps fold with shuffles (ties -> lowest vertex index)
     {
         float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
@@ -407,6 +415,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                 const int il2 = __float_as_int(bp[6 + c]), ih2 = __float_as_int(bp[9 + c]);
                 if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
                 if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
+                if (tl < 256) { s_ch[tl][c] = l2; s_ch[tl][3 + c] = h2; }
             }
         }
 #pragma unroll
@@ -426,59 +435,97 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         if (t < G && t < 256) ctab[t] = (float)(-1 + (t + 0.5) * (double)(float)(2. / (G - 1)));   // voxel_centre, tabulated
     }
     __syncthreads();
-    if (t == 0) {
-        FrameBox fb;
+    // every warp folds the eight warp boxes itself (lanes 0..7, three shuffle levels): no second barrier
+    FrameBox fb;
+    {
+        const int wsrc = lane & 7;
+        float lo[3], hi[3];
+        int ilo[3], ihi[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { lo[c] = s_wb[wsrc][c]; hi[c] = s_wb[wsrc][3 + c]; ilo[c] = s_wi[wsrc][c]; ihi[c] = s_wi[wsrc][3 + c]; }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float l2 = __shfl_xor_sync(0xffffffffu, lo[c], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[c], o);
+                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
+                const float h2 = __shfl_xor_sync(0xffffffffu, hi[c], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[c], o);
+                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
+            }
+        }
         float ext = -1.f;
         fb.cmax = 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float lo = s_wb[0][c], hi = s_wb[0][3 + c];
-            int ilo = s_wi[0][c], ihi = s_wi[0][3 + c];
-            for (int w2 = 1; w2 < 8; ++w2) {
-                const float l2 = s_wb[w2][c], h2 = s_wb[w2][3 + c];
-                const int il2 = s_wi[w2][c], ih2 = s_wi[w2][3 + c];
-                if (l2 < lo || (l2 == lo && il2 < ilo)) { lo = l2; ilo = il2; }
-                if (h2 > hi || (h2 == hi && ih2 < ihi)) { hi = h2; ihi = ih2; }
-            }
             // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
             // arg-indices commute with the translation (body_models_scale.py:403)
-            const float lc = lo + tr[c], hc = hi + tr[c];
+            const float lc = lo[c] + tr[c], hc = hi[c] + tr[c];
             fb.centre[c] = (lc + hc) / 2.f;
-            fb.ilo[c] = ilo; fb.ihi[c] = ihi;
+            fb.ilo[c] = ilo[c]; fb.ihi[c] = ihi[c];
             const float e = hc - lc;
             if (e > ext) { ext = e; fb.cmax = c; }
         }
         fb.scale = 0.6f * ext;
         fb.pad = 0.f;
-        s_box = fb;
-        if (pidx == 0) boxout[slot] = fb;
+        if (pidx == 0 && t == 0) boxout[slot] = fb;
     }
-    __syncthreads();
-    const FrameBox fb = s_box;
-    if (t < 9) tri0[t] = ((vf[3 * faces[t / 3] + t % 3] + tr[t % 3]) - fb.centre[t % 3]) / fb.scale;
-    __syncthreads();
-    if (t < 3) {
-        const float* a = &tri0[3 * t];
-        const float* bb = &tri0[3 * ((t + 1) % 3)];
+    // triangle 0 in box coordinates (fitting.py:362-363) and the cone it spans from the corner (-1,-1,-1): per thread,
+    // in registers (identical values in every thread)
+    float tri[9], cn[3][3], cm[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) tri[q] = ((traw[q] + tr[q % 3]) - fb.centre[q % 3]) / fb.scale;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float* a = &tri[3 * q];
+        const float* bb = &tri[3 * ((q + 1) % 3)];
         const float ea[3] = {a[0] + 1.f, a[1] + 1.f, a[2] + 1.f}, eb[3] = {bb[0] + 1.f, bb[1] + 1.f, bb[2] + 1.f};
-        const float nx = ea[1] * eb[2] - ea[2] * eb[1], ny = ea[2] * eb[0] - ea[0] * eb[2], nz = ea[0] * eb[1] - ea[1] * eb[0];
-        cone[4 * t] = nx; cone[4 * t + 1] = ny; cone[4 * t + 2] = nz; cone[4 * t + 3] = sqrtf(nx * nx + ny * ny + nz * nz);
+        cn[q][0] = ea[1] * eb[2] - ea[2] * eb[1]; cn[q][1] = ea[2] * eb[0] - ea[0] * eb[2]; cn[q][2] = ea[0] * eb[1] - ea[1] * eb[0];
+        cm[q] = 3.5e-4f * sqrtf(cn[q][0] * cn[q][0] + cn[q][1] * cn[q][1] + cn[q][2] * cn[q][2]);
     }
-    __syncthreads();
-    // ---- one 256-vertex block per pass.  Sums, vertex lists and adjoint partials are emitted PER BLOCK, so the
-    //      arithmetic of a frame does not depend on how many blocks this launch gave to one CTA (i.e. not on how
-    //      many other frames are still active): frames stay bit-for-bit independent problems.
+    // ---- sampling: block (pidx * passes + pass) of 256 vertices per pass, one vertex per thread and pass.  Sums,
+    //      vertex lists and adjoint partials are emitted PER BLOCK, so the arithmetic of a frame does not depend on
+    //      how many blocks this launch gave to one CTA (i.e. not on how many other frames are still active): frames
+    //      stay bit-for-bit independent problems.  All passes are sampled before the first barrier.
     const bool cull = (num_faces == 1);
     const bool tab = (G <= 256);
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
-    bool have_A = false;
+#pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
         const int blk = pidx * passes + pass;
-        if (blk >= nblocks) break;
+        if (blk >= nblocks) { if (lane == 0) s_wcnt[pass][warp] = 0; continue; }
         const int n = blk * kSdfFThreads + t;
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float gcv[3] = {0.f, 0.f, 0.f};
-        if (n < N) {
+        // Chunk-level cull: the skinning kernel left the box of every 64 consecutive vertices.  The voxel centres a
+        // vertex at `loc` can touch lie within (loc + 1) G/(G-1) +- 2/(G-1) (+1 shifted); if that whole box is on the
+        // negative side of one cone plane and on the positive side of another, no vertex of the chunk can see a
+        // voxel with phi != 0: value and gradient are exactly zero and its two warps skip loads, divisions, corners.
+        bool skip = false;
+        const int chunk = (blk * kSdfFThreads + warp * 32) / 64;
+        if (cull && nbox <= 256 && chunk < nbox) {
+            const float gs = (float)G / (float)(G - 1), pad = 2.02f / (float)(G - 1) + 1e-5f;
+            float wlo[3], whi[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float l_lo = ((s_ch[chunk][c] + tr[c]) - fb.centre[c]) / fb.scale;
+                const float l_hi = ((s_ch[chunk][3 + c] + tr[c]) - fb.centre[c]) / fb.scale;
+                wlo[c] = (l_lo + 1.f) * gs - pad; whi[c] = (l_hi + 1.f) * gs + pad;
+            }
+            bool all_neg = false, all_pos = false;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float smin = 0.f, smax = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float a = cn[q][c] * wlo[c], b2 = cn[q][c] * whi[c];
+                    smin += fminf(a, b2); smax += fmaxf(a, b2);
+                }
+                all_neg = all_neg || (smax < -cm[q]);
+                all_pos = all_pos || (smin > cm[q]);
+            }
+            skip = all_neg && all_pos;
+        }
+        if (n < N && !skip) {
             float loc[3], w1[3];
             int i0[3];
 #pragma unroll
@@ -490,26 +537,38 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                 w1[c] = ix - fl;
             }
             float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
+            // voxel centres of the 2 x 2 x 2 cell and, per cone plane, the per-axis parts of <centre + 1, normal>:
+            // a corner's three plane distances are then two adds each
+            float cx[2], cy[2], cz[2], px[3][2], py[3][2], pz[3][2];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int ii = min(max(i0[0] + o, 0), G - 1), jj = min(max(i0[1] + o, 0), G - 1), kk = min(max(i0[2] + o, 0), G - 1);
+                if (tab) { cx[o] = ctab[ii]; cy[o] = ctab[jj]; cz[o] = ctab[kk]; }
+                else { float c3[3]; voxel_centre(ii, jj, kk, G, c3); cx[o] = c3[0]; cy[o] = c3[1]; cz[o] = c3[2]; }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    px[q][o] = (cx[o] + 1.f) * cn[q][0]; py[q][o] = (cy[o] + 1.f) * cn[q][1]; pz[q][o] = (cz[o] + 1.f) * cn[q][2];
+                }
+            }
 #pragma unroll
             for (int corner = 0; corner < 8; ++corner) {
                 const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
                 const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
                 if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
-                float cc[3];
-                if (tab) { cc[0] = ctab[ii]; cc[1] = ctab[jj]; cc[2] = ctab[kk]; }
-                else voxel_centre(ii, jj, kk, G, cc);
                 if (cull) {
-                    const float wv[3] = {cc[0] + 1.f, cc[1] + 1.f, cc[2] + 1.f};
-                    const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) * 1e-4f;
-                    const float s1 = wv[0] * cone[0] + wv[1] * cone[1] + wv[2] * cone[2];
-                    const float s2 = wv[0] * cone[4] + wv[1] * cone[5] + wv[2] * cone[6];
-                    const float s3 = wv[0] * cone[8] + wv[1] * cone[9] + wv[2] * cone[10];
-                    const float m1 = wn * cone[3], m2 = wn * cone[7], m3 = wn * cone[11];
-                    const bool neg = (s1 < -m1) || (s2 < -m2) || (s3 < -m3);
-                    const bool pos = (s1 > m1) || (s2 > m2) || (s3 > m3);
+                    // phi != 0 needs the ray from the voxel centre to (-1,-1,-1) to cross triangle 0, i.e. the centre
+                    // inside the cone the triangle spans from that corner: on the same side of its three planes.
+                    // Conservative margin (|centre + 1| <= 2 sqrt 3): only voxels safely outside are skipped, every
+                    // other one is decided exactly by ray_hits.
+                    const float s1 = px[0][ox] + py[0][oy] + pz[0][oz];
+                    const float s2 = px[1][ox] + py[1][oy] + pz[1][oz];
+                    const float s3 = px[2][ox] + py[2][oy] + pz[2][oz];
+                    const bool neg = (s1 < -cm[0]) || (s2 < -cm[1]) || (s3 < -cm[2]);
+                    const bool pos = (s1 > cm[0]) || (s2 > cm[1]) || (s3 > cm[2]);
                     if (neg && pos) continue;
                 }
-                const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri0);
+                const float cc[3] = {cx[ox], cy[oy], cz[oz]};
+                const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
                 if (p == 0.f) continue;
                 const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
                 val += p * wx * wy * wz;
@@ -527,39 +586,58 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             acc[4] = gdl;
         }
         const bool nz = (gcv[0] != 0.f) || (gcv[1] != 0.f) || (gcv[2] != 0.f);
-        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        const unsigned nzm = __ballot_sync(0xffffffffu, nz);
+        if (nz) { s_gc[pass][0][t] = gcv[0]; s_gc[pass][1][t] = gcv[1]; s_gc[pass][2][t] = gcv[2]; }
+        // almost every warp is outside the cone: all-zero contributions need no shuffle tree (adding zeros is exact)
+        if (__ballot_sync(0xffffffffu, acc[0] != 0.f || nz)) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            float a = acc[q];
+            for (int q = 0; q < 5; ++q) {
+                float a = acc[q];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) s_red[warp][q] = a;
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) s_red[pass][warp][q] = a;
+            }
+        } else if (lane < 5) {
+            s_red[pass][warp][lane] = 0.f;
         }
-        if (lane == 0) s_wcnt[warp] = __popc(mask);
-        __syncthreads();                                   // also: the previous block's adjoint is done with c_* / seg_*
-        if (t < 5) {
+        if (lane == 0) { s_wcnt[pass][warp] = __popc(nzm); s_mask[pass][warp] = nzm; }
+    }
+    __syncthreads();
+    if (t < 5 * passes) {
+        const int pass = t / 5, q = t % 5, blk = pidx * passes + pass;
+        if (blk < nblocks) {
             float a = 0.f;
-            for (int w2 = 0; w2 < 8; ++w2) a += s_red[w2][t];
-            parts5[((size_t)slot * nblocks + blk) * 5 + t] = a;
+            for (int w2 = 0; w2 < 8; ++w2) a += s_red[pass][w2][q];
+            parts5[((size_t)slot * nblocks + blk) * 5 + q] = a;
         }
-        if (t == 0) {
-            int o = 0;
-            for (int w2 = 0; w2 < 8; ++w2) { s_woff[w2] = o; o += s_wcnt[w2]; }
-            s_woff[8] = o;
+    } else if (t >= 32 && t < 32 + passes) {
+        const int pass = t - 32, blk = pidx * passes + pass;
+        int o = 0;
+        if (blk < nblocks) {
+            for (int w2 = 0; w2 < 8; ++w2) { s_woff[pass][w2] = o; o += s_wcnt[pass][w2]; }
             pflag[(size_t)slot * nblocks + blk] = o > 0 ? 1 : 0;
         }
-        __syncthreads();
-        const int total = s_woff[8];
+        s_woff[pass][8] = o;
+    }
+    __syncthreads();
+    // ---- adjoint of the vertex stage for the listed vertices of each block (unit frame factor); rare
+    bool have_A = false;
+#pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+        const int blk = pidx * passes + pass;
+        const int total = s_woff[pass][8];
         if (total == 0) continue;
-        if (nz) {                                          // ascending vertex order: (warp, lane)
-            const int pos = s_woff[warp] + __popc(mask & ((1u << lane) - 1u));
-            seg_n[pos] = n; seg_g[3 * pos] = gcv[0]; seg_g[3 * pos + 1] = gcv[1]; seg_g[3 * pos + 2] = gcv[2];
+        __syncthreads();                                   // the previous block's adjoint is done with seg_* / c_*
+        const unsigned nzm = s_mask[pass][warp];
+        if (nzm & (1u << lane)) {                          // ascending vertex order: (warp, lane)
+            const int pos = s_woff[pass][warp] + __popc(nzm & ((1u << lane) - 1u));
+            seg_n[pos] = blk * kSdfFThreads + t;
+            seg_g[3 * pos] = s_gc[pass][0][t]; seg_g[3 * pos + 1] = s_gc[pass][1][t]; seg_g[3 * pos + 2] = s_gc[pass][2][t];
         }
         if (!have_A) {
             for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
             have_A = true;
         }
-        // ---- adjoint of the vertex stage for the listed vertices of this block (unit frame factor)
         float accA0 = 0.f, accA1 = 0.f;
         float accP[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // d Phi[lane + 32 i], this warp's share of the columns
         for (int e0 = 0; e0 < total; e0 += kSdfFChunk) {
@@ -645,8 +723,10 @@ int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars
     const DevModel& m = ctx->m;
     const LossParams& lp = ctx->loss;
     const int B = w.B, N = m.N;
-    const int nparts = sdf_parts_for(1, N);           // the finest split (grid); the kernel picks by *na_ptr
+    const int nb = w.na_bound > 0 ? w.na_bound : B;    // host-side upper bound of the active-frame count
+    const int passes = sdf_passes_for(nb, N);          // 256-vertex blocks per CTA (results do not depend on it)
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
+    const int nparts = (nblocks + passes - 1) / passes;
     int rc;
     if (!w.sdf_parts5) {
         if ((rc = dev_alloc(ctx, &w.sdf_parts5, (size_t)B * nblocks * 5))) return rc;
@@ -658,13 +738,14 @@ int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars
         if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
         w.sdf_box = raw;
     }
-    dim3 g(nparts, w.na_bound > 0 ? w.na_bound : B);
+    dim3 g(nparts, nb);
     MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
-               sdf_fused_kernel<<<g, kSdfFThreads, 0, st>>>(w.verts, w.vposed, x_dev, w.fidx, w.na,
-                                                            static_cast<const FrameScalars*>(frame_scalars), N, (N + 63) / 64,
-                                                            w.bboxp, m.faces, lp.sdf_all_faces ? m.F : 1, lp.sdf_grid, w.At, w.ldA,
-                                                            m.ell_j, m.ell_w, m.KW, m.Wd, m.Qk, w.sdf_parts5, w.sdf_part,
-                                                            w.sdf_pflag, reinterpret_cast<FrameBox*>(w.sdf_box)));
+               MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel, g, dim3(kSdfFThreads), 0, st, (const float*)w.verts, (const float*)w.vposed,
+                                           (const float*)w.slot_tr, (const int*)w.na, N, (N + 63) / 64, (const float*)w.bboxp,
+                                           (const int*)m.faces, lp.sdf_all_faces ? m.F : 1, m.tri0[0], m.tri0[1], m.tri0[2],
+                                           lp.sdf_grid, (const float*)w.At, w.ldA, (const int*)m.ell_j, (const float*)m.ell_w, m.KW,
+                                           (const float*)m.Wd, (const float*)m.Qk, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
+                                           reinterpret_cast<FrameBox*>(w.sdf_box), passes)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

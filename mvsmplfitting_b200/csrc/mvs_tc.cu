@@ -103,10 +103,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
 }
 
+#ifdef MVS_PHASE_DBG
+__device__ long long g_tc_clk[32];      // clock64 stamps of CTA (0,0): see scripts/phase_times.py
+#define TC_MARK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_tc_clk[i] = clock64(); } while (0)
+#else
+#define TC_MARK(i) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
                         const int* __restrict__ na_ptr, int cta_slots, int ntiles, float* __restrict__ poffT,
                         int* __restrict__ err_flag) {
+    pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = base;                                        // 7 x [128 rows][128 B], 1024-aligned
@@ -132,6 +140,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int tile_end = min(tile_begin + tiles_per_cta, ntiles);
     if (tile_begin >= tile_end) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TC_MARK(0);
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -147,6 +156,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_MARK(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -168,6 +178,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             // ---------------- MMA issuer
             constexpr uint32_t idesc = umma_idesc_tf32(kTcBM, kTcBN);
             if (!mbar_wait(a_full, 0, err_flag)) return;
+            TC_MARK(2);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t tphase[2] = {0, 0};
             for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -187,6 +198,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&t_full[buf]);                           // accumulator of this tile complete
+                TC_MARK(3 + (tile - tile_begin));
                 tphase[buf] ^= 1;
                 buf ^= 1;
             }
@@ -200,6 +212,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         int buf = 0; uint32_t tphase[2] = {0, 0};
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             if (!mbar_wait(&t_full[buf], tphase[buf], err_flag)) return;
+            if (threadIdx.x == 128) TC_MARK(8 + 2 * (tile - tile_begin));
             tphase[buf] ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * kTcBN);
@@ -217,11 +230,44 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 for (int c = 0; c < kTcBN; ++c)
                     if (c0 + c < ncols) poffT[(size_t)(c0 + c) * ldA + slot] = __uint_as_float(acc[c]);
             }
+            if (threadIdx.x == 128) TC_MARK(9 + 2 * (tile - tile_begin));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    if (threadIdx.x == 0) TC_MARK(20);
+}
+
+// One vertex of one frame: v_posed = template + shapedirs.betas + pose offset, then linear blend skinning
+// (lbs.py:179,203,207-220).  skin_kernel (lane = frame) and skin_small_kernel (lane = vertex) both call this with every
+// operation spelled out, so the two produce the same bits: a frame's result must not depend on which of the two
+// kernels its batch size selected.  A(j, c) returns entry c (row-major 3x4) of joint j's transform for this frame.
+template <class AFn>
+__device__ __forceinline__ void skin_vertex(const float* __restrict__ st /* [3][11]: shapedirs row | template */,
+                                            const float* beta, const float* poff, const int* __restrict__ ell_j,
+                                            const float* __restrict__ ell_w, int KW, size_t n, AFn A, float* vp, float* vv) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = st[11 * c + kBetas];
+#pragma unroll
+        for (int l = 0; l < kBetas; ++l) a = fmaf(st[11 * c + l], beta[l], a);
+        vp[c] = __fadd_rn(a, poff[c]);
+    }
+    float T[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) T[c] = 0.f;
+    for (int e = 0; e < KW; ++e) {
+        const float w = ell_w[n * KW + e];
+        if (w != 0.f) {
+            const int j = ell_j[n * KW + e];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) T[c] = fmaf(w, A(j, c), T[c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        vv[r] = __fadd_rn(fmaf(T[4 * r + 2], vp[2], fmaf(T[4 * r + 1], vp[1], __fmul_rn(T[4 * r], vp[0]))), T[4 * r + 3]);
 }
 
 // ------------------------------------------------------------------------------------------------ skinning
@@ -241,6 +287,7 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW,
             int N, const int* __restrict__ na_ptr, int cta_slots, float* __restrict__ vposed, float* __restrict__ verts,
             float* __restrict__ bboxp) {
+    pdl_wait();
     extern __shared__ __align__(16) float sk[];
     float* As = sk;                                   // [288][32]
     float* Bs = As + kSkinFloats * 32;                // [10][32]
@@ -291,29 +338,12 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             const int li = warp * kVw + i;
             const int n = v0 + li;
             if (n < N) {
-                const float* st = Sts + li * 33;                          // [3][11]: shapedirs row | template
-                float vp[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float a = st[11 * c + kBetas];
-#pragma unroll
-                    for (int l = 0; l < kBetas; ++l) a = fmaf(st[11 * c + l], beta[l], a);
-                    vp[c] = a + pf[i][c];
-                }
-                float T[12];
-#pragma unroll
-                for (int c = 0; c < 12; ++c) T[c] = 0.f;
-                for (int e = 0; e < KW; ++e) {
-                    const float w = ell_w[(size_t)n * KW + e];
-                    if (w != 0.f) {
-                        const float* Aj = As + (size_t)ell_j[(size_t)n * KW + e] * 12 * 32 + lane;
-#pragma unroll
-                        for (int c = 0; c < 12; ++c) T[c] = fmaf(w, Aj[c * 32], T[c]);
-                    }
-                }
+                float vp[3], vvv[3];
+                skin_vertex(Sts + li * 33, beta, pf[i], ell_j, ell_w, KW, (size_t)n,
+                            [&](int j, int c) { return As[(j * 12 + c) * 32 + lane]; }, vp, vvv);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float vv = T[4 * r] * vp[0] + T[4 * r + 1] * vp[1] + T[4 * r + 2] * vp[2] + T[4 * r + 3];
+                    const float vv = vvv[r];
                     Ovp[lane * kSkinOutLd + 3 * li + r] = vp[r];
                     Ov[lane * kSkinOutLd + 3 * li + r] = vv;
                     if (vv < blo[r]) { blo[r] = vv; bilo[r] = n; }       // strict: ties keep the lowest vertex index
@@ -353,6 +383,82 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             float* bp = bboxp + ((size_t)(f0 + lane) * nchunks + ch) * 12;
 #pragma unroll
             for (int r = 0; r < 3; ++r) { bp[r] = lo[r]; bp[3 + r] = hi[r]; bp[6 + r] = __int_as_float(ilo[r]); bp[9 + r] = __int_as_float(ihi[r]); }
+        }
+    }
+}
+
+// The same for a handful of frames (the straggler tail of a fit): with lane = frame almost every lane of skin_kernel
+// idles and its fixed costs (36 KB of transforms per CTA, staging, three barriers per chunk) are pure latency.  Here
+// lane = vertex, a CTA owns one 64-vertex chunk (= one box partial) and loops over the <= kSkinSmallMax frames.
+constexpr int kSkinSmallMax = 8;
+constexpr int kSkinSmallThreads = 64;
+static_assert(kSkinSmallThreads == kSkinV, "one thread per vertex of a box chunk");
+
+__global__ void __launch_bounds__(kSkinSmallThreads)
+skin_small_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const float* __restrict__ Phi,
+                  const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w, int KW,
+                  int N, const int* __restrict__ na_ptr, float* __restrict__ vposed, float* __restrict__ verts,
+                  float* __restrict__ bboxp) {
+    __shared__ float As[kSkinSmallMax][kSkinFloats];
+    __shared__ float Bs[kSkinSmallMax][kBetas];
+    __shared__ float s_b[kSkinSmallMax][6];
+    __shared__ int s_i[kSkinSmallMax][6];
+    pdl_wait();
+    const int na = min(*na_ptr, kSkinSmallMax);
+    if (na <= 0) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int chunk = blockIdx.x, nchunks = gridDim.x;
+    const int n = chunk * kSkinSmallThreads + t;
+    for (int e = t; e < na * kSkinFloats; e += kSkinSmallThreads) As[e / kSkinFloats][e % kSkinFloats] = At[(size_t)(e % kSkinFloats) * ldA + e / kSkinFloats];
+    for (int e = t; e < na * kBetas; e += kSkinSmallThreads) Bs[e / kBetas][e % kBetas] = Phi[(size_t)(e / kBetas) * kFeatPad + kPoseBasis + e % kBetas];
+    float st[33];
+    if (n < N) {
+#pragma unroll
+        for (int q = 0; q < 33; ++q) st[q] = ST[(size_t)n * 33 + q];
+    }
+    __syncthreads();
+    for (int f = 0; f < na; ++f) {
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        int ilo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, ihi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        if (n < N) {
+            float poff[3], vp[3], vv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) poff[c] = poffT[(size_t)(3 * n + c) * ldA + f];
+            skin_vertex(st, Bs[f], poff, ell_j, ell_w, KW, (size_t)n, [&](int j, int c) { return As[f][j * 12 + c]; }, vp, vv);
+            const size_t off = ((size_t)f * N + n) * 3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                vposed[off + r] = vp[r]; verts[off + r] = vv[r];
+                lo[r] = vv[r]; hi[r] = vv[r]; ilo[r] = n; ihi[r] = n;
+            }
+        }
+        if (bboxp) {               // box of the chunk: extreme value, ties -> lowest vertex index (as skin_kernel)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float l2 = __shfl_xor_sync(0xffffffffu, lo[r], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[r], o);
+                    if (l2 < lo[r] || (l2 == lo[r] && il2 < ilo[r])) { lo[r] = l2; ilo[r] = il2; }
+                    const float h2 = __shfl_xor_sync(0xffffffffu, hi[r], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[r], o);
+                    if (h2 > hi[r] || (h2 == hi[r] && ih2 < ihi[r])) { hi[r] = h2; ihi[r] = ih2; }
+                }
+            }
+            if (warp == 1 && lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { s_b[f][r] = lo[r]; s_b[f][3 + r] = hi[r]; s_i[f][r] = ilo[r]; s_i[f][3 + r] = ihi[r]; }
+            }
+            __syncthreads();
+            if (warp == 0 && lane == 0) {
+                float* bp = bboxp + ((size_t)f * nchunks + chunk) * 12;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float l2 = s_b[f][r], h2 = s_b[f][3 + r];
+                    const int il2 = s_i[f][r], ih2 = s_i[f][3 + r];
+                    if (l2 < lo[r] || (l2 == lo[r] && il2 < ilo[r])) { lo[r] = l2; ilo[r] = il2; }
+                    if (h2 > hi[r] || (h2 == hi[r] && ih2 < ihi[r])) { hi[r] = h2; ihi[r] = ih2; }
+                    bp[r] = lo[r]; bp[3 + r] = hi[r]; bp[6 + r] = __int_as_float(ilo[r]); bp[9 + r] = __int_as_float(ihi[r]);
+                }
+            }
         }
     }
 }
@@ -432,14 +538,24 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
     const int mtiles = (nb + kTcBM - 1) / kTcBM;
     dim3 grid(std::min(ctx->sm_count, ntiles), mtiles);          // surplus CTAs exit: the kernel splits the tiles from *na
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
-               posedirs_gemm_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(T->map_a, T->map_b, w.ldA, 3 * m.N, w.na, ctx->sm_count,
-                                                                          ntiles, T->poffT, T->err));
-    // one wave of CTAs (two per SM): each CTA keeps its 32 frames' transforms in shared memory and walks several chunks
+               MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_b, w.ldA,
+                                           3 * m.N, (const int*)w.na, ctx->sm_count, ntiles, T->poffT, T->err)));
     const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (nb + 31) / 32;
-    dim3 g2(nchunks, fgroups);                          // surplus CTAs exit: the kernel sizes its chunk loop from *na
-    MVS_LAUNCH(ctx, KID_SKIN, st,
-               skin_kernel<<<g2, kSkinThreads, kSkinSmem, st>>>(T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N,
-                                                                w.na, 2 * ctx->sm_count, w.vposed, w.verts, w.bboxp));
+    if (nb <= kSkinSmallMax) {                          // straggler tail: lane = vertex, one chunk per CTA
+        MVS_LAUNCH(ctx, KID_SKIN, st,
+                   MVS_CUDA_OK(ctx, launch_pdl(skin_small_kernel, dim3(nchunks), dim3(kSkinSmallThreads), 0, st,
+                                               (const float*)T->poffT, (const float*)m.ST, (const float*)w.Phi, (const float*)w.At,
+                                               w.ldA, (const int*)m.ell_j, (const float*)m.ell_w, m.KW, m.N, (const int*)w.na,
+                                               w.vposed, w.verts, w.bboxp)));
+    } else {
+        // each CTA keeps its 32 frames' transforms in shared memory and walks 1..3 chunks (sized from *na in the kernel)
+        dim3 g2(nchunks, fgroups);                      // surplus CTAs exit
+        MVS_LAUNCH(ctx, KID_SKIN, st,
+                   MVS_CUDA_OK(ctx, launch_pdl(skin_kernel, g2, dim3(kSkinThreads), kSkinSmem, st, (const float*)T->poffT,
+                                               (const float*)m.ST, (const float*)w.Phi, (const float*)w.At, w.ldA,
+                                               (const int*)m.ell_j, (const float*)m.ell_w, m.KW, m.N, (const int*)w.na,
+                                               2 * ctx->sm_count, w.vposed, w.verts, w.bboxp)));
+    }
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }
@@ -454,3 +570,12 @@ int tc_check_error(mvs_ctx* ctx) {          // host-side check after a synchroni
 }
 
 }  // namespace mvs
+
+#ifdef MVS_PHASE_DBG
+extern "C" int mvs_debug_tc_clocks(long long* out, int n) {       // debug builds only; not part of the ABI
+    long long h[32];
+    if (cudaMemcpyFromSymbol(h, mvs::g_tc_clk, sizeof(h)) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+    return 0;
+}
+#endif

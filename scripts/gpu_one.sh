@@ -1,2 +1,4 @@
 #!/bin/bash
-timeout 300 python -m pytest "tests/test_gpu_closure.py::test_closure_matches_reference_fixtures" -x -q -k "True-gmm8_gt" 2>&1 | grep -E "^E|assert|Error" | head -30
+mkdir -p gpurun_out
+timeout 300 python scripts/tail_latency.py 1 > gpurun_out/k_tail1.txt 2>&1; tail -14 gpurun_out/k_tail1.txt
+timeout 300 python scripts/tail_latency.py 4 > gpurun_out/k_tail4.txt 2>&1; tail -12 gpurun_out/k_tail4.txt

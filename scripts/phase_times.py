@@ -19,8 +19,9 @@ ctx.set_model(model); ctx.set_gmm_from_dict(gmm)
 ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"]); ctx.set_batch(B)
 ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
 x = torch.tensor(S.pack_params(fr["init"]), device="cuda")
-ctx.set_loss(body_prior="gmm", interpenetration=True, coll_loss_weight=1000.0, data_weight=500 / 1536, body_pose_weight=57.4,
-             shape_weight=10.0, bending_prior_weight=3.17 * 57.4)
+SDF = not (len(sys.argv) > 2 and sys.argv[2] == "resident")      # "resident": the frame-resident kernel's last evaluation
+ctx.set_loss(body_prior="gmm", interpenetration=SDF, coll_loss_weight=1000.0 if SDF else 0.0, data_weight=500 / 1536,
+             body_pose_weight=57.4, shape_weight=10.0, bending_prior_weight=3.17 * 57.4)
 ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=1, max_iter=12))
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
@@ -40,3 +41,12 @@ for i in range(1, 29):
 print("total %.2f us" % ((prev - buf[0]) / ghz / 1e3))
 print("max over all CTAs and launches (us): closure %.2f | history wait %.2f | advance+write-back %.2f | next pose %.2f | "
       "start->advanced %.2f | start->end %.2f" % tuple(buf[32 + k] / ghz / 1e3 for k in range(6)))
+
+# tensor-core contraction: stamps of CTA (0, 0) in the last launch
+tb = (ctypes.c_longlong * 32)()
+if hasattr(lib, "mvs_debug_tc_clocks") and lib.mvs_debug_tc_clocks(tb, 32) == 0 and tb[0]:
+    def us(i): return (tb[i] - tb[0]) / ghz / 1e3
+    print("posedirs_gemm_tc CTA(0,0), us from kernel entry: setup done %.2f | A operand landed %.2f | MMA tile commits %s | "
+          "epilogue (tile ready, stored) %s | exit %.2f" % (
+              us(1), us(2), ["%.2f" % us(3 + i) for i in range(4) if tb[3 + i] > tb[0]],
+              ["%.2f/%.2f" % (us(8 + 2 * i), us(9 + 2 * i)) for i in range(4) if tb[8 + 2 * i] > tb[0]], us(20)))

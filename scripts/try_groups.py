@@ -10,8 +10,8 @@ model = S.make_model(0); gmm = S.make_gmm(7); cams = S.make_cameras(8)
 B = 256
 fr = S.make_frames(model, cams, B, seed=1000)
 X0 = S.pack_params(fr["init"])
-for G in (1, 2, 4, 8):
-    per = B // G
+for G in (1, 2, 4):
+    per = (B + G - 1) // G
     groups = []
     for g in range(G):
         sl = slice(g * per, (g + 1) * per)
@@ -27,12 +27,8 @@ for G in (1, 2, 4, 8):
     def work(gr):
         with torch.cuda.stream(gr["stream"]):
             gr["x"].copy_(gr["x0"])
-            it = 0
-            for cfg in gr["stages"]:
-                gr["ctx"].set_loss(config=cfg)
-                _, st = gr["ctx"].lbfgs_run(gr["x"], None)
-                it += st["frame_iterations"]
-            gr["it"] = it
+            _, st = gr["ctx"].fit(gr["x"], gr["stages"])
+            gr["it"] = st["frame_iterations"]
     def step():
         ths = [threading.Thread(target=work, args=(gr,)) for gr in groups]
         for t in ths: t.start()

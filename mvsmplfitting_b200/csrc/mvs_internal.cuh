@@ -138,11 +138,6 @@ __host__ __device__ inline int sdf_passes_for(int na, int n_verts) {
     if (na * ((p1 + 1) / 2) <= 640) return 2;
     return 4;
 }
-__host__ __device__ inline int sdf_parts_for(int na, int n_verts) {
-    const int per = 256 * sdf_passes_for(na, n_verts);
-    return (n_verts + per - 1) / per;
-}
-
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
@@ -238,7 +233,7 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg
 bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
-int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st);   // mvs_sdf.cu
+int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st);   // mvs_sdf.cu
 // mvs_tc.cu: tcgen05 / TMA dense vertex forward
 int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);

@@ -56,6 +56,7 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
     const int b = fidx[slot];
     const int lane = threadIdx.x;
     __shared__ float al[128];
+    __shared__ float scratch[96];
     FrameScalars s = S.sc[b];
     float* x = params + (size_t)b * kParams;
     float* g = S.g + (size_t)b * kParams;
@@ -72,7 +73,8 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
     const float* g_new = S.g_eval + (size_t)b * kParams;
     const float f_new = S.loss_eval[b];
 
-    LbfgsPtrs P{x, g, d, prev_g, x_init, g_prev, bg0, bg1, hy, hs, ro, al, x_eval, g_new, S.H};
+    LbfgsPtrs P{x, g, d, prev_g, x_init, g_prev, bg0, bg1, hy, hs, ro, al, x_eval, g_new, S.H,
+                S.gram + (size_t)b * kGramFloats, scratch};
     lbfgs_advance_core(s, P, f_new, cfg, lane);
     __syncwarp();
     if (lane == 0) S.sc[b] = s;
@@ -140,6 +142,7 @@ static int ensure_state(mvs_ctx* ctx, int H) {
     if ((rc = dev_alloc(ctx, &S->hist_y, V * H))) return rc;
     if ((rc = dev_alloc(ctx, &S->hist_s, V * H))) return rc;
     if ((rc = dev_alloc(ctx, &S->ro, (size_t)B * H))) return rc;
+    if ((rc = dev_alloc(ctx, &S->gram, (size_t)B * kGramFloats))) return rc;
     if ((rc = dev_alloc(ctx, &S->x_eval, V))) return rc;
     if ((rc = dev_alloc(ctx, &S->loss_eval, B))) return rc;
     if ((rc = dev_alloc(ctx, &S->g_eval, V))) return rc;
@@ -231,7 +234,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         while (rounds < max_rounds) {
             for (int r = 0; r < chunk; ++r) {
                 if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;        // tcgen05 GEMM + LBS + bbox partials
-                if ((rc = launch_sdf_fused(ctx, S.x_eval, S.sc, st))) return rc;   // samples + adjoint of the listed vertices
+                if ((rc = launch_sdf_fused(ctx, st))) return rc;   // samples + adjoint of the listed vertices
                 if ((rc = launch_frame_step(ctx, params_dev, &S, &cfg, nst, st))) return rc;
                 ++rounds;
             }

@@ -6,6 +6,8 @@
 namespace mvs {
 
 constexpr int kMaxStages = 16;
+constexpr int kGramBlocks = 16;          // history ring slots / 8 (H <= 128)
+constexpr int kGramFloats = kGramBlocks * 64;
 
 enum Phase { PH_STEP_ENTRY = 0, PH_LS_BRACKET = 1, PH_LS_ZOOM = 2, PH_DONE = 3 };
 
@@ -26,6 +28,7 @@ struct LbfgsState {
     int B = 0, H = 0;
     float *g = nullptr, *d = nullptr, *prev_g = nullptr, *x_init = nullptr, *g_prev = nullptr, *bg = nullptr;
     float *hist_y = nullptr, *hist_s = nullptr, *ro = nullptr;
+    float* gram = nullptr;           // [B][kGramFloats] s_i . y_j of pairs in the same 8-slot block of the history ring
     float *x_eval = nullptr, *loss_eval = nullptr, *g_eval = nullptr;
     FrameScalars* sc = nullptr;
     long long* totals = nullptr;     // [4] iters, evals, nan frames, real rounds
@@ -93,7 +96,24 @@ struct LbfgsPtrs {
     float *x, *g, *d, *prev_g, *x_init, *g_prev, *bg0, *bg1, *hy, *hs, *ro, *al, *x_eval;
     const float* g_new;
     int H;
+    float* gram;        // [kGramFloats] block Gram entries (shared or global)
+    float* scratch;     // [96] shared-memory scratch of the two-loop recursion (q vector + 8 coefficients)
 };
+
+// 8 groups of 4 lanes: group u takes one history pair, its lanes split the 86 elements (i = sub + 4 e)
+__device__ __forceinline__ float group_dot(const float* a, const float* b, int sub) {
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 22; e += 2) {
+        const int i0 = sub + 4 * e, i1 = sub + 4 * (e + 1);
+        if (i0 < kParams) p0 = fmaf(a[i0], b[i0], p0);
+        if (i1 < kParams) p1 = fmaf(a[i1], b[i1], p1);
+    }
+    float p = p0 + p1;
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    return p;
+}
 
 // One warp walks ONE frame's optimiser from "closure result (f_new, g_new) available" to its next closure
 // request (x_eval written, s.phase says what is pending) or to PH_DONE.  Pointers may be global or shared.
@@ -101,7 +121,7 @@ __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsP
                                                    const LbfgsCfg& cfg, const int lane) {
     float* const x = P.x; float* const g = P.g; float* const d = P.d; float* const prev_g = P.prev_g;
     float* const x_init = P.x_init; float* const g_prev = P.g_prev; float* const bg0 = P.bg0; float* const bg1 = P.bg1;
-    float* const hy = P.hy; float* const hs = P.hs; float* const ro = P.ro;
+    float* const hy = P.hy; float* const hs = P.hs; float* const ro = P.ro; float* const al = P.al;
     float* const x_eval = P.x_eval; const float* const g_new = P.g_new;
     const float c1 = 1e-4f, c2 = 0.9f;
     s.pushed_slot = -1;
@@ -154,58 +174,88 @@ __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsP
                     s.H_diag = ys / yy;
                 }
                 __syncwarp();
-                // two-loop recursion (collapsed to one buffer like the reference), q lives in registers.  The chain
-                // dot -> shuffle tree -> axpy is strictly serial in the history index, so everything that does not
-                // depend on q is taken off it: the NEXT pair's rows are loaded before the current reduction starts,
-                // the ring index is stepped incrementally and alpha stays in registers (lane k % 32, no shared-memory
-                // store that the loads would have to be ordered against).
-                float q[3] = {0.f, 0.f, 0.f};
-                VL(c, i) q[c] = -g[i];
-                float al_r[4] = {0.f, 0.f, 0.f, 0.f};            // alpha[k] lives in lane k & 31, register k >> 5
+                // Two-loop recursion, eight pairs at a time.  The textbook loop is a strictly serial chain of
+                // (86-dot, warp reduction, axpy) per history pair: ~300 cycles x 2 x 100 pairs = 30 us for a full
+                // history, the longest phase of a straggler's round.  Within a block of 8 consecutive ring slots the
+                // products s_i . y_j are kept (updated when a pair is pushed), so the eight dots against the CURRENT
+                // vector can be taken at once (8 groups of 4 lanes), the eight coefficients follow from an 8-step
+                // scalar recurrence   a_u = ro_u (s_u.q - sum_{v<u} a_v s_u.y_v),   and the eight axpys are applied
+                // together.  Same mathematics, different rounding; everything stays frame-local and deterministic.
+#ifdef MVS_TL_MARK
+                const long long tl_t0 = clock64();
+#endif
+                const int gq = lane >> 2, sub = lane & 3;
+                float* const gram = P.gram;
+                float* const qb = P.scratch;                     // [88] q / r vector
+                float* const cb = P.scratch + 88;                // [8] coefficients of the current block
+                if (s.pushed_slot >= 0) {                        // Gram row and column of the new pair
+                    const int wp = s.pushed_slot, bw = wp >> 3, j = (bw << 3) + gq;
+                    const bool live = j < P.H && (s.hist_len == P.H || j < s.hist_len);
+                    const int jj = live ? j : wp;                // idle groups recompute the diagonal (and drop it)
+                    const float g1 = group_dot(hs + (size_t)wp * kParams, hy + (size_t)jj * kParams, sub);
+                    const float g2 = group_dot(hs + (size_t)jj * kParams, hy + (size_t)wp * kParams, sub);
+                    if (live && sub == 0) { gram[bw * 64 + (wp & 7) * 8 + gq] = g1; gram[bw * 64 + gq * 8 + (wp & 7)] = g2; }
+                    __syncwarp();
+                }
+                VLOOP(i) qb[i] = -g[i];
+                __syncwarp();
                 const int hl = s.hist_len;
-                {
-                    int w = (s.hist_head + hl - 1) % P.H;
-                    float sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f}, rw = 0.f;
-                    if (hl > 0) { VL(c, i) { sv[c] = hs[(size_t)w * kParams + i]; yv[c] = hy[(size_t)w * kParams + i]; } rw = ro[w]; }
-                    for (int k = hl - 1; k >= 0; --k) {
-                        const int wn = (w == 0) ? P.H - 1 : w - 1;
-                        float sn[3] = {0.f, 0.f, 0.f}, yn[3] = {0.f, 0.f, 0.f}, rn = 0.f;
-                        if (k > 0) { VL(c, i) { sn[c] = hs[(size_t)wn * kParams + i]; yn[c] = hy[(size_t)wn * kParams + i]; } rn = ro[wn]; }
-                        float p = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) p = fmaf(sv[c], q[c], p);
-                        const float a = warp_sum(p) * rw;
-                        if (lane == (k & 31)) {
-                            const int r = k >> 5;
-                            if (r == 0) al_r[0] = a; else if (r == 1) al_r[1] = a; else if (r == 2) al_r[2] = a; else al_r[3] = a;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { q[c] = fmaf(-a, yv[c], q[c]); sv[c] = sn[c]; yv[c] = yn[c]; }
-                        rw = rn; w = wn;
+                for (int k = hl - 1; k >= 0;) {                  // newest -> oldest
+                    const int w_hi = (s.hist_head + k) % P.H;
+                    const int cnt = min(k + 1, (w_hi & 7) + 1);
+                    const bool on = gq < cnt;
+                    const int wu = on ? w_hi - gq : w_hi;
+                    float acc = group_dot(hs + (size_t)wu * kParams, qb, sub);
+                    const float rou = ro[wu];
+                    const float* grow = gram + (w_hi >> 3) * 64 + (wu & 7) * 8;      // s_wu . y_*
+                    float a_mine = 0.f;
+                    for (int v = 0; v < cnt; ++v) {
+                        const float av = __shfl_sync(0xffffffffu, rou * acc, 4 * v);
+                        if (gq == v) a_mine = av;
+                        else if (on && gq > v) acc = fmaf(-av, grow[(w_hi - v) & 7], acc);
                     }
-                }
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) q[cc] *= s.H_diag;
-                {
-                    int w = s.hist_head % P.H;
-                    float sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f}, rw = 0.f;
-                    if (hl > 0) { VL(c, i) { sv[c] = hs[(size_t)w * kParams + i]; yv[c] = hy[(size_t)w * kParams + i]; } rw = ro[w]; }
-                    for (int k = 0; k < hl; ++k) {
-                        const int wn = (w + 1 == P.H) ? 0 : w + 1;
-                        float sn[3] = {0.f, 0.f, 0.f}, yn[3] = {0.f, 0.f, 0.f}, rn = 0.f;
-                        if (k + 1 < hl) { VL(c, i) { sn[c] = hs[(size_t)wn * kParams + i]; yn[c] = hy[(size_t)wn * kParams + i]; } rn = ro[wn]; }
-                        const int r = k >> 5;
-                        const float alk = __shfl_sync(0xffffffffu, r == 0 ? al_r[0] : r == 1 ? al_r[1] : r == 2 ? al_r[2] : al_r[3], k & 31);
-                        float p = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) p = fmaf(yv[c], q[c], p);
-                        const float be = warp_sum(p) * rw;
-                        const float coef = alk - be;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) { q[c] = fmaf(coef, sv[c], q[c]); sv[c] = sn[c]; yv[c] = yn[c]; }
-                        rw = rn; w = wn;
+                    if (on && sub == 0) { al[k - gq] = a_mine; cb[gq] = a_mine; }
+                    __syncwarp();
+                    VLOOP(i) {
+                        float qi = qb[i];
+                        for (int v = 0; v < cnt; ++v) qi = fmaf(-cb[v], hy[(size_t)(w_hi - v) * kParams + i], qi);
+                        qb[i] = qi;
                     }
+                    __syncwarp();
+                    k -= cnt;
                 }
+                VLOOP(i) qb[i] *= s.H_diag;
+                __syncwarp();
+                for (int k = 0; k < hl;) {                       // oldest -> newest
+                    const int w_lo = (s.hist_head + k) % P.H;
+                    const int cnt = min(min(hl - k, 8 - (w_lo & 7)), P.H - w_lo);
+                    const bool on = gq < cnt;
+                    const int wu = on ? w_lo + gq : w_lo;
+                    float acc = group_dot(hy + (size_t)wu * kParams, qb, sub);
+                    const float rou = ro[wu];
+                    const float alu = on ? al[k + gq] : 0.f;
+                    const float* gcol = gram + (w_lo >> 3) * 64 + (wu & 7);          // s_* . y_wu
+                    float c_mine = 0.f;
+                    for (int v = 0; v < cnt; ++v) {
+                        const float cv = __shfl_sync(0xffffffffu, alu - rou * acc, 4 * v);
+                        if (gq == v) c_mine = cv;
+                        else if (on && gq > v) acc = fmaf(cv, gcol[((w_lo + v) & 7) * 8], acc);
+                    }
+                    if (on && sub == 0) cb[gq] = c_mine;
+                    __syncwarp();
+                    VLOOP(i) {
+                        float qi = qb[i];
+                        for (int v = 0; v < cnt; ++v) qi = fmaf(cb[v], hs[(size_t)(w_lo + v) * kParams + i], qi);
+                        qb[i] = qi;
+                    }
+                    __syncwarp();
+                    k += cnt;
+                }
+                float q[3] = {0.f, 0.f, 0.f};
+                VL(c, i) q[c] = qb[i];
+#ifdef MVS_TL_MARK
+                if (lane == 0) MVS_TL_MARK(clock64() - tl_t0, hl);
+#endif
                 VL(c, i) d[i] = q[c];
             }
             VLOOP(i) prev_g[i] = g[i];

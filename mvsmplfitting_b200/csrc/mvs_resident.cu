@@ -13,7 +13,18 @@
 //
 // The arithmetic is the same set of building blocks (mvs_math.cuh) in the same data flow as the
 // batched kernels of mvs_closure.cu; only reduction orders differ (warp-tree vs serial sums).
+#include <cstddef>
 #include "mvs_internal.cuh"
+#ifdef MVS_PHASE_DBG
+namespace mvs { __device__ long long g_phase_clk[64];   /* [0..31] stamps of CTA 0; [32..39] max over CTAs of coarse segment times; [40,41] two-loop */ }
+// longest two-loop recursion seen (cycles) and the history length it ran with
+#define MVS_TL_MARK(dt, hl)                                                                                         \
+    do {                                                                                                            \
+        if ((unsigned long long)(dt) > atomicMax(reinterpret_cast<unsigned long long*>(&mvs::g_phase_clk[40]),      \
+                                                 (unsigned long long)(dt)))                                         \
+            mvs::g_phase_clk[41] = (hl);                                                                            \
+    } while (0)
+#endif
 #include "mvs_lbfgs_core.cuh"
 
 namespace mvs {
@@ -21,7 +32,6 @@ namespace mvs {
 // -DMVS_PHASE_DBG (scripts/phase_times.py builds libmvsmpl_dbg.so with it): thread 0 of CTA 0 stamps clock64() after
 // every barrier of frame_step_kernel, so the serial phases of one frame's round can be timed without a profiler.
 #ifdef MVS_PHASE_DBG
-__device__ long long g_phase_clk[64];       // [0..31] stamps of CTA 0; [32..39] max over CTAs of coarse segment times
 __device__ __forceinline__ void phase_mark(int i) {
     if (threadIdx.x != 0) return;
     const long long c = clock64();
@@ -87,6 +97,8 @@ struct ResidentSmem {
     // optimiser vectors (lbfgs_resident_kernel only)
     float lx[88], lg[88], ld[88], lprev_g[88], lx_init[88], lg_prev[88], lbg0[88], lbg1[88], lx_eval[88], lg_new[88];
     float ro[128], al[128];
+    float gram[kGramFloats];               // s_i . y_j within 8-slot blocks of the history ring (blocked two-loop recursion)
+    float tl_scratch[96];
     // level schedule of the kinematic tree (copy of ResidentModel::cs / par: shared-memory latency instead of
     // dependent constant-bank loads inside the level loops)
     int nlev, lev_ptr[kJoints + 1], lev_j[kJoints], ch_ptr[kJoints + 1], ch_j[kJoints], par[kJoints];
@@ -101,6 +113,9 @@ struct ResidentSmem {
     LossParams lp;                         // this frame's CURRENT stage (multi-stage kernels)
     FrameScalars fs;
 };
+
+static_assert(offsetof(ResidentSmem, gram) % 16 == 0, "cp.async 16-byte staging of the block Gram");
+static_assert(sizeof(ResidentSmem) + 2 * 100 * kParams * sizeof(float) <= 112 * 1024, "two frame CTAs per SM (227 KB)");
 
 // Inputs of the dense regime (SDF term on): the skinning kernel already produced every vertex of the frame, and
 // sdf_fused_kernel the unit-factor adjoint of the vertices inside the penetration cone (per 1024-vertex part).
@@ -272,28 +287,29 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
             S.rowbase[ncol + t] = 3 * n + t % 3;
         }
     } else {
+        // warp per Qk row (896 B = 2 x LDG.128 per lane), FOUR rows in flight per warp: the 231 KB slice comes from L2
+        // and the phase is pure latency, so the depth of the load queue is what sets its length
         const float4 ph0 = *reinterpret_cast<const float4*>(&S.Phi[4 * lane]);
         const float4 ph1 = lane < 24 ? *reinterpret_cast<const float4*>(&S.Phi[128 + 4 * lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int col0 = warp; col0 < ncol; col0 += 2 * (kResThreads / 32)) {
-            const int col1 = col0 + kResThreads / 32;
-            const float* r0 = m.Qk + (size_t)S.rowbase[col0] * kFeatPad;
-            const float* r1 = m.Qk + (size_t)S.rowbase[col1 < ncol ? col1 : col0] * kFeatPad;
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(r0 + 4 * lane));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(r1 + 4 * lane));
-            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
-            if (lane < 24) {
-                a1 = __ldg(reinterpret_cast<const float4*>(r0 + 128 + 4 * lane));
-                b1 = __ldg(reinterpret_cast<const float4*>(r1 + 128 + 4 * lane));
+        constexpr int kW = kResThreads / 32;
+        for (int col0 = warp; col0 < ncol; col0 += 4 * kW) {
+            float4 a[4], bq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int col = col0 + u * kW;
+                const float* r = m.Qk + (size_t)S.rowbase[col < ncol ? col : col0] * kFeatPad;
+                a[u] = __ldg(reinterpret_cast<const float4*>(r + 4 * lane));
+                bq[u] = lane < 24 ? __ldg(reinterpret_cast<const float4*>(r + 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float p0 = a0.x * ph0.x;
-            p0 = fmaf(a0.y, ph0.y, p0); p0 = fmaf(a0.z, ph0.z, p0); p0 = fmaf(a0.w, ph0.w, p0);
-            p0 = fmaf(a1.x, ph1.x, p0); p0 = fmaf(a1.y, ph1.y, p0); p0 = fmaf(a1.z, ph1.z, p0); p0 = fmaf(a1.w, ph1.w, p0);
-            float p1 = b0.x * ph0.x;
-            p1 = fmaf(b0.y, ph0.y, p1); p1 = fmaf(b0.z, ph0.z, p1); p1 = fmaf(b0.w, ph0.w, p1);
-            p1 = fmaf(b1.x, ph1.x, p1); p1 = fmaf(b1.y, ph1.y, p1); p1 = fmaf(b1.z, ph1.z, p1); p1 = fmaf(b1.w, ph1.w, p1);
-            p0 = warp_sum(p0);
-            p1 = warp_sum(p1);
-            if (lane == 0) { S.vp[col0] = p0; if (col1 < ncol) S.vp[col1] = p1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float p = a[u].x * ph0.x;
+                p = fmaf(a[u].y, ph0.y, p); p = fmaf(a[u].z, ph0.z, p); p = fmaf(a[u].w, ph0.w, p);
+                p = fmaf(bq[u].x, ph1.x, p); p = fmaf(bq[u].y, ph1.y, p); p = fmaf(bq[u].z, ph1.z, p); p = fmaf(bq[u].w, ph1.w, p);
+                p = warp_sum(p);
+                const int col = col0 + u * kW;
+                if (lane == 0 && col < ncol) S.vp[col] = p;
+            }
         }
     }
     __syncthreads();
@@ -697,7 +713,8 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
     }
     if (t < (int)(sizeof(LossParams) / 4)) reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[0])[t];
     __syncthreads();
-    LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval, S.lg_new, H};
+    LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval, S.lg_new, H,
+                S.gram, S.tl_scratch};
     // hard bound on closure evaluations per frame and stage (never reached by a terminating line search; a guard
     // against hanging the GPU): every outer step costs at most 1 + max_eval + max_iter evaluations
     const long long eval_cap = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
@@ -788,6 +805,14 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ss), "l"(gs + 2 * i));
         }
         for (int i = t; i < hl; i += kResThreads) S.ro[i] = L.ro[(size_t)b * L.H + i];
+        {   // block Gram of the live part of the ring
+            const float* gg = L.gram + (size_t)b * kGramFloats;
+            const int nfl4 = ((hl == L.H ? L.H : hl) + 7) / 8 * 16;      // float4 packets
+            for (int i = t; i < nfl4; i += kResThreads) {
+                const unsigned sg = (unsigned)__cvta_generic_to_shared(S.gram + 4 * i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sg), "l"(gg + 4 * i));
+            }
+        }
         asm volatile("cp.async.commit_group;");
         // the optimiser's seven 86-vectors: one coalesced read now, one write-back after the step (every dot
         // product / axpy of the state machine then runs out of shared memory instead of ~30 dependent L2 round trips)
@@ -866,7 +891,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     if (warp == 0) {
         FrameScalars s = fs0;
         LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval,
-                    S.lg_new, L.H};
+                    S.lg_new, L.H, S.gram, S.tl_scratch};
         lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
         __syncwarp();
         if (s.phase == PH_DONE && s.stage + 1 < nstages) {      // this frame moves on to its next stage
@@ -892,6 +917,8 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
                 L.hist_s[((size_t)b * L.H + wslot) * kParams + i] = hs[(size_t)wslot * kParams + i];
             }
             if (lane == 0) L.ro[(size_t)b * L.H + wslot] = S.ro[wslot];
+            float* gg = L.gram + (size_t)b * kGramFloats + (wslot >> 3) * 64;
+            gg[lane] = S.gram[(wslot >> 3) * 64 + lane]; gg[lane + 32] = S.gram[(wslot >> 3) * 64 + lane + 32];
         }
         if (lane == 0) { L.sc[b] = s; S.fs = s; }
     }

@@ -718,7 +718,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
     }
 }
 
-int launch_sdf_fused(mvs_ctx* ctx, const float* x_dev, const void* frame_scalars, cudaStream_t st) {
+int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;
     const LossParams& lp = ctx->loss;

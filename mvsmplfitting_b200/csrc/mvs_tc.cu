@@ -111,7 +111,8 @@ __device__ long long g_tc_clk[32];      // clock64 stamps of CTA (0,0): see scri
 #endif
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
+posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a8,
+                        const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
                         const int* __restrict__ na_ptr, int cta_slots, int ntiles, float* __restrict__ poffT,
                         int* __restrict__ err_flag) {
     pdl_wait();
@@ -161,8 +162,21 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer
-            mbar_expect_tx(a_full, kTcKCh * kTcABytes);
-            for (int kc = 0; kc < kTcKCh; ++kc) tma_load_2d(sA + (size_t)kc * kTcABytes, &map_a, kc * kTcBK, m0, a_full);
+            // A operand.  Every CTA of the M tile reads it, so with 148 CTAs the 112 KB tile costs as much L2 traffic
+            // as posedirs itself; at the tail of a fit only a few of its 128 rows are live, and those are fetched as
+            // 8-row boxes (one swizzle atom each: same shared-memory image).  Rows that are not loaded hold whatever
+            // was there: their accumulator rows are never read.
+            const int live_rows = min(kTcBM, na - m0);
+            if (live_rows <= 32) {
+                const int groups = (live_rows + 7) / 8;
+                mbar_expect_tx(a_full, kTcKCh * groups * 8 * kTcBK * 4);
+                for (int kc = 0; kc < kTcKCh; ++kc)
+                    for (int gq = 0; gq < groups; ++gq)
+                        tma_load_2d(sA + (size_t)kc * kTcABytes + (size_t)gq * 1024, &map_a8, kc * kTcBK, m0 + 8 * gq, a_full);
+            } else {
+                mbar_expect_tx(a_full, kTcKCh * kTcABytes);
+                for (int kc = 0; kc < kTcKCh; ++kc) tma_load_2d(sA + (size_t)kc * kTcABytes, &map_a, kc * kTcBK, m0, a_full);
+            }
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 for (int kc = 0; kc < kTcKCh; ++kc) {
@@ -465,7 +479,7 @@ skin_small_kernel(const float* __restrict__ poffT, const float* __restrict__ ST,
 
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_a8, map_b;
     float* Qtc = nullptr;       // [3N][224] TF32-rounded posedirs rows (columns >= 207 zero)
     float* poffT = nullptr;     // [3N][ldA] pose offsets, frame fastest (output of the tensor-core contraction)
     int* err = nullptr;
@@ -527,6 +541,7 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
     if (!T->ready) {
         int rc;
         if ((rc = encode_map(ctx, &T->map_a, w.PhiTc, (uint64_t)w.ldA, kTcBM))) return rc;
+        if ((rc = encode_map(ctx, &T->map_a8, w.PhiTc, (uint64_t)w.ldA, 8))) return rc;
         if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)3 * m.N, kTcBN))) return rc;
         if ((rc = dev_alloc(ctx, &T->poffT, (size_t)3 * m.N * w.ldA))) return rc;
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(posedirs_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
@@ -538,7 +553,7 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
     const int mtiles = (nb + kTcBM - 1) / kTcBM;
     dim3 grid(std::min(ctx->sm_count, ntiles), mtiles);          // surplus CTAs exit: the kernel splits the tiles from *na
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
-               MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_b, w.ldA,
+               MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_a8, T->map_b, w.ldA,
                                            3 * m.N, (const int*)w.na, ctx->sm_count, ntiles, T->poffT, T->err)));
     const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (nb + 31) / 32;
     if (nb <= kSkinSmallMax) {                          // straggler tail: lane = vertex, one chunk per CTA

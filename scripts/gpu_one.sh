@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python scripts/tail_latency.py 1 > gpurun_out/k_tail1.txt 2>&1; tail -14 gpurun_out/k_tail1.txt
-timeout 300 python scripts/tail_latency.py 4 > gpurun_out/k_tail4.txt 2>&1; tail -12 gpurun_out/k_tail4.txt
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:lbfgs_resident_kernel -c 1 -o gpurun_out/p_lbfgs_resident_kernel python scripts/prof_closure.py resident > gpurun_out/p_ncu_res.log 2>&1
+ls -la gpurun_out | grep p_lbfgs

@@ -42,6 +42,7 @@ print("total %.2f us" % ((prev - buf[0]) / ghz / 1e3))
 print("max over all CTAs and launches (us): closure %.2f | history wait %.2f | advance+write-back %.2f | next pose %.2f | "
       "start->advanced %.2f | start->end %.2f" % tuple(buf[32 + k] / ghz / 1e3 for k in range(6)))
 
+print("longest two-loop recursion: %.2f us with %d history pairs" % (buf[40] / ghz / 1e3, buf[41]))
 # tensor-core contraction: stamps of CTA (0, 0) in the last launch
 tb = (ctypes.c_longlong * 32)()
 if hasattr(lib, "mvs_debug_tc_clocks") and lib.mvs_debug_tc_clocks(tb, 32) == 0 and tb[0]:

@@ -21,6 +21,10 @@ for B in ((256, 1) if mode == "closure" else (256,)):
             for _ in range(3):
                 ctx.closure(x)
             torch.cuda.synchronize()
+    elif mode == "resident":          # frame-resident regime: one launch runs the whole stage
+        ctx.set_loss(body_prior="gmm", interpenetration=False, **w)
+        ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=2))
+        torch.cuda.synchronize()
     else:
         ctx.set_loss(body_prior="gmm", interpenetration=True, coll_loss_weight=1000.0, **w)
         ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=2))

@@ -363,7 +363,9 @@ def run_reference(args):
     import multiprocessing as mp
     import warnings
     warnings.filterwarnings("ignore")
-    cores = max(1, min(os.cpu_count() or 1, args.ref_workers))
+    # one process per PHYSICAL core (hyper-thread pairs share the FP units and the L2; with 64 logical CPUs busy a
+    # frame takes 3.3x its single-process time and a step would not fit the few-minutes budget)
+    cores = max(1, min((os.cpu_count() or 2) // 2, args.ref_workers))
     V, sdf = args.views, bool(args.sdf)
     from oracle import sdf_oracle
     sdf_oracle.build()

@@ -215,6 +215,29 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Warp-wide extreme of a float with the arg-index of its first occurrence ("ties -> lowest vertex index", like
+// torch.min / max on CPU) in two redux.sync instructions: floats are mapped to unsigned keys of the same order
+// (-0 is folded into +0 first, so equal floats have equal keys).
+__device__ __forceinline__ unsigned float_order_key(float f) {
+    const unsigned u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ void warp_argmin(float& v, int& idx) {
+    const unsigned k = float_order_key(v);
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, k);
+    idx = (int)__reduce_min_sync(0xffffffffu, k == kmin ? (unsigned)idx : 0x7fffffffu);
+    v = float_from_order_key(kmin);
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& idx) {
+    const unsigned k = float_order_key(v);
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, k);
+    idx = (int)__reduce_min_sync(0xffffffffu, k == kmax ? (unsigned)idx : 0x7fffffffu);
+    v = float_from_order_key(kmax);
+}
+
 template <class T> int dev_alloc(mvs_ctx* ctx, T** p, size_t count);
 template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t count);
 

@@ -419,15 +419,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float l2 = __shfl_xor_sync(0xffffffffu, lo[c], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[c], o);
-                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
-                const float h2 = __shfl_xor_sync(0xffffffffu, hi[c], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[c], o);
-                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
-            }
-        }
+        for (int c = 0; c < 3; ++c) { warp_argmin(lo[c], ilo[c]); warp_argmax(hi[c], ihi[c]); }
         if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) { s_wb[warp][c] = lo[c]; s_wb[warp][3 + c] = hi[c]; s_wi[warp][c] = ilo[c]; s_wi[warp][3 + c] = ihi[c]; }
@@ -435,7 +427,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         if (t < G && t < 256) ctab[t] = (float)(-1 + (t + 0.5) * (double)(float)(2. / (G - 1)));   // voxel_centre, tabulated
     }
     __syncthreads();
-    // every warp folds the eight warp boxes itself (lanes 0..7, three shuffle levels): no second barrier
+    // every warp folds the eight warp boxes itself (each lane holds one of them): no second barrier
     FrameBox fb;
     {
         const int wsrc = lane & 7;
@@ -444,15 +436,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
 #pragma unroll
         for (int c = 0; c < 3; ++c) { lo[c] = s_wb[wsrc][c]; hi[c] = s_wb[wsrc][3 + c]; ilo[c] = s_wi[wsrc][c]; ihi[c] = s_wi[wsrc][3 + c]; }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float l2 = __shfl_xor_sync(0xffffffffu, lo[c], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[c], o);
-                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
-                const float h2 = __shfl_xor_sync(0xffffffffu, hi[c], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[c], o);
-                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
-            }
-        }
+        for (int c = 0; c < 3; ++c) { warp_argmin(lo[c], ilo[c]); warp_argmax(hi[c], ihi[c]); }
         float ext = -1.f;
         fb.cmax = 0;
 #pragma unroll
@@ -489,19 +473,14 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
     const bool cull = (num_faces == 1);
     const bool tab = (G <= 256);
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
-#pragma unroll 1
-    for (int pass = 0; pass < passes; ++pass) {
-        const int blk = pidx * passes + pass;
-        if (blk >= nblocks) { if (lane == 0) s_wcnt[pass][warp] = 0; continue; }
-        const int n = blk * kSdfFThreads + t;
-        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float gcv[3] = {0.f, 0.f, 0.f};
-        // Chunk-level cull: the skinning kernel left the box of every 64 consecutive vertices.  The voxel centres a
-        // vertex at `loc` can touch lie within (loc + 1) G/(G-1) +- 2/(G-1) (+1 shifted); if that whole box is on the
-        // negative side of one cone plane and on the positive side of another, no vertex of the chunk can see a
-        // voxel with phi != 0: value and gradient are exactly zero and its two warps skip loads, divisions, corners.
-        bool skip = false;
-        const int chunk = (blk * kSdfFThreads + warp * 32) / 64;
+    // Chunk-level cull: the skinning kernel left the box of every 64 consecutive vertices.  The voxel centres a vertex
+    // at `loc` can touch lie within (loc + 1) G/(G-1) +- 2/(G-1) (+1 shifted); if that whole box is on the negative
+    // side of one cone plane and on the positive side of another, no vertex of the chunk can see a voxel with
+    // phi != 0: value and gradient are exactly zero and its two warps skip loads, divisions, corners.  Lane p of a
+    // warp tests the warp's chunk of pass p once; the pass loop reads the verdict with a shuffle.
+    bool my_skip = false;
+    if (lane < passes) {
+        const int chunk = ((pidx * passes + lane) * kSdfFThreads + warp * 32) / 64;
         if (cull && nbox <= 256 && chunk < nbox) {
             const float gs = (float)G / (float)(G - 1), pad = 2.02f / (float)(G - 1) + 1e-5f;
             float wlo[3], whi[3];
@@ -523,8 +502,17 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                 all_neg = all_neg || (smax < -cm[q]);
                 all_pos = all_pos || (smin > cm[q]);
             }
-            skip = all_neg && all_pos;
+            my_skip = all_neg && all_pos;
         }
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+        const int blk = pidx * passes + pass;
+        if (blk >= nblocks) { if (lane == 0) s_wcnt[pass][warp] = 0; continue; }
+        const int n = blk * kSdfFThreads + t;
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        float gcv[3] = {0.f, 0.f, 0.f};
+        const bool skip = __shfl_sync(0xffffffffu, (int)my_skip, pass) != 0;
         if (n < N && !skip) {
             float loc[3], w1[3];
             int i0[3];
@@ -550,8 +538,24 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                     px[q][o] = (cx[o] + 1.f) * cn[q][0]; py[q][o] = (cy[o] + 1.f) * cn[q][1]; pz[q][o] = (cz[o] + 1.f) * cn[q][2];
                 }
             }
+            // whole-cell test first: the extreme plane distances over the 8 corners are sums of per-axis extremes; if
+            // one plane has every corner outside (negative) and another every corner on its positive side, no corner
+            // can be inside the cone -- true for almost every vertex -- and the corner loop is skipped
+            bool cell_out = false;
+            if (cull) {
+                bool any_neg = false, any_pos = false;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float smax = fmaxf(px[q][0], px[q][1]) + fmaxf(py[q][0], py[q][1]) + fmaxf(pz[q][0], pz[q][1]);
+                    const float smin = fminf(px[q][0], px[q][1]) + fminf(py[q][0], py[q][1]) + fminf(pz[q][0], pz[q][1]);
+                    any_neg = any_neg || (smax < -cm[q]);
+                    any_pos = any_pos || (smin > cm[q]);
+                }
+                cell_out = any_neg && any_pos;
+            }
 #pragma unroll
             for (int corner = 0; corner < 8; ++corner) {
+                if (cell_out) break;
                 const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
                 const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
                 if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;

@@ -256,7 +256,7 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 // One vertex of one frame: v_posed = template + shapedirs.betas + pose offset, then linear blend skinning
 // (lbs.py:179,203,207-220).  skin_kernel (lane = frame) and skin_small_kernel (lane = vertex) both call this with every
 // operation spelled out, so the two produce the same bits: a frame's result must not depend on which of the two
-// kernels its batch size selected.  A(j, c) returns entry c (row-major 3x4) of joint j's transform for this frame.
+// kernels its batch size selected.  A(j, a12) loads the 12 entries (row-major 3x4) of joint j's transform for this frame.
 template <class AFn>
 __device__ __forceinline__ void skin_vertex(const float* __restrict__ st /* [3][11]: shapedirs row | template */,
                                             const float* beta, const float* poff, const int* __restrict__ ell_j,
@@ -274,9 +274,10 @@ __device__ __forceinline__ void skin_vertex(const float* __restrict__ st /* [3][
     for (int e = 0; e < KW; ++e) {
         const float w = ell_w[n * KW + e];
         if (w != 0.f) {
-            const int j = ell_j[n * KW + e];
+            float a12[12];
+            A(ell_j[n * KW + e], a12);
 #pragma unroll
-            for (int c = 0; c < 12; ++c) T[c] = fmaf(w, A(j, c), T[c]);
+            for (int c = 0; c < 12; ++c) T[c] = fmaf(w, a12[c], T[c]);
         }
     }
 #pragma unroll
@@ -303,7 +304,7 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             float* __restrict__ bboxp) {
     pdl_wait();
     extern __shared__ __align__(16) float sk[];
-    float* As = sk;                                   // [288][32]
+    float* As = sk;                                   // [24 joints][32 lanes][12]
     float* Bs = As + kSkinFloats * 32;                // [10][32]
     float* Ovp = Bs + kBetas * 32;                    // [32][193]
     float* Ov = Ovp + 32 * kSkinOutLd;                // [32][193]
@@ -321,7 +322,11 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
     const int nx = (nchunks + per_cta - 1) / per_cta;
     if ((int)blockIdx.x >= nx) return;
     // the 32 frames' transforms and shape coefficients are loaded once and reused for every vertex chunk of this CTA
-    for (int e = tid; e < kSkinFloats * 32; e += kSkinThreads) As[e] = At[(size_t)(e >> 5) * ldA + min(f0 + (e & 31), na - 1)];
+    // layout [joint][lane][12]: a lane's 3x4 transform is three conflict-free LDS.128 (lane stride 48 B)
+    for (int e = tid; e < kSkinFloats * 32; e += kSkinThreads) {
+        const int jc = e >> 5, ln = e & 31;
+        As[((jc / 12) * 32 + ln) * 12 + jc % 12] = At[(size_t)jc * ldA + min(f0 + ln, na - 1)];
+    }
     for (int e = tid; e < kBetas * 32; e += kSkinThreads)
         Bs[e] = Phi[(size_t)min(f0 + (e & 31), na - 1) * kFeatPad + kPoseBasis + (e >> 5)];
     constexpr int kVw = kSkinV / 8;                                       // vertices per warp and chunk
@@ -354,7 +359,12 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             if (n < N) {
                 float vp[3], vvv[3];
                 skin_vertex(Sts + li * 33, beta, pf[i], ell_j, ell_w, KW, (size_t)n,
-                            [&](int j, int c) { return As[(j * 12 + c) * 32 + lane]; }, vp, vvv);
+                            [&](int j, float* a12) {
+                                const float4* q = reinterpret_cast<const float4*>(As + (j * 32 + lane) * 12);
+                                const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                                a12[0] = q0.x; a12[1] = q0.y; a12[2] = q0.z; a12[3] = q0.w; a12[4] = q1.x; a12[5] = q1.y;
+                                a12[6] = q1.z; a12[7] = q1.w; a12[8] = q2.x; a12[9] = q2.y; a12[10] = q2.z; a12[11] = q2.w;
+                            }, vp, vvv);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float vv = vvv[r];
@@ -438,7 +448,11 @@ skin_small_kernel(const float* __restrict__ poffT, const float* __restrict__ ST,
             float poff[3], vp[3], vv[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) poff[c] = poffT[(size_t)(3 * n + c) * ldA + f];
-            skin_vertex(st, Bs[f], poff, ell_j, ell_w, KW, (size_t)n, [&](int j, int c) { return As[f][j * 12 + c]; }, vp, vv);
+            skin_vertex(st, Bs[f], poff, ell_j, ell_w, KW, (size_t)n,
+                        [&](int j, float* a12) {
+#pragma unroll
+                            for (int c = 0; c < 12; ++c) a12[c] = As[f][j * 12 + c];
+                        }, vp, vv);
             const size_t off = ((size_t)f * N + n) * 3;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -448,15 +462,7 @@ skin_small_kernel(const float* __restrict__ poffT, const float* __restrict__ ST,
         }
         if (bboxp) {               // box of the chunk: extreme value, ties -> lowest vertex index (as skin_kernel)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float l2 = __shfl_xor_sync(0xffffffffu, lo[r], o); const int il2 = __shfl_xor_sync(0xffffffffu, ilo[r], o);
-                    if (l2 < lo[r] || (l2 == lo[r] && il2 < ilo[r])) { lo[r] = l2; ilo[r] = il2; }
-                    const float h2 = __shfl_xor_sync(0xffffffffu, hi[r], o); const int ih2 = __shfl_xor_sync(0xffffffffu, ihi[r], o);
-                    if (h2 > hi[r] || (h2 == hi[r] && ih2 < ihi[r])) { hi[r] = h2; ihi[r] = ih2; }
-                }
-            }
+            for (int r = 0; r < 3; ++r) { warp_argmin(lo[r], ilo[r]); warp_argmax(hi[r], ihi[r]); }
             if (warp == 1 && lane == 0) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r) { s_b[f][r] = lo[r]; s_b[f][3 + r] = hi[r]; s_i[f][r] = ilo[r]; s_i[f][3 + r] = ihi[r]; }

@@ -128,16 +128,17 @@ struct FrameBox {                     // bounding box of one frame's mesh (fitti
     float pad;
 };
 
-// sdf_fused_kernel gives a CTA 1, 2 or 4 blocks of 256 vertices: few active frames -> more, smaller CTAs (latency),
-// many -> fewer, larger ones (less per-CTA overhead).  Results are emitted per block, so they do not depend on it.
-constexpr int kSdfMaxParts = 32;
-__host__ __device__ inline int sdf_passes_for(int na, int n_verts) {
-    const int p1 = (n_verts + 255) / 256;
-    if (p1 > kSdfMaxParts) return 4;
-    if (na * p1 <= 640) return 1;
-    if (na * ((p1 + 1) / 2) <= 640) return 2;
-    return 4;
+// sdf_fused_kernel gives a CTA 1..8 blocks of 256 vertices: few active frames -> more, smaller CTAs (latency), many ->
+// fewer, larger ones, sized so that one wave of resident CTAs covers the launch (the per-CTA prologue -- box fold,
+// triangle, cone -- is then paid once per several blocks; capped so that the few expensive blocks near the cone
+// cannot pile up in one CTA).
+constexpr int kSdfMaxPasses = 8;
+inline int sdf_passes_for(int na, int nblocks, int cta_slots) {
+    const long long blocks = (long long)na * nblocks;
+    int p = (int)((blocks + cta_slots - 1) / cta_slots);
+    return p < 1 ? 1 : (p > kSdfMaxPasses ? kSdfMaxPasses : p);
 }
+
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,

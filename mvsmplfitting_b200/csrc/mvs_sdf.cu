@@ -372,7 +372,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                  const int* __restrict__ faces, int num_faces, int f0, int f1, int f2, int G,
                  const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w,
                  int KW, const float* __restrict__ Wd, const float* __restrict__ Qk, float* __restrict__ parts5,
-                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout, int passes) {
+                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout, int passes,
+                 float* __restrict__ gcoord) {
     pdl_wait();
     const int slot = blockIdx.y, pidx = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -392,10 +393,9 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
     __shared__ float s_wb[8][6];
     __shared__ int s_wi[8][6];
     __shared__ float ctab[256];
-    __shared__ float s_red[4][8][5];
-    __shared__ int s_wcnt[4][8], s_woff[4][9];
-    __shared__ unsigned s_mask[4][8];
-    __shared__ float s_gc[4][3][kSdfFThreads];         // sample gradients of the vertices that have one
+    __shared__ float s_red[kSdfMaxPasses][8][5];
+    __shared__ int s_wcnt[kSdfMaxPasses][8], s_woff[kSdfMaxPasses][9];
+    __shared__ unsigned s_mask[kSdfMaxPasses][8];
     __shared__ int seg_n[kSdfFThreads];               // one block's vertices with a non-zero sample gradient
     __shared__ float seg_g[kSdfFThreads * 3];
     __shared__ float sA[kSkinFloats];
@@ -466,6 +466,16 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         cn[q][0] = ea[1] * eb[2] - ea[2] * eb[1]; cn[q][1] = ea[2] * eb[0] - ea[0] * eb[2]; cn[q][2] = ea[0] * eb[1] - ea[1] * eb[0];
         cm[q] = 3.5e-4f * sqrtf(cn[q][0] * cn[q][0] + cn[q][1] * cn[q][1] + cn[q][2] * cn[q][2]);
     }
+    // plane of triangle 0 in the same shifted coordinates (w = centre + 1, the corner is the origin): the ray from a
+    // voxel centre to the corner can only cross the triangle if the two lie on opposite sides of this plane, i.e.
+    // <pn, w> - pd has the sign of pd.  Voxels between the corner and the triangle pass the cone test but fail this one.
+    float pn[3], pd, pm;
+    {
+        const float e1[3] = {tri[3] - tri[0], tri[4] - tri[1], tri[5] - tri[2]}, e2[3] = {tri[6] - tri[0], tri[7] - tri[1], tri[8] - tri[2]};
+        pn[0] = e1[1] * e2[2] - e1[2] * e2[1]; pn[1] = e1[2] * e2[0] - e1[0] * e2[2]; pn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        pd = pn[0] * (tri[0] + 1.f) + pn[1] * (tri[1] + 1.f) + pn[2] * (tri[2] + 1.f);
+        pm = 2e-3f * sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);      // conservative: |w| <= 2 sqrt 3, fp32 rounding
+    }
     // ---- sampling: block (pidx * passes + pass) of 256 vertices per pass, one vertex per thread and pass.  Sums,
     //      vertex lists and adjoint partials are emitted PER BLOCK, so the arithmetic of a frame does not depend on
     //      how many blocks this launch gave to one CTA (i.e. not on how many other frames are still active): frames
@@ -505,11 +515,20 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             my_skip = all_neg && all_pos;
         }
     }
+    float vcur[3] = {0.f, 0.f, 0.f};                   // this pass' vertex; the next one is fetched a pass ahead
+    {
+        const int n0 = pidx * passes * kSdfFThreads + t;
+        if (n0 < N) { vcur[0] = vf[3 * n0]; vcur[1] = vf[3 * n0 + 1]; vcur[2] = vf[3 * n0 + 2]; }
+    }
 #pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
         const int blk = pidx * passes + pass;
         if (blk >= nblocks) { if (lane == 0) s_wcnt[pass][warp] = 0; continue; }
         const int n = blk * kSdfFThreads + t;
+        const float vme[3] = {vcur[0], vcur[1], vcur[2]};
+        if (pass + 1 < passes && n + kSdfFThreads < N) {
+            vcur[0] = vf[3 * (n + kSdfFThreads)]; vcur[1] = vf[3 * (n + kSdfFThreads) + 1]; vcur[2] = vf[3 * (n + kSdfFThreads) + 2];
+        }
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float gcv[3] = {0.f, 0.f, 0.f};
         const bool skip = __shfl_sync(0xffffffffu, (int)my_skip, pass) != 0;
@@ -518,7 +537,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             int i0[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                loc[c] = ((vf[3 * n + c] + tr[c]) - fb.centre[c]) / fb.scale;
+                loc[c] = ((vme[c] + tr[c]) - fb.centre[c]) / fb.scale;
                 const float ix = ((loc[c] + 1.f) * G - 1.f) / 2.f;
                 const float fl = floorf(ix);
                 i0[c] = (int)fl;
@@ -541,8 +560,15 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             // whole-cell test first: the extreme plane distances over the 8 corners are sums of per-axis extremes; if
             // one plane has every corner outside (negative) and another every corner on its positive side, no corner
             // can be inside the cone -- true for almost every vertex -- and the corner loop is skipped
+            float qx[2], qy[2], qz[2];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) { qx[o] = (cx[o] + 1.f) * pn[0]; qy[o] = (cy[o] + 1.f) * pn[1]; qz[o] = (cz[o] + 1.f) * pn[2]; }
             bool cell_out = false;
             if (cull) {
+                // plane side of the whole cell
+                const float smaxp = fmaxf(qx[0], qx[1]) + fmaxf(qy[0], qy[1]) + fmaxf(qz[0], qz[1]) - pd;
+                const float sminp = fminf(qx[0], qx[1]) + fminf(qy[0], qy[1]) + fminf(qz[0], qz[1]) - pd;
+                if ((pd > pm && smaxp < -pm) || (pd < -pm && sminp > pm)) cell_out = true;
                 bool any_neg = false, any_pos = false;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -551,7 +577,7 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                     any_neg = any_neg || (smax < -cm[q]);
                     any_pos = any_pos || (smin > cm[q]);
                 }
-                cell_out = any_neg && any_pos;
+                cell_out = cell_out || (any_neg && any_pos);
             }
 #pragma unroll
             for (int corner = 0; corner < 8; ++corner) {
@@ -570,6 +596,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                     const bool neg = (s1 < -cm[0]) || (s2 < -cm[1]) || (s3 < -cm[2]);
                     const bool pos = (s1 > cm[0]) || (s2 > cm[1]) || (s3 > cm[2]);
                     if (neg && pos) continue;
+                    const float sp = qx[ox] + qy[oy] + qz[oz] - pd;
+                    if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
                 }
                 const float cc[3] = {cx[ox], cy[oy], cz[oz]};
                 const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
@@ -591,7 +619,10 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         }
         const bool nz = (gcv[0] != 0.f) || (gcv[1] != 0.f) || (gcv[2] != 0.f);
         const unsigned nzm = __ballot_sync(0xffffffffu, nz);
-        if (nz) { s_gc[pass][0][t] = gcv[0]; s_gc[pass][1][t] = gcv[1]; s_gc[pass][2][t] = gcv[2]; }
+        if (nz) {                                          // rare: parked in global scratch until the adjoint phase
+            float* gp = gcoord + ((size_t)slot * N + n) * 3;
+            gp[0] = gcv[0]; gp[1] = gcv[1]; gp[2] = gcv[2];
+        }
         // almost every warp is outside the cone: all-zero contributions need no shuffle tree (adding zeros is exact)
         if (__ballot_sync(0xffffffffu, acc[0] != 0.f || nz)) {
 #pragma unroll
@@ -614,8 +645,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
             for (int w2 = 0; w2 < 8; ++w2) a += s_red[pass][w2][q];
             parts5[((size_t)slot * nblocks + blk) * 5 + q] = a;
         }
-    } else if (t >= 32 && t < 32 + passes) {
-        const int pass = t - 32, blk = pidx * passes + pass;
+    } else if (t >= 128 && t < 128 + passes) {
+        const int pass = t - 128, blk = pidx * passes + pass;
         int o = 0;
         if (blk < nblocks) {
             for (int w2 = 0; w2 < 8; ++w2) { s_woff[pass][w2] = o; o += s_wcnt[pass][w2]; }
@@ -636,7 +667,8 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         if (nzm & (1u << lane)) {                          // ascending vertex order: (warp, lane)
             const int pos = s_woff[pass][warp] + __popc(nzm & ((1u << lane) - 1u));
             seg_n[pos] = blk * kSdfFThreads + t;
-            seg_g[3 * pos] = s_gc[pass][0][t]; seg_g[3 * pos + 1] = s_gc[pass][1][t]; seg_g[3 * pos + 2] = s_gc[pass][2][t];
+            const float* gp = gcoord + ((size_t)slot * N + blk * kSdfFThreads + t) * 3;       // written by this thread
+            seg_g[3 * pos] = gp[0]; seg_g[3 * pos + 1] = gp[1]; seg_g[3 * pos + 2] = gp[2];
         }
         if (!have_A) {
             for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
@@ -728,10 +760,13 @@ int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
     const LossParams& lp = ctx->loss;
     const int B = w.B, N = m.N;
     const int nb = w.na_bound > 0 ? w.na_bound : B;    // host-side upper bound of the active-frame count
-    const int passes = sdf_passes_for(nb, N);          // 256-vertex blocks per CTA (results do not depend on it)
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
+    // 256-vertex blocks per CTA: as few as fit the active frames into ONE wave of resident CTAs (3 per SM); the results
+    // are emitted per block and do not depend on it
+    const int passes = sdf_passes_for(nb, nblocks, 3 * ctx->sm_count);
     const int nparts = (nblocks + passes - 1) / passes;
     int rc;
+    if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
     if (!w.sdf_parts5) {
         if ((rc = dev_alloc(ctx, &w.sdf_parts5, (size_t)B * nblocks * 5))) return rc;
         if ((rc = dev_alloc(ctx, &w.sdf_part, (size_t)B * nblocks * kPartFloats))) return rc;
@@ -749,7 +784,7 @@ int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
                                            (const int*)m.faces, lp.sdf_all_faces ? m.F : 1, m.tri0[0], m.tri0[1], m.tri0[2],
                                            lp.sdf_grid, (const float*)w.At, w.ldA, (const int*)m.ell_j, (const float*)m.ell_w, m.KW,
                                            (const float*)m.Wd, (const float*)m.Qk, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
-                                           reinterpret_cast<FrameBox*>(w.sdf_box), passes)));
+                                           reinterpret_cast<FrameBox*>(w.sdf_box), passes, w.sdf_gcoord)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

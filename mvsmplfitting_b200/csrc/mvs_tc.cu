@@ -271,14 +271,15 @@ __device__ __forceinline__ void skin_vertex(const float* __restrict__ st /* [3][
     float T[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) T[c] = 0.f;
+    // padding entries have weight 0 and a valid joint: fma(0, a, T) == T exactly, so no branch (and no dependent
+    // load behind it) is needed
+#pragma unroll 4
     for (int e = 0; e < KW; ++e) {
         const float w = ell_w[n * KW + e];
-        if (w != 0.f) {
-            float a12[12];
-            A(ell_j[n * KW + e], a12);
+        float a12[12];
+        A(ell_j[n * KW + e], a12);
 #pragma unroll
-            for (int c = 0; c < 12; ++c) T[c] = fmaf(w, a12[c], T[c]);
-        }
+        for (int c = 0; c < 12; ++c) T[c] = fmaf(w, a12[c], T[c]);
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -294,8 +295,9 @@ __device__ __forceinline__ void skin_vertex(const float* __restrict__ st /* [3][
 constexpr int kSkinV = 64;
 constexpr int kSkinThreads = 256;
 constexpr int kSkinOutLd = 3 * kSkinV + 1;     // 193
+constexpr int kSkinEllMax = 8;                 // skinning weights per vertex staged in shared memory (SMPL: 4)
 constexpr size_t kSkinSmem =
-    (size_t)(kSkinFloats * 32 + kBetas * 32 + 2 * 32 * kSkinOutLd + 8 * 32 * 6 * 2 + kSkinV * 33) * sizeof(float);
+    (size_t)(kSkinFloats * 32 + kBetas * 32 + 2 * 32 * kSkinOutLd + 8 * 32 * 6 * 2 + kSkinV * 33 + 2 * kSkinV * kSkinEllMax) * sizeof(float);
 
 __global__ void __launch_bounds__(kSkinThreads)
 skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const float* __restrict__ Phi,
@@ -310,6 +312,9 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
     float* Ov = Ovp + 32 * kSkinOutLd;                // [32][193]
     float* Bb = Ov + 32 * kSkinOutLd;                 // [8 warps][32 lanes][6] values, then [..][6] indices
     float* Sts = Bb + 8 * 32 * 6 * 2;                 // [64][33] shapedirs rows | template of this CTA's vertices
+    float* Ews = Sts + kSkinV * 33;                   // [64][KW] skinning weights of the chunk
+    int* Ejs = reinterpret_cast<int*>(Ews + kSkinV * kSkinEllMax);   // [64][KW] their joints
+    const bool ell_smem = KW <= kSkinEllMax;
     const int na = *na_ptr;
     const int f0 = blockIdx.y * 32;
     if (f0 >= na) return;
@@ -344,6 +349,12 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
         }
         __syncthreads();                                                  // previous chunk's staging buffers are free
         for (int e = tid; e < kSkinV * 33; e += kSkinThreads) Sts[e] = (v0 * 33 + e < N * 33) ? ST[(size_t)v0 * 33 + e] : 0.f;
+        if (ell_smem)
+            for (int e = tid; e < kSkinV * KW; e += kSkinThreads) {
+                const bool in = (size_t)v0 * KW + e < (size_t)N * KW;
+                Ews[e] = in ? ell_w[(size_t)v0 * KW + e] : 0.f;
+                Ejs[e] = in ? ell_j[(size_t)v0 * KW + e] : 0;
+            }
         __syncthreads();
         if (!have_beta) {
 #pragma unroll
@@ -358,7 +369,8 @@ skin_kernel(const float* __restrict__ poffT, const float* __restrict__ ST, const
             const int n = v0 + li;
             if (n < N) {
                 float vp[3], vvv[3];
-                skin_vertex(Sts + li * 33, beta, pf[i], ell_j, ell_w, KW, (size_t)n,
+                skin_vertex(Sts + li * 33, beta, pf[i], ell_smem ? Ejs : ell_j, ell_smem ? Ews : ell_w, KW,
+                            ell_smem ? (size_t)li : (size_t)n,
                             [&](int j, float* a12) {
                                 const float4* q = reinterpret_cast<const float4*>(As + (j * 32 + lane) * 12);
                                 const float4 q0 = q[0], q1 = q[1], q2 = q[2];

@@ -266,6 +266,26 @@ class FittingMonitor(object):
         return FittingClosure(optimizer, body_model, camera, gt_joints, loss, joints_conf, joint_weights, use_vposer,
                               vposer, pose_embedding, return_verts=return_verts)
 
+    def run_fitting_stages(self, optimizer, closure, opt_weights):
+        """The stage loop of non_linear_solver.py:109-203 in ONE call.  The reference does, per entry of
+        `opt_weights`: loss.reset_loss_weights(weights); new optimiser; run_fitting.  Here the stages go to mvs_fit,
+        where every frame moves to its next stage as soon as ITS current stage stops (same per-frame schedule and bits
+        as the loop, no waiting for the slowest frame at a stage boundary).  Returns the last stage's final loss."""
+        from .optimizers.lbfgs_ls import LBFGS
+        if not (isinstance(optimizer, LBFGS) and isinstance(closure, FittingClosure) and not closure.use_vposer):
+            raise NotImplementedError("run_fitting_stages needs this package's LBFGS and closure without VPoser")
+        cfgs = []
+        for w in opt_weights:
+            closure.loss.reset_loss_weights(w)
+            cfgs.append(closure.sync_loss_config())
+        x = closure.gather_params()
+        cfg = optimizer.lbfgs_config(closure.ctx, max_outer=self.maxiters, ftol=self.ftol, gtol=self.gtol)
+        final, st = closure.ctx.fit(x, cfgs, cfg)
+        self.last_stats = st
+        closure.scatter_params(x)
+        vals = final.detach().cpu().numpy()
+        return float(vals[0]) if vals.shape[0] == 1 else vals
+
     def run_fitting(self, optimizer, closure, params, body_model, use_vposer=True, pose_embedding=None, vposer=None,
                     camera=None, img_path=None, **kwargs):
         """fitting.py:71-142.  With this package's LBFGS + closure the whole loop (all outer steps, all

@@ -122,3 +122,44 @@ def test_step_by_step_driving_matches_fused_run(syn_model, syn_gmm, tmp_path):
         return torch.cat([p.detach().reshape(B, -1) for p in model.parameters()], dim=1)
     a, b = run(True), run(False)
     assert torch.equal(a, b)
+
+
+def test_run_fitting_stages_equals_stage_loop(syn_model, syn_gmm, tmp_path):
+    """FittingMonitor.run_fitting_stages (mvs_fit: frames change stage on their own) against the reference-style loop
+    'reset_loss_weights -> new optimiser -> run_fitting' over the same stage weights: identical parameters."""
+    from mvsmplfitting_b200 import fitting, prior
+    from mvsmplfitting_b200.optimizers import optim_factory
+    c = G.load_case("gmm8_s3")
+    B = 1
+    stage_w = [{k: torch.tensor(v) for k, v in c["w"].items()} for _ in range(2)]
+    stage_w[1]["body_pose_weight"] = stage_w[1]["body_pose_weight"] * 0.25
+    stage_w[1]["shape_weight"] = stage_w[1]["shape_weight"] * 0.5
+    results = []
+    for merged in (False, True):
+        model, cams, bp = build_scene(syn_model, syn_gmm, tmp_path, c["cams"], B, c["meta"]["model_type"], c["meta"]["body_prior"])
+        x = S.unpack_params(c["X"][:B])
+        model.reset_params(**{k: torch.tensor(v) for k, v in x.items()})
+        loss = fitting.create_loss("smplify", rho=100.0, use_joints_conf=c["meta"]["use_joints_conf"], body_pose_prior=bp,
+                                   shape_prior=prior.create_prior("l2"), angle_prior=prior.create_prior("angle"),
+                                   interpenetration=False, fix_shape=False).to("cuda")
+        params = [p for p in model.parameters() if p.requires_grad]
+        mon = fitting.FittingMonitor(maxiters=5, ftol=1e-9, gtol=1e-9)
+        V = c["gt_uv"].shape[0]
+
+        def make(opt):
+            return mon.create_fitting_closure(
+                opt, model, camera=cams, gt_joints=torch.tensor(c["gt_uv"][:, :B]).cuda(),
+                joints_conf=[torch.tensor(c["conf"][v, :B]).cuda() for v in range(V)],
+                joint_weights=torch.tensor(c["joint_weights"]).unsqueeze(0).cuda(), loss=loss, create_graph=False,
+                use_vposer=False, vposer=None, pose_embedding=None, return_verts=True, return_full_pose=True, use_3d=False)
+        if merged:
+            opt, _ = optim_factory.create_optimizer(params, optim_type="lbfgsls", lr=1.0, maxiters=30)
+            mon.run_fitting_stages(opt, make(opt), stage_w)
+        else:
+            for w in stage_w:
+                loss.reset_loss_weights(w)
+                opt, _ = optim_factory.create_optimizer(params, optim_type="lbfgsls", lr=1.0, maxiters=30)
+                mon.run_fitting(opt, make(opt), params, model, use_vposer=False)
+        results.append({k: getattr(model, k).detach().cpu().clone() for k in fitting.PARAM_SLICES})
+    for k in fitting.PARAM_SLICES:
+        assert torch.equal(results[0][k], results[1][k]), k

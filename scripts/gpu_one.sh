@@ -1,4 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:lbfgs_resident_kernel -c 1 -o gpurun_out/p_lbfgs_resident_kernel python scripts/prof_closure.py resident > gpurun_out/p_ncu_res.log 2>&1
-ls -la gpurun_out | grep p_lbfgs
+for p in 1 2 3; do
+  MVS_SDF_PASSES=$p timeout 300 python bench.py --steps 3 --warmup 2 --cpu-seconds 1 > gpurun_out/k_p$p.txt 2>/dev/null
+  python - <<PY
+import json
+for line in open('gpurun_out/k_p$p.txt'):
+    if line.startswith('{'):
+        d=json.loads(line); r=d['roofline']
+        print('passes $p', round(d['ms_per_step'],2), d['rounds_per_step'], r['kernel_avg_us_instrumented_step'])
+PY
+done

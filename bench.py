@@ -232,8 +232,15 @@ def run_ours(args):
         dense_rounds_frac = None
         alg = algorithmic_bytes(dom, na_avg, V, dense=bool(args.sdf))
         ach = (alg * dom_n) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (cold caches, 256 active
+        # frames): profiles/r01_traffic.json, written from the .ncu-rep files by the profiling scripts
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom]["traffic"]
+        except Exception:
+            pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (ach / hbm_peak) if ach else None, "traffic": None,
+                "frac": (ach / hbm_peak) if ach else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg, "launches": dom_n, "avg_launch_us": (dom_ms * 1e3 / dom_n) if dom_n else None,
                 "avg_active_frames_per_launch": na_avg, "peak_source": peak_src,
                 "note": "the path is latency / L2 bound, not HBM bound: constants (20 MB) live in the 126 MB L2 and one "
@@ -291,9 +298,16 @@ def algorithmic_bytes(kernel: str, na: float, V: int, dense: bool) -> float:
         return N * 33 * 4 + N * 32 + na * (3 * N * 4 + 288 * 4 + 40 + 2 * N * 12)
     if kernel == "vertex_bwd":
         return 3 * N * 218 * 4 + N * 24 * 4 + na * (1152 + 2 * N * 12 + 2048)
-    if kernel in ("sdf_sample", "sdf_finalize", "sdf_fused"):
+    if kernel in ("sdf_sample", "sdf_finalize"):
         return na * (N * 12 + N * 12)
-    if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance", "frame_step"):
+    if kernel == "sdf_fused":                       # vertices + chunk boxes in, per-block sums / flags out (adjoint partials are rare)
+        return na * (N * 12 + 108 * 48 + 27 * 24)
+    if kernel == "frame_step":
+        # once: the 86-vertex slice of Qk (adjoint) and the GMM precisions; per frame: 9 optimiser vectors, detections,
+        # support vertices, SDF block sums, and the curvature history the two-loop recursion reads (about 50 of the
+        # 100 pairs are live on average, 2 x 344 B each, on the ~40 % of the calls that start an iteration)
+        return 3 * 86 * 224 * 4 + 6 * 69 * 69 * 4 + na * (344 * 9 + 204 * V + 86 * 24 + 27 * 24 + 0.4 * 2 * 50 * 344)
+    if kernel in ("frame_fwd", "frame_bwd", "keypoint_loss", "lbfgs_advance"):
         return na * (344 * 3 + 204 * V + 2048 + 86 * 24)
     if kernel == "lbfgs_resident":                  # per frame and evaluation: two passes over its 86-vertex Qk slice
         return na * (2 * 3 * 86 * 218 * 4 + 344 * 3 + 204 * V)

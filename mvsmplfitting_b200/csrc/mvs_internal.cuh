@@ -91,6 +91,8 @@ struct Workspace {
     float* PhiTc = nullptr;           // [ldA][224] pose feature rounded to TF32 (A operand of the tensor-core contraction)
     float* At = nullptr;              // [288][ldA]   skinning transforms, frame fastest
     float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
+    float* pose_cache = nullptr;      // [B][864] per FRAME: R | J | Gam | g | A of the pending trial point (frame_step -> frame_step)
+    int* pose_valid = nullptr;        // [B]
     float* slot_tr = nullptr;         // [B][4] translation of the frame in each slot (dense-regime kernels index by slot only)
     float* vposed = nullptr;          // [B][nvmax][3]
     float* verts = nullptr;           // [B][nvmax][3]  (pre-transl)
@@ -128,15 +130,13 @@ struct FrameBox {                     // bounding box of one frame's mesh (fitti
     float pad;
 };
 
-// sdf_fused_kernel gives a CTA 1..8 blocks of 256 vertices: few active frames -> more, smaller CTAs (latency), many ->
-// fewer, larger ones, sized so that one wave of resident CTAs covers the launch (the per-CTA prologue -- box fold,
-// triangle, cone -- is then paid once per several blocks; capped so that the few expensive blocks near the cone
-// cannot pile up in one CTA).
+// sdf_fused_kernel gives a CTA 1 or 2 blocks of 256 vertices (results are emitted per block and do not depend on it).
+// Measured on the benchmark (us per launch, ~150 active frames): 1 block 40.0, 2 blocks 37.7, 3: 40.7, 4: 42, 8: 54,
+// 16: 76 -- the few expensive blocks near the cone must not pile up in one CTA, and small CTAs balance better than the
+// shorter prologue of large ones saves.
 constexpr int kSdfMaxPasses = 8;
 inline int sdf_passes_for(int na, int nblocks, int cta_slots) {
-    const long long blocks = (long long)na * nblocks;
-    int p = (int)((blocks + cta_slots - 1) / cta_slots);
-    return p < 1 ? 1 : (p > kSdfMaxPasses ? kSdfMaxPasses : p);
+    return (long long)na * nblocks > 2LL * cta_slots ? 2 : 1;
 }
 
 enum KernelId {
@@ -265,6 +265,7 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
 int tc_check_error(mvs_ctx* ctx);
 int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
                       cudaStream_t st);
+int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st);                 // mvs_resident.cu
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
 int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion

@@ -221,6 +221,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         static const bool trace_na = getenv("MVS_TRACE_NA") != nullptr;       // debugging aid: active-list size per chunk
         rc = launch_frame_fwd(ctx, S.x_eval, st);
         if (rc) return rc;
+        if ((rc = frame_step_begin_run(ctx, st))) return rc;
         // The host only needs the active count to know when to stop, so chunk k+1 is enqueued BEFORE the count of
         // chunk k is awaited (kernels exit at once when the list is empty): the GPU never idles on the host round trip.
         if (!S.na_event[0]) {

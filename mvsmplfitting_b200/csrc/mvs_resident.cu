@@ -114,6 +114,8 @@ struct ResidentSmem {
     FrameScalars fs;
 };
 
+constexpr int kPoseCacheFloats = 216 + 72 + 216 + 72 + 288;      // R | J | Gam | g | A
+static_assert(offsetof(ResidentSmem, A) - offsetof(ResidentSmem, R) == (216 + 72 + 216 + 72) * sizeof(float), "pose cache layout");
 static_assert(offsetof(ResidentSmem, gram) % 16 == 0, "cp.async 16-byte staging of the block Gram");
 static_assert(sizeof(ResidentSmem) + 2 * 100 * kParams * sizeof(float) <= 112 * 1024, "two frame CTAs per SM (227 KB)");
 
@@ -131,6 +133,7 @@ struct DenseIn {
     const int* fl;            // [nfl] blocks that wrote partials, ascending
     int nfl;
     float factor;             // cg / scale: d pen / d (sum of samples) over the box scale
+    bool pose_ready;          // R, J, Gam, g, A of this trial point are already in shared memory (frame_step's pose cache)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -243,34 +246,39 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nsup = m.nsup, K = m.K, V = cams.num_views, ncol = 3 * nsup;
 
-    // ---- P1 Rodrigues, rest joints
-    if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
-    else if (t >= 32 && t < 32 + 72) {
-        const int jc = t - 32;
-        float a = m.Jt[jc];
+    // ---- P1 Rodrigues, rest joints (skipped when the caller restored them: the previous frame_step computed the pose
+    //      forward of exactly this trial point for the dense kernels and parked it in the per-frame pose cache)
+    if (!din.pose_ready) {
+        if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
+        else if (t >= 32 && t < 32 + 72) {
+            const int jc = t - 32;
+            float a = m.Jt[jc];
 #pragma unroll
-        for (int l = 0; l < kBetas; ++l) a = fmaf(m.JS[jc * kBetas + l], S.x[kOffBetas + l], a);
-        S.J[jc] = a;
+            for (int l = 0; l < kBetas; ++l) a = fmaf(m.JS[jc * kBetas + l], S.x[kOffBetas + l], a);
+            S.J[jc] = a;
+        }
     }
     for (int i = t; i < kJoints * 9; i += kResThreads) { S.dGam[i] = 0.f; S.dR[i] = 0.f; }
     for (int i = t; i < kJoints * 3; i += kResThreads) { S.dg[i] = 0.f; S.dJ[i] = 0.f; }
     for (int i = t; i < kParams; i += kResThreads) S.grad[i] = 0.f;
     __syncthreads();
     PHASE_MARK(2);
-    // ---- P2 kinematic chain, level-parallel
-    chain_fwd_levels(S);
-    PHASE_MARK(3);
-    // ---- P3 skinning transforms and the feature row
-    if (t < kJoints) make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], &S.A[12 * t]);
-    else if (t >= 32) {
-        const int k = t - 32;                                                      // 224 threads, 224 entries
-        float v;
-        if (k < kPoseBasis) v = S.R[9 + k] - (((k % 9) % 4 == 0) ? 1.0f : 0.0f);
-        else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
-        else v = (k == kFeat - 1) ? 1.0f : 0.0f;
-        S.Phi[k] = v;
+    if (!din.pose_ready) {
+        // ---- P2 kinematic chain, level-parallel
+        chain_fwd_levels(S);
+        PHASE_MARK(3);
+        // ---- P3 skinning transforms and the feature row
+        if (t < kJoints) make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], &S.A[12 * t]);
+        else if (t >= 32) {
+            const int k = t - 32;                                                      // 224 threads, 224 entries
+            float v;
+            if (k < kPoseBasis) v = S.R[9 + k] - (((k % 9) % 4 == 0) ? 1.0f : 0.0f);
+            else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
+            else v = (k == kFeat - 1) ? 1.0f : 0.0f;
+            S.Phi[k] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     PHASE_MARK(4);
     // ---- P4 v_posed for the support columns: warp per Qk row, 2 x LDG.128 per lane
     if (din.vposed) {                 // dense regime: the vertex kernel already has them
@@ -768,7 +776,8 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
                   const float* __restrict__ vposed_ws, const float* __restrict__ verts_ws,
                   const float* __restrict__ parts5, const float* __restrict__ part, const int* __restrict__ pflag,
                   const FrameBox* __restrict__ box, const float* __restrict__ Wd, float* __restrict__ Phi,
-                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA, float* __restrict__ slot_tr) {
+                  float* __restrict__ PhiTc, float* __restrict__ At, int ldA, float* __restrict__ slot_tr,
+                  float* __restrict__ pose_cache, int* __restrict__ pose_valid) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
@@ -827,6 +836,15 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
             S.lbg1[i] = L.bg[(size_t)b * 2 * kParams + kParams + i];
         }
     }
+    // pose forward of THIS trial point: computed by the previous round's frame_step (for the dense kernels), restored here
+    // (loaded unconditionally, next to the validity flag instead of behind it: an invalid cache is simply overwritten
+    // by P1-P3 of the closure)
+    const bool pose_ready = pose_valid[b] != 0;
+    {
+        float* dst = &S.R[0];                         // R | J | Gam | g | A are contiguous (864 floats)
+        const float* src = pose_cache + (size_t)b * kPoseCacheFloats;
+        for (int i = t; i < kPoseCacheFloats; i += kResThreads) dst[i] = src[i];
+    }
     if (warp == 7) {
         // frame scalars of the penetration term (fitting.py:386-392): total of the sampled values -> loss, the
         // factor of the listed vertices' adjoint, and the <= 6 box-extreme vertices that carry the gradient through
@@ -883,6 +901,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     din.part = (din.factor != 0.f && S.nfl > 0) ? part + (size_t)slot * nparts * kPartFloats : nullptr;
     din.fl = S.fl;
     din.nfl = S.nfl;
+    din.pose_ready = pose_ready;
     resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
@@ -942,7 +961,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     chain_fwd_levels(S);
     PHASE_MARK(27);
     if (t < kJoints) {
-        float A[12];
+        float* A = &S.A[12 * t];
         make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], A);
 #pragma unroll
         for (int c = 0; c < 12; ++c) At[(size_t)(t * 12 + c) * ldA + slot] = A[c];
@@ -959,6 +978,13 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
             if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
             PhiTc[(size_t)slot * kFeatPad + k] = r;
         }
+    }
+    __syncthreads();
+    {   // park R | J | Gam | g | A for the next round's closure adjoint
+        const float* src = &S.R[0];
+        float* dst = pose_cache + (size_t)b * kPoseCacheFloats;
+        for (int i = t; i < kPoseCacheFloats; i += kResThreads) dst[i] = src[i];
+        if (t == 0) pose_valid[b] = 1;
     }
     PHASE_MARK(28);
 }
@@ -1045,6 +1071,18 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, 
     return MVS_OK;
 }
 
+// per-frame pose cache of frame_step; invalidated at the start of every run (the first round recomputes the pose)
+int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st) {
+    Workspace& w = ctx->ws;
+    if (!w.pose_cache) {
+        int rc;
+        if ((rc = dev_alloc(ctx, &w.pose_cache, (size_t)w.B * kPoseCacheFloats))) return rc;
+        if ((rc = dev_alloc(ctx, &w.pose_valid, (size_t)w.B))) return rc;
+    }
+    MVS_CUDA_OK(ctx, cudaMemsetAsync(w.pose_valid, 0, (size_t)w.B * sizeof(int), st));
+    return MVS_OK;
+}
+
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
     return resident_supported(ctx) && sdf_on && (ctx->m.N + 255) / 256 <= 64;      // frame_step's block list holds 64 entries
@@ -1069,7 +1107,7 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
                                            (const float*)w.joint_w, w.B, dm.N, (const float*)w.vposed, (const float*)w.verts,
                                            (const float*)w.sdf_parts5, (const float*)w.sdf_part, (const int*)w.sdf_pflag,
                                            reinterpret_cast<const FrameBox*>(w.sdf_box), (const float*)dm.Wd, w.Phi, w.PhiTc, w.At,
-                                           w.ldA, w.slot_tr)));
+                                           w.ldA, w.slot_tr, w.pose_cache, w.pose_valid)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -14,6 +14,7 @@
 // Reference quirks reproduced: voxel centres use dx = 2/(G-1) while grid_sample assumes 2/G;
 // the fitting code passes faces as [1,F,3] so the kernel loops over ONE triangle (sdf_all_faces = 0);
 // gradients flow through the sample coordinates and through the bounding-box centre / scale, not through phi.
+#include <cstdlib>
 #include "mvs_internal.cuh"
 #include "mvs_lbfgs_core.cuh"
 
@@ -761,9 +762,12 @@ int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
     const int B = w.B, N = m.N;
     const int nb = w.na_bound > 0 ? w.na_bound : B;    // host-side upper bound of the active-frame count
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
-    // 256-vertex blocks per CTA: as few as fit the active frames into ONE wave of resident CTAs (3 per SM); the results
-    // are emitted per block and do not depend on it
-    const int passes = sdf_passes_for(nb, nblocks, 3 * ctx->sm_count);
+    // 256-vertex blocks per CTA (1 at the tail, 2 in the bulk; see sdf_passes_for)
+    int passes = sdf_passes_for(nb, nblocks, 3 * ctx->sm_count);
+    {   // tuning knob (experiments only): MVS_SDF_PASSES=n forces n blocks per CTA
+        static const int forced = getenv("MVS_SDF_PASSES") ? atoi(getenv("MVS_SDF_PASSES")) : 0;
+        if (forced >= 1 && forced <= kSdfMaxPasses) passes = forced;
+    }
     const int nparts = (nblocks + passes - 1) / passes;
     int rc;
     if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;

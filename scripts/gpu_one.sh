@@ -1,12 +1,7 @@
 #!/bin/bash
+# other BASELINE.json configs as bench lines (parity-test cases; kept under profiles/ for the BASELINE.md table)
 mkdir -p gpurun_out
-for p in 1 2 3; do
-  MVS_SDF_PASSES=$p timeout 300 python bench.py --steps 3 --warmup 2 --cpu-seconds 1 > gpurun_out/k_p$p.txt 2>/dev/null
-  python - <<PY
-import json
-for line in open('gpurun_out/k_p$p.txt'):
-    if line.startswith('{'):
-        d=json.loads(line); r=d['roofline']
-        print('passes $p', round(d['ms_per_step'],2), d['rounds_per_step'], r['kernel_avg_us_instrumented_step'])
-PY
-done
+timeout 300 python bench.py --frames 64 --views 4 --sdf 0 --steps 5 --warmup 3 > gpurun_out/c_cfg3.txt 2>/dev/null; tail -c 300 gpurun_out/c_cfg3.txt
+timeout 300 python bench.py --frames 1 --views 8 --sdf 1 --steps 5 --warmup 3 > gpurun_out/c_cfg2.txt 2>/dev/null; tail -c 300 gpurun_out/c_cfg2.txt
+timeout 300 python bench.py --steps 3 --warmup 2 > gpurun_out/c_cfg4.txt 2>/dev/null; tail -c 300 gpurun_out/c_cfg4.txt
+timeout 600 python -m pytest tests/test_gpu_fit.py tests/test_gpu_resident.py -x -q -m gpu 2>&1 | tail -2

@@ -68,6 +68,133 @@ template <class T> MVS_HD void mat3_tvec(const T* A, const T* x, T* y) {      //
     for (int r = 0; r < 3; ++r) y[r] = A[r] * x[0] + A[3 + r] * x[1] + A[6 + r] * x[2];
 }
 
+// ---------------------------------------------------------------- VPoser rotation head (model/VPoser.py)
+// One joint of VPoser.decode(z, 'aa') after the last linear layer: the 6 outputs o[0..5] -> continuous rotation
+// representation -> rotation matrix (ContinousRotReprDecoder, VPoser.py:161-174) -> quaternion
+// (rotation_matrix_to_quaternion, VPoser.py:29-98, on the TRANSPOSED matrix, four branches, eps 1e-6) -> axis-angle
+// (quaternion_to_angle_axis, VPoser.py:101-156).  view(-1, 3, 2): a1 = (o0, o2, o4), a2 = (o1, o3, o5).
+MVS_HD float mvs_atan2(float y, float x) { return atan2f(y, x); }
+MVS_HD double mvs_atan2(double y, double x) { return atan2(y, x); }
+
+template <class T> struct Cont6dState {      // intermediates shared by the forward pass and its adjoint
+    T a1[3], a2[3], n1, b1[3], d, u[3], n2, b2[3], b3[3];
+    int branch;                               // which of the four quaternion formulas was selected
+    T qs[4], tsel, q[4], sin2, sn, k, tt;
+};
+
+template <class T> MVS_HD void cont6d_to_aa_fwd(const T* o, T* aa, Cont6dState<T>& S) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { S.a1[i] = o[2 * i]; S.a2[i] = o[2 * i + 1]; }
+    const T l1 = mvs_sqrt(S.a1[0] * S.a1[0] + S.a1[1] * S.a1[1] + S.a1[2] * S.a1[2]);
+    S.n1 = l1 > T(1e-12) ? l1 : T(1e-12);                     // F.normalize: x / max(|x|, eps)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.b1[i] = S.a1[i] / S.n1;
+    S.d = S.b1[0] * S.a2[0] + S.b1[1] * S.a2[1] + S.b1[2] * S.a2[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.u[i] = S.a2[i] - S.d * S.b1[i];
+    const T l2 = mvs_sqrt(S.u[0] * S.u[0] + S.u[1] * S.u[1] + S.u[2] * S.u[2]);
+    S.n2 = l2 > T(1e-12) ? l2 : T(1e-12);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.b2[i] = S.u[i] / S.n2;
+    S.b3[0] = S.b1[1] * S.b2[2] - S.b1[2] * S.b2[1];
+    S.b3[1] = S.b1[2] * S.b2[0] - S.b1[0] * S.b2[2];
+    S.b3[2] = S.b1[0] * S.b2[1] - S.b1[1] * S.b2[0];
+    // R = [b1 b2 b3] (columns); the quaternion routine works on rt = R^T, whose ROWS are b1, b2, b3
+    const T* r0 = S.b1; const T* r1 = S.b2; const T* r2 = S.b3;
+    const T m00 = r0[0], m11 = r1[1], m22 = r2[2];
+    const bool d2 = m22 < T(1e-6), d0_d1 = m00 > m11, d0_nd1 = m00 < -m11;
+    if (d2 && d0_d1) {
+        S.branch = 0; S.tsel = T(1) + m00 - m11 - m22;
+        S.qs[0] = r1[2] - r2[1]; S.qs[1] = S.tsel; S.qs[2] = r0[1] + r1[0]; S.qs[3] = r2[0] + r0[2];
+    } else if (d2) {
+        S.branch = 1; S.tsel = T(1) - m00 + m11 - m22;
+        S.qs[0] = r2[0] - r0[2]; S.qs[1] = r0[1] + r1[0]; S.qs[2] = S.tsel; S.qs[3] = r1[2] + r2[1];
+    } else if (d0_nd1) {
+        S.branch = 2; S.tsel = T(1) - m00 - m11 + m22;
+        S.qs[0] = r0[1] - r1[0]; S.qs[1] = r2[0] + r0[2]; S.qs[2] = r1[2] + r2[1]; S.qs[3] = S.tsel;
+    } else {
+        S.branch = 3; S.tsel = T(1) + m00 + m11 + m22;
+        S.qs[0] = S.tsel; S.qs[1] = r1[2] - r2[1]; S.qs[2] = r2[0] - r0[2]; S.qs[3] = r0[1] - r1[0];
+    }
+    const T isq = T(0.5) / mvs_sqrt(S.tsel);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) S.q[i] = S.qs[i] * isq;
+    S.sin2 = S.q[1] * S.q[1] + S.q[2] * S.q[2] + S.q[3] * S.q[3];
+    S.sn = mvs_sqrt(S.sin2);
+    const T cs = S.q[0];
+    S.tt = T(2) * (cs < T(0) ? mvs_atan2(-S.sn, -cs) : mvs_atan2(S.sn, cs));
+    S.k = S.sin2 > T(0) ? S.tt / S.sn : T(2);
+    aa[0] = S.q[1] * S.k; aa[1] = S.q[2] * S.k; aa[2] = S.q[3] * S.k;
+}
+
+// d_o[0..5] = (d aa / d o)^T d_aa for the state left by cont6d_to_aa_fwd (branch selections are locally constant)
+template <class T> MVS_HD void cont6d_to_aa_bwd(const Cont6dState<T>& S, const T* daa, T* d_o) {
+    T dq[4] = {T(0), daa[0] * S.k, daa[1] * S.k, daa[2] * S.k};
+    if (S.sin2 > T(0)) {
+        const T dk = daa[0] * S.q[1] + daa[1] * S.q[2] + daa[2] * S.q[3];
+        const T dtt = dk / S.sn;
+        T dsn = -dk * S.tt / S.sin2;
+        const T cs = S.q[0], r2 = S.sin2 + cs * cs;
+        dsn += T(2) * dtt * cs / r2;                          // tt = 2 atan2(+-sn, +-cs): same partials in both branches
+        dq[0] += -T(2) * dtt * S.sn / r2;
+        const T dsin2 = dsn / (T(2) * S.sn);
+        dq[1] += T(2) * S.q[1] * dsin2; dq[2] += T(2) * S.q[2] * dsin2; dq[3] += T(2) * S.q[3] * dsin2;
+    }
+    // q = 0.5 qs / sqrt(t)
+    const T isq = T(0.5) / mvs_sqrt(S.tsel);
+    T dqs[4];
+    T dt = T(0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dqs[i] = dq[i] * isq; dt += dq[i] * S.q[i]; }
+    dt = -T(0.5) * dt / S.tsel;
+    T dr0[3] = {T(0), T(0), T(0)}, dr1[3] = {T(0), T(0), T(0)}, dr2[3] = {T(0), T(0), T(0)};   // d rows of rt = d b1, b2, b3
+    if (S.branch == 0) {
+        dt += dqs[1];
+        dr1[2] += dqs[0]; dr2[1] -= dqs[0]; dr0[1] += dqs[2]; dr1[0] += dqs[2]; dr2[0] += dqs[3]; dr0[2] += dqs[3];
+        dr0[0] += dt; dr1[1] -= dt; dr2[2] -= dt;
+    } else if (S.branch == 1) {
+        dt += dqs[2];
+        dr2[0] += dqs[0]; dr0[2] -= dqs[0]; dr0[1] += dqs[1]; dr1[0] += dqs[1]; dr1[2] += dqs[3]; dr2[1] += dqs[3];
+        dr0[0] -= dt; dr1[1] += dt; dr2[2] -= dt;
+    } else if (S.branch == 2) {
+        dt += dqs[3];
+        dr0[1] += dqs[0]; dr1[0] -= dqs[0]; dr2[0] += dqs[1]; dr0[2] += dqs[1]; dr1[2] += dqs[2]; dr2[1] += dqs[2];
+        dr0[0] -= dt; dr1[1] -= dt; dr2[2] += dt;
+    } else {
+        dt += dqs[0];
+        dr1[2] += dqs[1]; dr2[1] -= dqs[1]; dr2[0] += dqs[2]; dr0[2] -= dqs[2]; dr0[1] += dqs[3]; dr1[0] -= dqs[3];
+        dr0[0] += dt; dr1[1] += dt; dr2[2] += dt;
+    }
+    T db1[3] = {dr0[0], dr0[1], dr0[2]}, db2[3] = {dr1[0], dr1[1], dr1[2]};
+    const T* db3 = dr2;
+    // b3 = b1 x b2
+    db1[0] += S.b2[1] * db3[2] - S.b2[2] * db3[1]; db1[1] += S.b2[2] * db3[0] - S.b2[0] * db3[2]; db1[2] += S.b2[0] * db3[1] - S.b2[1] * db3[0];
+    db2[0] += db3[1] * S.b1[2] - db3[2] * S.b1[1]; db2[1] += db3[2] * S.b1[0] - db3[0] * S.b1[2]; db2[2] += db3[0] * S.b1[1] - db3[1] * S.b1[0];
+    // b2 = u / n2
+    T du[3];
+    {
+        const T pb = S.b2[0] * db2[0] + S.b2[1] * db2[1] + S.b2[2] * db2[2];
+        const bool live = S.n2 > T(1e-12);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) du[i] = live ? (db2[i] - S.b2[i] * pb) / S.n2 : db2[i] / S.n2;
+    }
+    // u = a2 - d b1,  d = b1 . a2
+    T da2[3] = {du[0], du[1], du[2]};
+    const T dd = -(du[0] * S.b1[0] + du[1] * S.b1[1] + du[2] * S.b1[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { db1[i] += -S.d * du[i] + dd * S.a2[i]; da2[i] += dd * S.b1[i]; }
+    // b1 = a1 / n1
+    T da1[3];
+    {
+        const T pb = S.b1[0] * db1[0] + S.b1[1] * db1[1] + S.b1[2] * db1[2];
+        const bool live = S.n1 > T(1e-12);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) da1[i] = live ? (db1[i] - S.b1[i] * pb) / S.n1 : db1[i] / S.n1;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { d_o[2 * i] = da1[i]; d_o[2 * i + 1] = da2[i]; }
+}
+
 // ---------------------------------------------------------------- Rodrigues (lbs.py:269-300)
 template <class T> MVS_HD void rodrigues_fwd(const T* r, T* R) {
     const T e = T(1e-8);

@@ -192,6 +192,23 @@ def make_gmm(seed: int = 7, num_gaussians: int = 6, dim: int = 69) -> dict:
     return dict(means=means, covars=covars, weights=w / w.sum())
 
 
+def make_vposer(seed: int = 11, num_neurons: int = 512, latent: int = 32, num_joints: int = 23) -> dict:
+    """Synthetic VPoser DECODER weights with the shapes of the reference's module (model/VPoser.py:190-197:
+    bodyprior_dec_fc1 [512,32], bodyprior_dec_fc2 [512,512], bodyprior_dec_out [138,512]).  The trained snapshot the
+    reference ships is its data, not ours; a seeded network of the same architecture exercises the same arithmetic."""
+    rng = np.random.RandomState(seed)
+    lin = lambda o, i, gain: (rng.normal(0.0, gain / np.sqrt(i), size=(o, i)).astype(np.float32),
+                              rng.normal(0.0, 0.05, size=o).astype(np.float32))
+    w1, b1 = lin(num_neurons, latent, 1.2)
+    w2, b2 = lin(num_neurons, num_neurons, 1.3)
+    w3, b3 = lin(num_joints * 6, num_neurons, 1.0)
+    # bias the 6-D heads towards (1,0,0 | 0,1,0) so that decoded poses stay moderate rotations, as a trained prior's do
+    b3 = b3.reshape(num_joints, 3, 2)
+    b3[:, 0, 0] += 1.0
+    b3[:, 1, 1] += 1.0
+    return dict(fc1_w=w1, fc1_b=b1, fc2_w=w2, fc2_b=b2, out_w=w3, out_b=b3.reshape(-1).astype(np.float32))
+
+
 def gmm_buffers(gmm: dict):
     """(means[M,69], precisions[M,69,69], nll_weights[M]) as float64, following
     reference prior.py:142-160 (precision = inv(cov); nll_weights = w / ((2pi)^34.5 *

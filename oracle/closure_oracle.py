@@ -279,3 +279,28 @@ def closure_eval_batch(om, cfg, pri, cams_t, X, gt_uv, conf, joint_weights, back
     if "proj" in res:
         res["proj"] = np.ascontiguousarray(np.transpose(res["proj"], (1, 0, 2, 3)))   # [V,B,17,2]
     return res
+
+
+def closure_eval_vposer(om: OracleModel, cfg: LossConfig, pri: OraclePriors, cams_t: dict, x86: np.ndarray, z: np.ndarray,
+                        vposer_w: dict, gt_uv: np.ndarray, conf: np.ndarray, joint_weights: np.ndarray):
+    """fitting_func() with use_vposer=True for ONE frame (fitting.py:162-203): body_pose = VPoser.decode(z, 'aa');
+    the 69 pose entries of x86 are ignored.  Returns dict(loss, grad_* for betas / global_orient / transl / scale /
+    pose_embedding, joints, body_pose)."""
+    from . import vposer_oracle as VO
+    dt = om.dtype
+    x = torch.tensor(np.asarray(x86, dtype=np.float64), dtype=dt)
+    betas = x[0:10].clone().view(1, 10).requires_grad_(True)
+    go = x[10:13].clone().view(1, 3).requires_grad_(True)
+    tr = x[82:85].clone().view(1, 3).requires_grad_(True)
+    sc = x[85:86].clone().view(1, 1).requires_grad_(True)
+    emb = torch.tensor(np.asarray(z, dtype=np.float64), dtype=dt).view(1, 32).requires_grad_(True)
+    bp = VO.decode_aa(vposer_w, emb)
+    verts, joints, full_pose = smpl_forward(om, betas, go, bp, tr, sc)
+    total, proj = smplify_loss(om, cfg, pri, cams_t, verts, joints, full_pose, betas, bp, torch.tensor(gt_uv, dtype=dt),
+                               torch.tensor(conf, dtype=dt), torch.tensor(joint_weights, dtype=dt), pose_embedding=emb)
+    g = torch.autograd.grad(total, [betas, go, tr, sc, emb])
+    names = ("betas", "global_orient", "transl", "scale", "pose_embedding")
+    out = dict(loss=float(total), joints=joints.detach().numpy().copy(), body_pose=bp.detach().numpy()[0].copy())
+    for n, gg in zip(names, g):
+        out["g_" + n] = gg.reshape(-1).numpy().copy()
+    return out

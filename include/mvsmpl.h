@@ -71,6 +71,15 @@ int mvs_set_model(mvs_ctx* ctx, const mvs_model_desc* desc);
 int mvs_set_gmm_prior(mvs_ctx* ctx, int num_gaussians, const float* means, const float* precisions,
                       const float* nll_weights);
 
+/* VPoser decoder weights (code/model/VPoser.py:190-197: bodyprior_dec_fc1 [512,32], bodyprior_dec_fc2 [512,512],
+ * bodyprior_dec_out [138,512] and their biases; host arrays, row-major [out,in] as torch.nn.Linear stores them).
+ * With them a loss configuration may set use_vposer = 2: the pose is VPoser.decode(z, 'aa') (VPoser.py:218-232 and
+ * fitting.py:121-123) evaluated ON THE DEVICE inside the closure, z = the first 32 entries of the body_pose slot of the
+ * 86-vector (entries 32..68 of the slot are ignored and get zero gradient), the body prior is |z|^2 * body_pose_weight^2
+ * (fitting.py:327-329).  Frame-resident regime only (no SDF term, no vertices requested). */
+int mvs_set_vposer(mvs_ctx* ctx, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
+                   const float* out_w, const float* out_b);
+
 /* PerspectiveCamera list (code/camera.py:41-117, built in code/init.py:108-131): host arrays
  * R [V,3,3], t [V,3], f [V,2] (focal x,y), c [V,2] */
 int mvs_set_cameras(mvs_ctx* ctx, int num_views, const float* R, const float* t, const float* f, const float* c);
@@ -95,7 +104,8 @@ typedef struct {
     float rho;                     /* GMoF rho (utils.py:427-438) */
     int body_prior;                /* mvs_body_prior */
     int use_joints_conf;
-    int use_vposer;                /* body-pose prior terms are the caller's (|z|^2) ; angle guard disabled */
+    int use_vposer;                /* 1: body_pose comes decoded from the caller, body-pose prior terms are the caller's
+                                      (|z|^2), angle guard disabled; 2: decoded on the device (mvs_set_vposer) */
     int fix_shape;                 /* no shape prior (fitting.py:340) */
     int interpenetration;          /* SDF term on (needs faces) */
     int sdf_grid;                  /* 128 in the reference call (fitting.py:367-368) */

@@ -53,7 +53,7 @@ class LbfgsStats(ctypes.Structure):
 
 EXPORTS = (
     "mvs_version", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
-    "mvs_set_gmm_prior", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
+    "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
     "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
     "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor",
 )
@@ -91,6 +91,7 @@ def load() -> ctypes.CDLL:
     lib.mvs_forward.argtypes = [vp, vp, vp, vp, vp]
     lib.mvs_lbfgs_run.argtypes = [vp, vp, vp, ctypes.POINTER(LbfgsConfig), ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_lbfgs_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LbfgsConfig), ci, ctypes.POINTER(LbfgsStats), vp]
+    lib.mvs_set_vposer.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.mvs_fit.argtypes = [vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp, ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_fit_host.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp,
                                  ctypes.POINTER(LbfgsStats), vp]

@@ -109,6 +109,14 @@ class FittingContext:
         nllw = np.asarray(gmm["weights"] / ((2 * np.pi) ** (69 / 2.0) * (sqrdets / sqrdets.min())))
         self.set_gmm(means, prec, nllw.astype(np.float32))
 
+    def set_vposer(self, weights: dict):
+        """VPoser decoder weights (mvs_set_vposer): dict(fc1_w [512,32], fc1_b, fc2_w [512,512], fc2_b, out_w [138,512],
+        out_b) -- e.g. the bodyprior_dec_* tensors of a loaded VPoser, or synthetic.make_vposer().  Enables
+        use_vposer=2 loss configurations (pose decoded on the device from the latent code in the pose slot)."""
+        arrs = [_f32(weights[k]) for k in ("fc1_w", "fc1_b", "fc2_w", "fc2_b", "out_w", "out_b")]
+        assert arrs[0].shape == (512, 32) and arrs[2].shape == (512, 512) and arrs[4].shape == (138, 512)
+        _lib.check(self.h, self.lib.mvs_set_vposer(self.h, *[_ptr(a) for a in arrs]), "mvs_set_vposer")
+
     def set_cameras(self, R, t, f, c):
         R, t, f, c = _f32(R), _f32(t), _f32(f), _f32(c)
         self.V = R.shape[0]

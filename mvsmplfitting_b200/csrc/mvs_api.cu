@@ -74,6 +74,11 @@ int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out) {
     MVS_REQUIRE(ctx, c->body_prior != MVS_PRIOR_GMM || c->use_vposer || ctx->m.M > 0,
                 "mvs_set_loss_config: GMM prior selected but mvs_set_gmm_prior was not called");
     MVS_REQUIRE(ctx, !c->interpenetration || ctx->m.faces, "mvs_set_loss_config: interpenetration needs faces");
+    MVS_REQUIRE(ctx, c->use_vposer >= 0 && c->use_vposer <= 2, "mvs_set_loss_config: use_vposer must be 0, 1 or 2");
+    MVS_REQUIRE(ctx, c->use_vposer != 2 || ctx->m.vp_w1, "mvs_set_loss_config: use_vposer = 2 needs mvs_set_vposer");
+    MVS_REQUIRE(ctx, c->use_vposer != 2 || !(c->interpenetration && c->coll_loss_weight > 0.f),
+                "mvs_set_loss_config: the on-device VPoser decode runs in the frame-resident regime only (no SDF term); "
+                "use use_vposer = 1 with a host-side decoder for that combination");
     LossParams l{};
     l.data_weight = c->data_weight; l.body_pose_weight = c->body_pose_weight; l.shape_weight = c->shape_weight;
     l.bending_prior_weight = c->bending_prior_weight; l.coll_loss_weight = c->coll_loss_weight; l.rho = c->rho;
@@ -352,6 +357,31 @@ int mvs_set_gmm_prior(mvs_ctx* ctx, int M, const float* means, const float* prec
     if ((rc = dev_upload(ctx, &dm.gmm_means, means, (size_t)M * D))) return rc;
     if ((rc = dev_upload(ctx, &dm.gmm_prec, P.data(), P.size()))) return rc;
     if ((rc = dev_upload(ctx, &dm.gmm_lognllw, lw.data(), lw.size()))) return rc;
+    return MVS_OK;
+}
+
+int mvs_set_vposer(mvs_ctx* ctx, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
+                   const float* out_w, const float* out_b) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, fc1_w && fc1_b && fc2_w && fc2_b && out_w && out_b, "mvs_set_vposer: NULL array");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    DevModel& m = ctx->m;
+    constexpr int H = 512, Z = 32, O = 138;
+    auto up = [&](float** plain, float** transposed, const float* w, int no, int ni) -> int {
+        std::vector<float> t((size_t)no * ni);
+        for (int o = 0; o < no; ++o)
+            for (int i = 0; i < ni; ++i) t[(size_t)i * no + o] = w[(size_t)o * ni + i];
+        int rc = dev_upload(ctx, plain, w, (size_t)no * ni);
+        if (rc) return rc;
+        return dev_upload(ctx, transposed, t.data(), t.size());
+    };
+    int rc;
+    if ((rc = up(&m.vp_w1, &m.vp_w1t, fc1_w, H, Z))) return rc;
+    if ((rc = up(&m.vp_w2, &m.vp_w2t, fc2_w, H, H))) return rc;
+    if ((rc = up(&m.vp_w3, &m.vp_w3t, out_w, O, H))) return rc;
+    if ((rc = dev_upload(ctx, &m.vp_b1, fc1_b, H))) return rc;
+    if ((rc = dev_upload(ctx, &m.vp_b2, fc2_b, H))) return rc;
+    if ((rc = dev_upload(ctx, &m.vp_b3, out_b, O))) return rc;
     return MVS_OK;
 }
 

@@ -740,6 +740,9 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
     const bool have_grad = grad_dev != nullptr;
     if (!dense && !geometry_only && resident_closure_available(ctx))     // sparse regime: one fused launch
         return launch_closure_resident(ctx, x_dev, loss_dev, grad_dev, joints_dev, proj_dev, st);
+    if (lp.use_vposer == 2)
+        return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) is implemented in the "
+                                               "frame-resident closure only (no vertices, no SDF term, exec mode 0 or 2)");
     const int nv = dense ? m.N : m.nsup;
     const int* vlist = dense ? nullptr : m.sup;
     const Parents par = ctx->parents;

@@ -77,6 +77,9 @@ struct DevModel {
     float* gmm_means = nullptr;     // [M][69]
     float* gmm_prec = nullptr;      // [M][69][69] symmetrised
     float* gmm_lognllw = nullptr;   // [M]  log(nll_weights)
+    // VPoser decoder (mvs_set_vposer): [out][in] as uploaded and the transposes [in][out] (coalesced mat-vec both ways)
+    float *vp_w1 = nullptr, *vp_w2 = nullptr, *vp_w3 = nullptr, *vp_w1t = nullptr, *vp_w2t = nullptr, *vp_w3t = nullptr;
+    float *vp_b1 = nullptr, *vp_b2 = nullptr, *vp_b3 = nullptr;
 };
 
 // Per-batch workspace (slot-indexed: slot = position in the active-frame list)
@@ -252,7 +255,7 @@ int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, f
                             float* proj_dev, cudaStream_t st);
 bool resident_lbfgs_available(const mvs_ctx* ctx, int history);
 int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, const void* lp_tab_dev,
-                          int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st);
+                          const void* lp_tab_host, int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st);
 // dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu

@@ -195,7 +195,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.lp_tab, S.lp_tab_host, (size_t)nst * sizeof(LossParams), cudaMemcpyHostToDevice, st));
     if (!step_mode && resident_lbfgs_available(ctx, H)) {
         // sparse regime: every frame runs its whole stage inside one CTA (mvs_resident.cu): one launch, no rounds
-        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.lp_tab, nst, S.sc, last_grad_dev, st);
+        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.lp_tab, lps, nst, S.sc, last_grad_dev, st);
         if (rc) return rc;
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
         long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
@@ -208,6 +208,9 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         MVS_CUDA_OK(ctx, cudaGetLastError());
         return MVS_OK;
     }
+    if (ctx->loss.use_vposer == 2)
+        return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) runs in the frame-resident regime "
+                                               "only: mvs_lbfgs_run / mvs_fit without SDF term, exec mode 0 or 2");
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
     if (!step_mode && hybrid_available(ctx)) {

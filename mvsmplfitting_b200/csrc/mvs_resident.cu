@@ -76,6 +76,7 @@ struct ResidentModel {                    // device pointers + sizes, by value
     const int* supj_ptr; const int* supj_i; const float* supj_w;      // per joint: (support index, weight)
     int M; const float* gmm_means; const float* gmm_prec; const float* gmm_lognllw;
     const float* anchor; const float* anchor_w;     // sequence mode (mvs_set_anchor)
+    const float *vp_w1, *vp_w2, *vp_w3, *vp_w1t, *vp_w2t, *vp_w3t, *vp_b1, *vp_b2, *vp_b3;      // VPoser decoder
     Parents par;
     ChainSched cs;
 };
@@ -237,19 +238,126 @@ __device__ __forceinline__ void chain_bwd_levels(ResidentSmem& S) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// VPoser decoder on the device (use_vposer = 2): body_pose = VPoser.decode(z, 'aa') (model/VPoser.py:218-232,
+// fitting.py:121-123) and its adjoint.  z = S.x[kOffPose .. kOffPose + 32).  The scratch lives in dynamic shared memory
+// behind the curvature history (only kernels launched for this mode reserve it).
+constexpr int kVpH = 512, kVpZ = 32, kVpO = 138;
+struct VposerSmem {
+    float h1[kVpH], h2[kVpH], o6[kVpO + 6], th[72], dth[72], dh[kVpH], red[256];
+};
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// all threads; ends with a barrier.  Leaves W.th = decoded axis-angle pose (69) and zeroes W.dth.
+__device__ void vposer_decode(const ResidentSmem& S, const ResidentModel& m, VposerSmem& W) {
+    const int t = threadIdx.x;
+    const float* z = &S.x[kOffPose];
+#pragma unroll
+    for (int o = t; o < kVpH; o += kResThreads) {
+        float a = m.vp_b1[o];
+#pragma unroll 8
+        for (int i = 0; i < kVpZ; ++i) a = fmaf(__ldg(m.vp_w1t + (size_t)i * kVpH + o), z[i], a);
+        W.h1[o] = lrelu(a);
+    }
+    __syncthreads();
+    {
+        float a0 = m.vp_b2[t], a1 = m.vp_b2[t + kResThreads];
+#pragma unroll 8
+        for (int i = 0; i < kVpH; ++i) {
+            const float hi = W.h1[i];
+            a0 = fmaf(__ldg(m.vp_w2t + (size_t)i * kVpH + t), hi, a0);
+            a1 = fmaf(__ldg(m.vp_w2t + (size_t)i * kVpH + t + kResThreads), hi, a1);
+        }
+        W.h2[t] = lrelu(a0); W.h2[t + kResThreads] = lrelu(a1);
+    }
+    __syncthreads();
+    if (t < kVpO) {
+        float a = m.vp_b3[t];
+#pragma unroll 8
+        for (int i = 0; i < kVpH; ++i) a = fmaf(__ldg(m.vp_w3t + (size_t)i * kVpO + t), W.h2[i], a);
+        W.o6[t] = a;
+    }
+    if (t < 72) W.dth[t] = 0.f;
+    __syncthreads();
+    if (t < kJoints - 1) {
+        Cont6dState<float> st;
+        cont6d_to_aa_fwd(&W.o6[6 * t], &W.th[3 * t], st);
+    }
+    __syncthreads();
+}
+
+// all threads; adjoint of vposer_decode: W.dth (d loss / d decoded pose, 69) -> dz[32] in W.red[0..31].  Ends with a barrier.
+__device__ void vposer_decode_bwd(const ResidentModel& m, VposerSmem& W) {
+    const int t = threadIdx.x;
+    if (t < kJoints - 1) {
+        Cont6dState<float> st;
+        float aa[3], d6[6];
+        cont6d_to_aa_fwd(&W.o6[6 * t], aa, st);               // recompute the intermediates (cheaper than keeping 23 states)
+        cont6d_to_aa_bwd(st, &W.dth[3 * t], d6);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) W.red[6 * t + c] = d6[c];                     // d o6 (138 <= 256)
+    }
+    __syncthreads();
+    {   // d h2 = lrelu'(h2) .* (W3^T d o6)
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 6
+        for (int o = 0; o < kVpO; ++o) {
+            const float d = W.red[o];
+            a0 = fmaf(__ldg(m.vp_w3 + (size_t)o * kVpH + t), d, a0);
+            a1 = fmaf(__ldg(m.vp_w3 + (size_t)o * kVpH + t + kResThreads), d, a1);
+        }
+        W.dh[t] = (W.h2[t] > 0.f ? 1.f : 0.2f) * a0;
+        W.dh[t + kResThreads] = (W.h2[t + kResThreads] > 0.f ? 1.f : 0.2f) * a1;
+    }
+    __syncthreads();
+    {   // d h1 = lrelu'(h1) .* (W2^T d h2)   (result overwrites h2, no longer needed)
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < kVpH; ++o) {
+            const float d = W.dh[o];
+            a0 = fmaf(__ldg(m.vp_w2 + (size_t)o * kVpH + t), d, a0);
+            a1 = fmaf(__ldg(m.vp_w2 + (size_t)o * kVpH + t + kResThreads), d, a1);
+        }
+        W.h2[t] = (W.h1[t] > 0.f ? 1.f : 0.2f) * a0;
+        W.h2[t + kResThreads] = (W.h1[t + kResThreads] > 0.f ? 1.f : 0.2f) * a1;
+    }
+    __syncthreads();
+    {   // d z = W1^T d h1: 8 partial sums of 64 terms per latent entry
+        const int k = t & 31, part = t >> 5;
+        float a = 0.f;
+#pragma unroll 8
+        for (int o = part * 64; o < part * 64 + 64; ++o) a = fmaf(__ldg(m.vp_w1 + (size_t)o * kVpZ + k), W.h2[o], a);
+        W.dh[t] = a;
+    }
+    __syncthreads();
+    if (t < kVpZ) {
+        float a = 0.f;
+#pragma unroll
+        for (int part = 0; part < 8; ++part) a += W.dh[32 * part + t];
+        W.red[t] = a;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // One closure evaluation at S.x (already loaded).  Writes S.sc[2] = total loss and S.lg_new = gradient
 // (frozen segments zeroed).  All kResThreads threads must call it.
 __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const CamSet& cams, const LossParams& lp,
                                  const float* __restrict__ gt_uv, const float* __restrict__ conf,
                                  const float* __restrict__ joint_w, int B, int b, bool have_grad,
-                                 float* __restrict__ joints_out, float* __restrict__ proj_out, const DenseIn& din) {
+                                 float* __restrict__ joints_out, float* __restrict__ proj_out, const DenseIn& din,
+                                 VposerSmem* W = nullptr) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nsup = m.nsup, K = m.K, V = cams.num_views, ncol = 3 * nsup;
+    // use_vposer == 2: the body pose is decoded from the latent code in the pose slot (fitting.py:121-123)
+    const bool vp2 = (lp.use_vposer == 2) && W != nullptr;
+    if (vp2) vposer_decode(S, m, *W);
+    const float* theta = vp2 ? W->th : &S.x[kOffPose];          // the 69 body-pose entries the model sees
 
     // ---- P1 Rodrigues, rest joints (skipped when the caller restored them: the previous frame_step computed the pose
     //      forward of exactly this trial point for the dense kernels and parked it in the per-frame pose cache)
     if (!din.pose_ready) {
-        if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
+        if (t < kJoints) rodrigues_fwd(t == 0 ? &S.x[kOffOrient] : &theta[3 * (t - 1)], &S.R[9 * t]);
         else if (t >= 32 && t < 32 + 72) {
             const int jc = t - 32;
             float a = m.Jt[jc];
@@ -530,8 +638,9 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         PHASE_MARK(16);
         if (t < kJoints) {
             float dr[3] = {0.f, 0.f, 0.f};
-            rodrigues_bwd(&S.x[kOffOrient + 3 * t], &S.dR[9 * t], dr);
-            S.grad[kOffOrient + 3 * t] = dr[0]; S.grad[kOffOrient + 3 * t + 1] = dr[1]; S.grad[kOffOrient + 3 * t + 2] = dr[2];
+            rodrigues_bwd(t == 0 ? &S.x[kOffOrient] : &theta[3 * (t - 1)], &S.dR[9 * t], dr);
+            float* go = (vp2 && t > 0) ? &W->dth[3 * (t - 1)] : &S.grad[kOffOrient + 3 * t];     // decoded pose: adjoint goes on
+            go[0] = dr[0]; go[1] = dr[1]; go[2] = dr[2];
         } else if (t >= 32 && t < 32 + kBetas) {
             const int l = t - 32;
             float a = S.dPhi[kPoseBasis + l];
@@ -541,11 +650,11 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
     }
     // ---- P11 priors (fitting.py:327-350), all GMM components in parallel
     const float bpw = lp.body_pose_weight, bpw2 = bpw * bpw;
-    const float* theta = &S.x[kOffPose];
     const int M = m.M;
     if (!lp.use_vposer && lp.body_prior == MVS_PRIOR_GMM)
         for (int e = t; e < M * 69; e += kResThreads) S.gm_diff[e] = theta[e % 69] - m.gmm_means[e];
-    S.red[t] = (t < 69) ? theta[t] * theta[t] : 0.f;
+    if (vp2) S.red[t] = (t < kVpZ) ? S.x[kOffPose + t] * S.x[kOffPose + t] : 0.f;      // |z|^2 (fitting.py:327-329)
+    else S.red[t] = (t < 69) ? theta[t] * theta[t] : 0.f;
     __syncthreads();
     PHASE_MARK(17);
     if (!lp.use_vposer && lp.body_prior == MVS_PRIOR_GMM) {
@@ -571,6 +680,7 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
     __syncthreads();
     PHASE_MARK(19);
     float pprior = 0.f, l2extra = 0.f;
+    if (vp2) pprior = S.sc[1] * bpw2;
     if (!lp.use_vposer) {
         float gs = bpw2;
         int best_m = -1;
@@ -612,12 +722,18 @@ __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m, const 
         float gs = lp.bending_prior_weight;
         if (angle > 1e4f && !lp.use_vposer) { angle = 0.f; gs = 0.f; }
         if (have_grad && t == 0) {
+            float* gth = vp2 ? W->dth : &S.grad[kOffPose];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) S.grad[kOffPose + idx[i]] += 2.f * sg[i] * ev[i] * gs;
+            for (int i = 0; i < 4; ++i) gth[idx[i]] += 2.f * sg[i] * ev[i] * gs;
         }
     }
     __syncthreads();
     PHASE_MARK(21);
+    if (vp2 && have_grad) {               // d loss / d decoded pose -> d loss / d z, plus the prior's 2 bpw^2 z
+        vposer_decode_bwd(m, *W);
+        if (t < 69) S.grad[kOffPose + t] = (t < kVpZ) ? fmaf(2.f * bpw2, S.x[kOffPose + t], W->red[t]) : 0.f;
+        __syncthreads();
+    }
     float anchor_loss = 0.f;
     if (lp.anchor_on) {                                   // sequence mode: sum_i w_i (x_i - a_i)^2
         float dif = 0.f, wt = 0.f;
@@ -691,7 +807,8 @@ closure_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, const float
     resident_setup(S, m);
     for (int i = threadIdx.x; i < kParams; i += kResThreads) S.x[i] = x[(size_t)b * kParams + i];
     __syncthreads();
-    resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, have_grad != 0, joints_out, proj_out, DenseIn{});
+    VposerSmem* W = lp.use_vposer == 2 ? reinterpret_cast<VposerSmem*>(smem_raw + sizeof(ResidentSmem)) : nullptr;
+    resident_closure(S, m, cams, lp, gt_uv, conf, joint_w, B, b, have_grad != 0, joints_out, proj_out, DenseIn{}, W);
     if (threadIdx.x == 0) loss_out[b] = S.sc[2];
     if (have_grad)
         for (int i = threadIdx.x; i < kParams; i += kResThreads) grad_out[(size_t)b * kParams + i] = S.lg_new[i];
@@ -702,11 +819,12 @@ __global__ void __launch_bounds__(kResThreads, 2)
 lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ lp_tab, int nstages, LbfgsCfg cfg,
                       float* __restrict__ params, const float* __restrict__ gt_uv, const float* __restrict__ conf,
                       const float* __restrict__ joint_w, int B, int H, FrameScalars* __restrict__ sc_out,
-                      float* __restrict__ last_grad_out) {
+                      float* __restrict__ last_grad_out, int with_vposer) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     float* hy = reinterpret_cast<float*>(smem_raw + sizeof(ResidentSmem));
     float* hs = hy + (size_t)H * kParams;
+    VposerSmem* W = with_vposer ? reinterpret_cast<VposerSmem*>(hs + (size_t)H * kParams) : nullptr;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (b >= B) return;
     resident_setup(S, m);
@@ -733,7 +851,7 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
         for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
         __syncthreads();
         PHASE_MARK(1);
-        resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, DenseIn{});
+        resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, DenseIn{}, W);
         PHASE_MARK(23);
         if (warp == 0) {
             FrameScalars s = S.fs;
@@ -1005,6 +1123,8 @@ static ResidentModel make_resident_model(const mvs_ctx* ctx) {
     r.supj_ptr = m.supj_ptr; r.supj_i = m.supj_i; r.supj_w = m.supj_w;
     r.M = m.M; r.gmm_means = m.gmm_means; r.gmm_prec = m.gmm_prec; r.gmm_lognllw = m.gmm_lognllw;
     r.anchor = ctx->ws.anchor; r.anchor_w = ctx->ws.anchor_w;
+    r.vp_w1 = m.vp_w1; r.vp_w2 = m.vp_w2; r.vp_w3 = m.vp_w3; r.vp_w1t = m.vp_w1t; r.vp_w2t = m.vp_w2t; r.vp_w3t = m.vp_w3t;
+    r.vp_b1 = m.vp_b1; r.vp_b2 = m.vp_b2; r.vp_b3 = m.vp_b3;
     r.par = ctx->parents;
     // level schedule of the tree (parents[j] < j is checked in mvs_set_model)
     int depth[kJoints];
@@ -1033,9 +1153,10 @@ bool resident_closure_available(const mvs_ctx* ctx) { return resident_supported(
 int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
                             float* proj_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
-    const size_t smem = sizeof(ResidentSmem);
+    const size_t smem = sizeof(ResidentSmem) + (ctx->loss.use_vposer == 2 ? sizeof(VposerSmem) : 0);
     if (!ctx->attr_done_res) {
-        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(closure_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(closure_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(ResidentSmem) + sizeof(VposerSmem))));
         ctx->attr_done_res = true;
     }
     MVS_LAUNCH(ctx, KID_RESIDENT_CLOSURE, st,
@@ -1053,11 +1174,14 @@ bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int 
 }
 bool resident_lbfgs_available(const mvs_ctx* ctx, int H) { return resident_lbfgs_available_for(ctx, ctx->loss, H); }
 
-int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, int H, const void* lp_tab_dev, int nstages,
-                          void* sc_out, float* last_grad_dev, cudaStream_t st) {
+int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, int H, const void* lp_tab_dev,
+                          const void* lp_tab_host, int nstages, void* sc_out, float* last_grad_dev, cudaStream_t st) {
     Workspace& w = ctx->ws;
     const LbfgsCfg& cfg = *static_cast<const LbfgsCfg*>(cfg_ptr);
-    const size_t smem = sizeof(ResidentSmem) + (size_t)2 * H * kParams * sizeof(float);
+    const LossParams* lph = static_cast<const LossParams*>(lp_tab_host);
+    int with_vposer = 0;
+    for (int i = 0; i < nstages; ++i) with_vposer |= (lph[i].use_vposer == 2);
+    const size_t smem = sizeof(ResidentSmem) + (size_t)2 * H * kParams * sizeof(float) + (with_vposer ? sizeof(VposerSmem) : 0);
     if (ctx->attr_res_lbfgs_smem < (int)smem) {
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(lbfgs_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attr_res_lbfgs_smem = (int)smem;
@@ -1066,7 +1190,7 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, 
                lbfgs_resident_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams,
                                                                      static_cast<const LossParams*>(lp_tab_dev), nstages, cfg,
                                                                      params_dev, w.gt_uv, w.conf, w.joint_w, w.B, H,
-                                                                     static_cast<FrameScalars*>(sc_out), last_grad_dev));
+                                                                     static_cast<FrameScalars*>(sc_out), last_grad_dev, with_vposer));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }
@@ -1085,7 +1209,7 @@ int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st) {
 
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
-    return resident_supported(ctx) && sdf_on && (ctx->m.N + 255) / 256 <= 64;      // frame_step's block list holds 64 entries
+    return resident_supported(ctx) && sdf_on && lp.use_vposer != 2 && (ctx->m.N + 255) / 256 <= 64;     // frame_step's block list holds 64 entries
 }
 bool hybrid_available(const mvs_ctx* ctx) { return hybrid_available_for(ctx, ctx->loss); }
 

@@ -166,10 +166,23 @@ class FittingClosure:
         self.ctx.set_keypoints(gt, conf, jw)
         self._gmm_of = None
         self.last = None
+        # VPoser: when the module exposes the reference's decoder layers (model/VPoser.py:190-197) the decode runs on
+        # the device inside the closure (mvs_set_vposer / use_vposer = 2); any other module is decoded by PyTorch upstream
+        self.vposer_native = False
+        if self.use_vposer and all(hasattr(vposer, n) for n in ("bodyprior_dec_fc1", "bodyprior_dec_fc2", "bodyprior_dec_out")) \
+                and pose_embedding is not None and tuple(pose_embedding.shape[-1:]) == (32,) \
+                and not bool(getattr(loss, "interpenetration", False)):
+            g = lambda layer, what: getattr(getattr(vposer, layer), what).detach().float().cpu().numpy()
+            self.ctx.set_vposer(dict(fc1_w=g("bodyprior_dec_fc1", "weight"), fc1_b=g("bodyprior_dec_fc1", "bias"),
+                                     fc2_w=g("bodyprior_dec_fc2", "weight"), fc2_b=g("bodyprior_dec_fc2", "bias"),
+                                     out_w=g("bodyprior_dec_out", "weight"), out_b=g("bodyprior_dec_out", "bias")))
+            self.vposer_native = True
 
     # -- parameter plumbing: the caller's nn.Parameters are the single source of truth
     def _named(self):
-        return {k: getattr(self.body_model, k) for k in PARAM_SLICES if hasattr(self.body_model, k)}
+        # under VPoser the pose slot belongs to the decoder (decoded pose or latent code), not to body_model.body_pose
+        return {k: getattr(self.body_model, k) for k in PARAM_SLICES
+                if hasattr(self.body_model, k) and not (self.use_vposer and k == "body_pose")}
 
     def gather_params(self, body_pose=None) -> torch.Tensor:
         B, dev = self.ctx.B, self.ctx.device
@@ -180,6 +193,9 @@ class FittingClosure:
             x[:, a:e] = p.detach().reshape(B, e - a)
         if body_pose is not None:
             x[:, 13:82] = body_pose.detach().reshape(B, 69)
+        elif self.vposer_native:
+            x[:, 13:82] = 0.0
+            x[:, 13:45] = self.pose_embedding.detach().reshape(B, 32)       # latent code in the pose slot (use_vposer = 2)
         return x.contiguous()
 
     @torch.no_grad()
@@ -190,6 +206,10 @@ class FittingClosure:
                 p.copy_(x[:, a:e].reshape(p.shape))
                 if grad is not None:
                     p.grad = grad[:, a:e].reshape(p.shape).clone()
+        if self.vposer_native and self.pose_embedding.requires_grad:
+            self.pose_embedding.copy_(x[:, 13:45].reshape(self.pose_embedding.shape))
+            if grad is not None:
+                self.pose_embedding.grad = grad[:, 13:45].reshape(self.pose_embedding.shape).clone()
 
     def sync_loss_config(self):
         rg = {k: bool(p.requires_grad) for k, p in self._named().items()}
@@ -198,6 +218,8 @@ class FittingClosure:
         for k in PARAM_SLICES:
             rg.setdefault(k, False)
         cfg, kind = loss_config_from(self.loss, rg, self.use_vposer)
+        if self.vposer_native:
+            cfg.use_vposer = 2
         if kind == "gmm" and not self.use_vposer and self._gmm_of is not self.loss.body_pose_prior:
             pr = self.loss.body_pose_prior
             self.ctx.set_gmm(pr.means.detach().cpu().numpy(), pr.precisions.detach().cpu().numpy(),
@@ -211,13 +233,13 @@ class FittingClosure:
             self.optimizer.zero_grad()
         B = self.ctx.B
         body_pose = None
-        if self.use_vposer:
+        if self.use_vposer and not self.vposer_native:
             body_pose = self.vposer.decode(self.pose_embedding, output_type="aa").view(B, -1)
         self.sync_loss_config()
         x = self.gather_params(body_pose=body_pose)
         out = self.ctx.closure(x, want_grad=backward)
         total = out["loss"].sum()
-        if self.use_vposer:
+        if self.use_vposer and not self.vposer_native:
             bpw = float(self.loss.body_pose_weight)
             total = total + (self.pose_embedding.detach() ** 2).sum() * bpw ** 2      # fitting.py:327-329
         if backward:
@@ -226,7 +248,10 @@ class FittingClosure:
                 if p.requires_grad:
                     a, e = PARAM_SLICES[k]
                     p.grad = g[:, a:e].reshape(p.shape).clone()
-            if self.use_vposer and self.pose_embedding.requires_grad:
+            if self.vposer_native:
+                if self.pose_embedding.requires_grad:
+                    self.pose_embedding.grad = g[:, 13:45].reshape(self.pose_embedding.shape).clone()
+            elif self.use_vposer and self.pose_embedding.requires_grad:
                 body_pose.backward(gradient=g[:, 13:82].reshape(body_pose.shape))
                 with torch.no_grad():
                     self.pose_embedding.grad += 2.0 * float(self.loss.body_pose_weight) ** 2 * self.pose_embedding
@@ -272,8 +297,10 @@ class FittingMonitor(object):
         where every frame moves to its next stage as soon as ITS current stage stops (same per-frame schedule and bits
         as the loop, no waiting for the slowest frame at a stage boundary).  Returns the last stage's final loss."""
         from .optimizers.lbfgs_ls import LBFGS
-        if not (isinstance(optimizer, LBFGS) and isinstance(closure, FittingClosure) and not closure.use_vposer):
-            raise NotImplementedError("run_fitting_stages needs this package's LBFGS and closure without VPoser")
+        if not (isinstance(optimizer, LBFGS) and isinstance(closure, FittingClosure) and
+                (not closure.use_vposer or closure.vposer_native)):
+            raise NotImplementedError("run_fitting_stages needs this package's LBFGS and closure (VPoser: the reference's "
+                                      "decoder layers, so that the decode runs on the device)")
         cfgs = []
         for w in opt_weights:
             closure.loss.reset_loss_weights(w)
@@ -291,7 +318,8 @@ class FittingMonitor(object):
         """fitting.py:71-142.  With this package's LBFGS + closure the whole loop (all outer steps, all
         frames) runs on the GPU in one call; any other optimiser is driven step by step from the host."""
         from .optimizers.lbfgs_ls import LBFGS
-        if isinstance(optimizer, LBFGS) and isinstance(closure, FittingClosure) and not closure.use_vposer:
+        if isinstance(optimizer, LBFGS) and isinstance(closure, FittingClosure) and \
+                (not closure.use_vposer or closure.vposer_native):
             x = closure.gather_params()
             closure.sync_loss_config()
             cfg = optimizer.lbfgs_config(closure.ctx, max_outer=self.maxiters, ftol=self.ftol, gtol=self.gtol)

@@ -1,0 +1,151 @@
+"""GPU: VPoser.decode on the device (use_vposer = 2) -- closure loss / gradients / joints against fixtures written by the
+unmodified reference fitting closure with use_vposer=True (oracle/make_golden_vposer.py), and the optimiser on top."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mvsmplfitting_b200 import synthetic as S
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vposer_s11.npz")
+
+
+def _ctx(model, c, B):
+    from mvsmplfitting_b200.context import FittingContext
+    ctx = FittingContext(0)
+    ctx.set_model(model)
+    ctx.set_vposer(S.make_vposer(11))
+    ctx.set_cameras(c["cam_R"], c["cam_t"], c["cam_f"], c["cam_c"])
+    ctx.set_batch(B)
+    ctx.set_keypoints(c["gt_uv"], c["conf"], c["joint_weights"])
+    return ctx
+
+
+def _x_with_latent(c):
+    X = c["X"].copy()
+    X[:, 13:82] = 0.0
+    X[:, 13:45] = c["closure_Z"]                  # latent code in the first 32 entries of the pose slot
+    return X
+
+
+@pytest.mark.parametrize("stage", [3, 0])
+def test_closure_with_device_vposer_matches_reference(stage, syn_model):
+    c = np.load(GOLD)
+    ctx = _ctx(syn_model, c, 2)
+    dw, bpw, sw, bend = [float(v) for v in c["w%d" % stage]]
+    ctx.set_loss(body_prior="l2", use_vposer=2, data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend)
+    out = ctx.closure(torch.tensor(_x_with_latent(c), device="cuda"), want_joints=True)
+    loss, g, joints = out["loss"].cpu().numpy(), out["grad"].cpu().numpy(), out["joints"].cpu().numpy()
+    for b in range(2):
+        pre = "s%d_b%d_f32_" % (stage, b)
+        assert abs(loss[b] - float(c[pre + "loss"])) / abs(float(c[pre + "loss"])) < 1e-4
+        assert G.relmax(joints[b], c[pre + "joints"]) < 1e-4
+        for name, (a, e) in (("betas", (0, 10)), ("global_orient", (10, 13)), ("transl", (82, 85)), ("scale", (85, 86)),
+                             ("pose_embedding", (13, 45))):
+            assert G.relmax(g[b, a:e], c[pre + "g_" + name]) < 2e-4, (stage, b, name)
+        assert (g[b, 45:82] == 0).all()
+    ctx.close()
+
+
+def test_lbfgs_in_latent_space(syn_model):
+    c = np.load(GOLD)
+    ctx = _ctx(syn_model, c, 2)
+    dw, bpw, sw, bend = [float(v) for v in c["w3"]]
+    ctx.set_loss(body_prior="l2", use_vposer=2, data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend)
+    X0 = _x_with_latent(c)
+    x = torch.tensor(X0, device="cuda")
+    l0 = ctx.closure(x, want_grad=False)["loss"].cpu().numpy()
+    n0 = ctx.launch_count()
+    final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=5))
+    assert ctx.launch_count() - n0 <= 4                      # frame-resident: the whole stage is one launch
+    l1 = ctx.closure(x, want_grad=False)["loss"].cpu().numpy()
+    assert (l1 < l0).all() and st["frames_nan"] == 0 and st["frame_iterations"] > 10
+    xn = x.cpu().numpy()
+    assert np.array_equal(xn[:, 45:82], X0[:, 45:82])        # only the latent code moves inside the pose slot
+    assert not np.array_equal(xn[:, 13:45], X0[:, 13:45])
+    ctx.close()
+
+
+def test_device_vposer_guards(syn_model):
+    from mvsmplfitting_b200.context import FittingContext
+    from mvsmplfitting_b200._lib import MvsError
+    c = np.load(GOLD)
+    ctx = FittingContext(0)
+    ctx.set_model(syn_model)
+    ctx.set_cameras(c["cam_R"], c["cam_t"], c["cam_f"], c["cam_c"])
+    ctx.set_batch(2)
+    with pytest.raises(MvsError):
+        ctx.set_loss(body_prior="l2", use_vposer=2)          # no decoder weights yet
+    ctx.set_vposer(S.make_vposer(11))
+    with pytest.raises(MvsError):
+        ctx.set_loss(body_prior="l2", use_vposer=2, interpenetration=True, coll_loss_weight=10.0)
+    ctx.close()
+
+
+class _Decoder(torch.nn.Module):
+    """a VPoser-shaped module: the reference's decoder layer names + decode(z, 'aa') (restated in oracle/vposer_oracle.py)"""
+
+    def __init__(self, w, native_names=True):
+        super().__init__()
+        pre = "bodyprior_dec_" if native_names else "dec_"
+        self._pre = pre
+        for name, (o, i) in (("fc1", (512, 32)), ("fc2", (512, 512)), ("out", (138, 512))):
+            lin = torch.nn.Linear(i, o)
+            lin.weight.data = torch.tensor(w[name + "_w"])
+            lin.bias.data = torch.tensor(w[name + "_b"])
+            setattr(self, pre + name, lin)
+
+    def decode(self, z, output_type="aa"):
+        from oracle import vposer_oracle as VO
+        g = lambda n: getattr(self, self._pre + n)
+        h = torch.nn.functional.leaky_relu(g("fc1")(z), 0.2)
+        h = torch.nn.functional.leaky_relu(g("fc2")(h), 0.2)
+        R = VO.cont6d_to_matrot(g("out")(h))
+        return VO.quaternion_to_angle_axis(VO.matrot_to_quaternion(R)).reshape(z.shape[0], 1, -1, 3)
+
+
+def test_dropin_closure_native_decode_equals_host_decode(syn_model, syn_gmm, tmp_path):
+    """FittingMonitor.create_fitting_closure(use_vposer=True): with the reference's decoder layers the decode runs on the
+    device; with any other module PyTorch decodes upstream.  Same loss and gradients; the fused run_fitting works."""
+    from mvsmplfitting_b200 import fitting, prior
+    from mvsmplfitting_b200.optimizers import optim_factory
+    from tests.test_gpu_dropin import build_scene
+    c = np.load(GOLD)
+    cams = dict(R=c["cam_R"], t=c["cam_t"], f=c["cam_f"], c=c["cam_c"])
+    w = S.make_vposer(11)
+    res = {}
+    for native in (True, False):
+        model, cam_list, _ = build_scene(syn_model, syn_gmm, tmp_path, cams, 1, "smpllsp", "l2")
+        x = S.unpack_params(c["X"][:1])
+        model.reset_params(**{k: torch.tensor(v) for k, v in x.items()})
+        vp = _Decoder(w, native_names=native).cuda()
+        emb = torch.tensor(c["closure_Z"][:1], device="cuda").requires_grad_(True)
+        loss = fitting.create_loss("smplify", rho=100.0, use_joints_conf=True, body_pose_prior=prior.create_prior("l2"),
+                                   shape_prior=prior.create_prior("l2"), angle_prior=prior.create_prior("angle"),
+                                   interpenetration=False).to("cuda")
+        dw, bpw, sw, bend = [float(v) for v in c["w3"]]
+        loss.reset_loss_weights(dict(data_weight=torch.tensor(dw), body_pose_weight=torch.tensor(bpw),
+                                     shape_weight=torch.tensor(sw), bending_prior_weight=torch.tensor(bend)))
+        model.body_pose.requires_grad = False
+        params = [p for p in model.parameters() if p.requires_grad] + [emb]
+        opt, cg = optim_factory.create_optimizer(params, optim_type="lbfgsls", lr=1.0, maxiters=30)
+        mon = fitting.FittingMonitor(maxiters=3, ftol=1e-9, gtol=1e-9)
+        closure = mon.create_fitting_closure(
+            opt, model, camera=cam_list, gt_joints=torch.tensor(c["gt_uv"][:, :1]).cuda(),
+            joints_conf=[torch.tensor(c["conf"][v, :1]).cuda() for v in range(4)],
+            joint_weights=torch.tensor(c["joint_weights"]).unsqueeze(0).cuda(), loss=loss, create_graph=cg, use_vposer=True,
+            vposer=vp, pose_embedding=emb, return_verts=True, return_full_pose=True, use_3d=False)
+        assert closure.vposer_native == native
+        total = float(closure())
+        res[native] = (total, emb.grad.detach().cpu().numpy().copy(), model.betas.grad.detach().cpu().numpy().copy())
+        if native:
+            assert abs(total - float(c["s3_b0_f32_loss"])) / float(c["s3_b0_f32_loss"]) < 1e-4
+            assert G.relmax(res[True][1].reshape(-1), c["s3_b0_f32_g_pose_embedding"]) < 2e-4
+            z0 = emb.detach().clone()
+            final = mon.run_fitting(opt, closure, params, model, use_vposer=True, pose_embedding=emb, vposer=vp)
+            assert final <= total and not torch.equal(emb.detach(), z0)
+    assert abs(res[True][0] - res[False][0]) / res[False][0] < 1e-4
+    assert G.relmax(res[True][1], res[False][1]) < 2e-4 and G.relmax(res[True][2], res[False][2]) < 2e-4

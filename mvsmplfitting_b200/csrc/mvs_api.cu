@@ -76,9 +76,6 @@ int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out) {
     MVS_REQUIRE(ctx, !c->interpenetration || ctx->m.faces, "mvs_set_loss_config: interpenetration needs faces");
     MVS_REQUIRE(ctx, c->use_vposer >= 0 && c->use_vposer <= 2, "mvs_set_loss_config: use_vposer must be 0, 1 or 2");
     MVS_REQUIRE(ctx, c->use_vposer != 2 || ctx->m.vp_w1, "mvs_set_loss_config: use_vposer = 2 needs mvs_set_vposer");
-    MVS_REQUIRE(ctx, c->use_vposer != 2 || !(c->interpenetration && c->coll_loss_weight > 0.f),
-                "mvs_set_loss_config: the on-device VPoser decode runs in the frame-resident regime only (no SDF term); "
-                "use use_vposer = 1 with a host-side decoder for that combination");
     LossParams l{};
     l.data_weight = c->data_weight; l.body_pose_weight = c->body_pose_weight; l.shape_weight = c->shape_weight;
     l.bending_prior_weight = c->bending_prior_weight; l.coll_loss_weight = c->coll_loss_weight; l.rho = c->rho;

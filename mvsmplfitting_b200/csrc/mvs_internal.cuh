@@ -269,6 +269,7 @@ int tc_check_error(mvs_ctx* ctx);
 int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
                       cudaStream_t st);
 int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st);                 // mvs_resident.cu
+int launch_frame_fwd_dense(mvs_ctx* ctx, const float* x_dev, const void* lbfgs_state, int nstages, cudaStream_t st);   // mvs_resident.cu
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
 int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion

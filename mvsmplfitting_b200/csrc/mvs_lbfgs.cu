@@ -222,7 +222,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         long long rounds = 0;
         int na_host = B;
         static const bool trace_na = getenv("MVS_TRACE_NA") != nullptr;       // debugging aid: active-list size per chunk
-        rc = launch_frame_fwd(ctx, S.x_eval, st);
+        rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, nst, st);
         if (rc) return rc;
         if ((rc = frame_step_begin_run(ctx, st))) return rc;
         // The host only needs the active count to know when to stop, so chunk k+1 is enqueued BEFORE the count of
@@ -244,7 +244,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
             }
             // compaction changes slot -> frame, so the surviving frames' Phi / transforms are rebuilt for their new slots
             MVS_LAUNCH(ctx, KID_LBFGS_COMPACT, st, lbfgs_compact_kernel<<<1, 1024, 0, st>>>(S, B, w.fidx, w.na));
-            if ((rc = launch_frame_fwd(ctx, S.x_eval, st))) return rc;
+            if ((rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, nst, st))) return rc;
             const int cur = (int)(chunk_idx & 1);
             MVS_CUDA_OK(ctx, cudaMemcpyAsync(&na_slots[cur], w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
             MVS_CUDA_OK(ctx, cudaEventRecord(S.na_event[cur], st));

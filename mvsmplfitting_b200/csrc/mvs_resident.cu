@@ -881,6 +881,77 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
     if (t == 0) sc_out[b] = S.fs;
 }
 
+// Pose forward of the trial point in S.x for the dense kernels of the next round: feature row (fp32 and TF32), skinning
+// transforms (frame fastest), translation -- all addressed by the slot -- and the per-frame pose cache.  With vp2 the
+// body pose is decoded from the latent code first.  All threads; no trailing barrier.
+__device__ __forceinline__ void next_pose_forward(ResidentSmem& S, const ResidentModel& m, VposerSmem* W, bool vp2, int slot, int b,
+                                                  float* __restrict__ Phi, float* __restrict__ PhiTc, float* __restrict__ At,
+                                                  int ldA, float* __restrict__ slot_tr, float* __restrict__ pose_cache,
+                                                  int* __restrict__ pose_valid) {
+    const int t = threadIdx.x;
+    if (vp2) vposer_decode(S, m, *W);
+    const float* theta = vp2 ? W->th : &S.x[kOffPose];
+    if (t < kJoints) rodrigues_fwd(t == 0 ? &S.x[kOffOrient] : &theta[3 * (t - 1)], &S.R[9 * t]);
+    else if (t >= 32 && t < 32 + 72) {
+        const int jc = t - 32;
+        float a = m.Jt[jc];
+#pragma unroll
+        for (int l = 0; l < kBetas; ++l) a = fmaf(m.JS[jc * kBetas + l], S.x[kOffBetas + l], a);
+        S.J[jc] = a;
+    }
+    __syncthreads();
+    PHASE_MARK(26);
+    chain_fwd_levels(S);
+    PHASE_MARK(27);
+    if (t < kJoints) {
+        float* A = &S.A[12 * t];
+        make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], A);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) At[(size_t)(t * 12 + c) * ldA + slot] = A[c];
+        if (t < 3) slot_tr[4 * slot + t] = S.x[kOffTransl + t];
+    } else if (t >= 32) {
+        const int k = t - 32;
+        float v;
+        if (k < kPoseBasis) v = S.R[9 + k] - (((k % 9) % 4 == 0) ? 1.0f : 0.0f);
+        else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
+        else v = (k == kFeat - 1) ? 1.0f : 0.0f;
+        Phi[(size_t)slot * kFeatPad + k] = v;
+        if (PhiTc) {
+            float r = 0.f;
+            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
+            PhiTc[(size_t)slot * kFeatPad + k] = r;
+        }
+    }
+    __syncthreads();
+    if (pose_cache) {   // park R | J | Gam | g | A for the next round's closure adjoint
+        const float* src = &S.R[0];
+        float* dst = pose_cache + (size_t)b * kPoseCacheFloats;
+        for (int i = t; i < kPoseCacheFloats; i += kResThreads) dst[i] = src[i];
+        if (t == 0) pose_valid[b] = 1;
+    }
+}
+
+// The same for every active slot at the start of a run and after a compaction (slots changed): the VPoser-capable
+// counterpart of frame_fwd_kernel (mvs_closure.cu), which only knows axis-angle poses.
+__global__ void __launch_bounds__(kResThreads, 2)
+frame_fwd_resident_kernel(ResidentModel m, const LossParams* __restrict__ lp_tab, const FrameScalars* __restrict__ sc,
+                          const float* __restrict__ x, const int* __restrict__ fidx, const int* __restrict__ na_ptr,
+                          float* __restrict__ Phi, float* __restrict__ PhiTc, float* __restrict__ At, int ldA,
+                          float* __restrict__ slot_tr) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
+    VposerSmem* W = reinterpret_cast<VposerSmem*>(smem_raw + sizeof(ResidentSmem));
+    const int slot = blockIdx.x;
+    if (slot >= *na_ptr) return;
+    const int b = fidx[slot], t = threadIdx.x;
+    resident_setup(S, m);
+    for (int i = t; i < kParams; i += kResThreads) S.x[i] = x[(size_t)b * kParams + i];
+    const bool vp2 = lp_tab[sc[b].stage].use_vposer == 2;
+    __syncthreads();
+    next_pose_forward(S, m, W, vp2, slot, b, Phi, PhiTc, At, ldA, slot_tr, nullptr, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------ dense regime
 // One round of the dense regime for one frame: consumes the dense vertices + the SDF gradient list of this
 // frame's trial point, finishes the closure (keypoint term, adjoint, priors), advances the frame's L-BFGS state
@@ -895,7 +966,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
                   const float* __restrict__ parts5, const float* __restrict__ part, const int* __restrict__ pflag,
                   const FrameBox* __restrict__ box, const float* __restrict__ Wd, float* __restrict__ Phi,
                   float* __restrict__ PhiTc, float* __restrict__ At, int ldA, float* __restrict__ slot_tr,
-                  float* __restrict__ pose_cache, int* __restrict__ pose_valid) {
+                  float* __restrict__ pose_cache, int* __restrict__ pose_valid, int with_vposer) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
@@ -918,6 +989,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     // shared memory ~5 us.
     float* hy = reinterpret_cast<float*>(smem_raw + sizeof(ResidentSmem));
     float* hs = hy + (size_t)L.H * kParams;
+    VposerSmem* W = with_vposer ? reinterpret_cast<VposerSmem*>(hs + (size_t)L.H * kParams) : nullptr;
     {
         const int hl = fs0.hist_len;
         const float* gy = L.hist_y + (size_t)b * L.H * kParams;
@@ -1020,7 +1092,7 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     din.fl = S.fl;
     din.nfl = S.nfl;
     din.pose_ready = pose_ready;
-    resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din);
+    resident_closure(S, m, cams, S.lp, gt_uv, conf, joint_w, B, b, true, nullptr, nullptr, din, W);
     for (int i = t; i < kParams; i += kResThreads) L.g_eval[(size_t)b * kParams + i] = S.lg_new[i];
     asm volatile("cp.async.wait_all;");
     __syncthreads();
@@ -1066,43 +1138,9 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
     __syncthreads();
     PHASE_MARK(25);
-    if (t < kJoints) rodrigues_fwd(&S.x[kOffOrient + 3 * t], &S.R[9 * t]);
-    else if (t >= 32 && t < 32 + 72) {
-        const int jc = t - 32;
-        float a = m.Jt[jc];
-#pragma unroll
-        for (int l = 0; l < kBetas; ++l) a = fmaf(m.JS[jc * kBetas + l], S.x[kOffBetas + l], a);
-        S.J[jc] = a;
-    }
-    __syncthreads();
-    PHASE_MARK(26);
-    chain_fwd_levels(S);
-    PHASE_MARK(27);
-    if (t < kJoints) {
-        float* A = &S.A[12 * t];
-        make_skin_transform(&S.Gam[9 * t], &S.g[3 * t], &S.J[3 * t], A);
-#pragma unroll
-        for (int c = 0; c < 12; ++c) At[(size_t)(t * 12 + c) * ldA + slot] = A[c];
-        if (t < 3) slot_tr[4 * slot + t] = S.x[kOffTransl + t];
-    } else if (t >= 32) {
-        const int k = t - 32;
-        float v;
-        if (k < kPoseBasis) v = S.R[9 + k] - (((k % 9) % 4 == 0) ? 1.0f : 0.0f);
-        else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
-        else v = (k == kFeat - 1) ? 1.0f : 0.0f;
-        Phi[(size_t)slot * kFeatPad + k] = v;
-        if (PhiTc) {
-            float r = 0.f;
-            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
-            PhiTc[(size_t)slot * kFeatPad + k] = r;
-        }
-    }
-    __syncthreads();
-    {   // park R | J | Gam | g | A for the next round's closure adjoint
-        const float* src = &S.R[0];
-        float* dst = pose_cache + (size_t)b * kPoseCacheFloats;
-        for (int i = t; i < kPoseCacheFloats; i += kResThreads) dst[i] = src[i];
-        if (t == 0) pose_valid[b] = 1;
+    {
+        const bool vp2n = W != nullptr && lp_tab[S.fs.stage].use_vposer == 2;     // the stage the NEXT evaluation belongs to
+        next_pose_forward(S, m, W, vp2n, slot, b, Phi, PhiTc, At, ldA, slot_tr, pose_cache, pose_valid);
     }
     PHASE_MARK(28);
 }
@@ -1209,9 +1247,15 @@ int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st) {
 
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
-    return resident_supported(ctx) && sdf_on && lp.use_vposer != 2 && (ctx->m.N + 255) / 256 <= 64;     // frame_step's block list holds 64 entries
+    return resident_supported(ctx) && sdf_on && (ctx->m.N + 255) / 256 <= 64;      // frame_step's block list holds 64 entries
 }
 bool hybrid_available(const mvs_ctx* ctx) { return hybrid_available_for(ctx, ctx->loss); }
+
+static int stages_with_vposer(const LbfgsState& L, int nstages) {
+    int v = 0;
+    for (int i = 0; i < nstages; ++i) v |= (L.lp_tab_host[i].use_vposer == 2);
+    return v;
+}
 
 int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
                       cudaStream_t st) {
@@ -1219,9 +1263,14 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
     const DevModel& dm = ctx->m;
     const LbfgsState& L = *static_cast<const LbfgsState*>(lbfgs_state);
     const LbfgsCfg& cfg = *static_cast<const LbfgsCfg*>(lbfgs_cfg);
-    const size_t smem = sizeof(ResidentSmem) + (size_t)2 * L.H * kParams * sizeof(float);
+    const int with_vposer = stages_with_vposer(L, nstages);
+    const size_t base_smem = sizeof(ResidentSmem) + (size_t)2 * L.H * kParams * sizeof(float);
+    const size_t smem = base_smem + (with_vposer ? sizeof(VposerSmem) : 0);
     if (!ctx->attr_done_step) {
-        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(frame_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(frame_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(base_smem + sizeof(VposerSmem))));
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(frame_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(ResidentSmem) + sizeof(VposerSmem))));
         ctx->attr_done_step = true;
     }
     MVS_LAUNCH(ctx, KID_FRAME_STEP, st,
@@ -1231,7 +1280,24 @@ int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, 
                                            (const float*)w.joint_w, w.B, dm.N, (const float*)w.vposed, (const float*)w.verts,
                                            (const float*)w.sdf_parts5, (const float*)w.sdf_part, (const int*)w.sdf_pflag,
                                            reinterpret_cast<const FrameBox*>(w.sdf_box), (const float*)dm.Wd, w.Phi, w.PhiTc, w.At,
-                                           w.ldA, w.slot_tr, w.pose_cache, w.pose_valid)));
+                                           w.ldA, w.slot_tr, w.pose_cache, w.pose_valid, with_vposer)));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
+// slot-indexed pose forward of every active frame (run start, after a compaction); the axis-angle-only frame_fwd_kernel
+// serves runs without a device-decoded VPoser stage
+int launch_frame_fwd_dense(mvs_ctx* ctx, const float* x_dev, const void* lbfgs_state, int nstages, cudaStream_t st) {
+    const LbfgsState& L = *static_cast<const LbfgsState*>(lbfgs_state);
+    if (!stages_with_vposer(L, nstages)) return launch_frame_fwd(ctx, x_dev, st);
+    Workspace& w = ctx->ws;
+    if (!ctx->attr_done_step) {
+        MVS_CUDA_OK(ctx, cudaFuncSetAttribute(frame_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(ResidentSmem) + sizeof(VposerSmem))));
+    }
+    MVS_LAUNCH(ctx, KID_FRAME_FWD, st,
+               frame_fwd_resident_kernel<<<w.na_bound > 0 ? w.na_bound : w.B, kResThreads, sizeof(ResidentSmem) + sizeof(VposerSmem), st>>>(
+                   make_resident_model(ctx), L.lp_tab, L.sc, x_dev, w.fidx, w.na, w.Phi, w.PhiTc, w.At, w.ldA, w.slot_tr));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -170,8 +170,7 @@ class FittingClosure:
         # the device inside the closure (mvs_set_vposer / use_vposer = 2); any other module is decoded by PyTorch upstream
         self.vposer_native = False
         if self.use_vposer and all(hasattr(vposer, n) for n in ("bodyprior_dec_fc1", "bodyprior_dec_fc2", "bodyprior_dec_out")) \
-                and pose_embedding is not None and tuple(pose_embedding.shape[-1:]) == (32,) \
-                and not bool(getattr(loss, "interpenetration", False)):
+                and pose_embedding is not None and tuple(pose_embedding.shape[-1:]) == (32,):
             g = lambda layer, what: getattr(getattr(vposer, layer), what).detach().float().cpu().numpy()
             self.ctx.set_vposer(dict(fc1_w=g("bodyprior_dec_fc1", "weight"), fc1_b=g("bodyprior_dec_fc1", "bias"),
                                      fc2_w=g("bodyprior_dec_fc2", "weight"), fc2_b=g("bodyprior_dec_fc2", "bias"),

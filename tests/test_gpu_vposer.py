@@ -80,8 +80,46 @@ def test_device_vposer_guards(syn_model):
     with pytest.raises(MvsError):
         ctx.set_loss(body_prior="l2", use_vposer=2)          # no decoder weights yet
     ctx.set_vposer(S.make_vposer(11))
+    ctx.set_keypoints(c["gt_uv"], c["conf"], c["joint_weights"])
+    ctx.set_loss(body_prior="l2", use_vposer=2)
+    with pytest.raises(MvsError):                            # vertices requested -> batched chain, which has no decoder
+        ctx.closure(torch.tensor(_x_with_latent(c), device="cuda"), want_verts=True)
+    ctx.set_exec_mode(1)
     with pytest.raises(MvsError):
-        ctx.set_loss(body_prior="l2", use_vposer=2, interpenetration=True, coll_loss_weight=10.0)
+        ctx.closure(torch.tensor(_x_with_latent(c), device="cuda"))
+    ctx.close()
+
+
+def test_dense_regime_with_device_vposer_matches_oracle(syn_model):
+    """SDF term + latent-space pose: the dense rounds decode the pose for the vertex kernels and back-propagate through the
+    decoder in frame_step.  Pinned like the axis-angle dense regime: loss at entry and first search direction."""
+    from oracle import closure_oracle as O
+    c = np.load(GOLD)
+    ctx = _ctx(syn_model, c, 2)
+    dw, bpw, sw, bend = [float(v) for v in c["w3"]]
+    cw = 1000.0
+    ctx.set_loss(body_prior="l2", use_vposer=2, interpenetration=True, coll_loss_weight=cw, sdf_grid=128, data_weight=dw,
+                 body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend)
+    X0 = _x_with_latent(c)
+    x = torch.tensor(X0, device="cuda")
+    n0 = ctx.launch_count()
+    final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=1, max_iter=1))
+    assert ctx.launch_count() - n0 > 8                       # dense rounds
+    om = O.OracleModel.from_numpy(syn_model, dtype=torch.float32)
+    cfg = O.LossConfig(data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend, use_vposer=True,
+                       interpenetration=True, coll_loss_weight=cw, sdf_grid=128)
+    cams = dict(R=c["cam_R"], t=c["cam_t"], f=c["cam_f"], c=c["cam_c"])
+    w = S.make_vposer(11)
+    d = x.cpu().numpy().astype(np.float64) - X0
+    for b in range(2):
+        r = O.closure_eval_vposer(om, cfg, O.OraclePriors(kind="l2"), O.cams_to_torch(cams, torch.float32), X0[b],
+                                  c["closure_Z"][b], w, c["gt_uv"][:, b], c["conf"][:, b], c["joint_weights"])
+        assert abs(float(final[b]) - r["loss"]) / abs(r["loss"]) < 2e-4
+        g = np.zeros(86)
+        g[0:10], g[10:13], g[13:45], g[82:85], g[85:86] = r["g_betas"], r["g_global_orient"], r["g_pose_embedding"], r["g_transl"], r["g_scale"]
+        cos = -(d[b] * g).sum() / (np.linalg.norm(d[b]) * np.linalg.norm(g))
+        assert cos > 1 - 1e-6, (b, cos)
+        assert (d[b, 45:82] == 0).all()
     ctx.close()
 
 

@@ -208,9 +208,9 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         MVS_CUDA_OK(ctx, cudaGetLastError());
         return MVS_OK;
     }
-    if (ctx->loss.use_vposer == 2)
-        return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) runs in the frame-resident regime "
-                                               "only: mvs_lbfgs_run / mvs_fit without SDF term, exec mode 0 or 2");
+    if (ctx->loss.use_vposer == 2 && (step_mode || !hybrid_available(ctx)))
+        return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) is not implemented in the batched "
+                                               "reference chain (exec mode 1, mvs_lbfgs_step): use use_vposer = 1 there");
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
     if (!step_mode && hybrid_available(ctx)) {

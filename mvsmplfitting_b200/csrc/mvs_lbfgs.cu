@@ -7,11 +7,16 @@
 //   utils/fitting.py:71-142        FittingMonitor.run_fitting (NaN/Inf guard, ftol, gtol)
 //
 // The reference runs this loop in Python with a blocking float(closure()) per evaluation
-// (lbfgs_ls.py:251,281).  Here no scalar leaves the GPU: every "round" evaluates the closure
-// at each active frame's trial point, then lbfgs_advance_kernel (one warp per frame) consumes
-// (f, g), walks the frame's state machine up to its next closure request and writes the next
-// trial point; finished frames are compacted out of the active list.  The host only polls the
-// active count every few rounds.
+// (lbfgs_ls.py:251,281).  Here no scalar leaves the GPU.  run_stage picks one of three execution regimes per
+// group of stages:
+//   frame-resident   one CTA per frame runs closure + state machine for ALL stages of the group inside ONE launch
+//                    (mvs_resident.cu: lbfgs_resident_kernel)
+//   dense rounds     SDF term on: per round posedirs_gemm_tc -> skin -> sdf_fused -> frame_step; finished frames are
+//                    compacted out every 8 rounds; the host reads the active count one chunk late (the next chunk is
+//                    already enqueued) and only uses it to size grids and to stop
+//   batched chain    the reference SIMT path (launch_closure + lbfgs_advance_kernel + lbfgs_compact_kernel), also
+//                    what mvs_lbfgs_step (one LBFGS.step per call, state persistent in the context) uses
+// run_fit hands consecutive stages of the same regime to one run in which every frame changes stage on its own.
 //
 // Arithmetic mirrors the reference's types: dot products, step lengths and directional
 // derivatives are fp32 (0-dim fp32 tensors there), losses are Python floats there and are

@@ -2,14 +2,17 @@
 //   sdf/sdf/csrc/sdf_cuda_kernel.cu:242-335  brute-force voxel SDF kernel (+ sdf_cuda.cpp:14-28 binding)
 //   code/utils/fitting.py:352-393            bounding box, normalisation, grid_sample, squared weighted sum
 //
-// Two entry points:
-//   sdf_grid_launch   the reference's op: phi[B,G,G,G] for normalised vertices (kept for callers that want the
-//                     grid; triangles staged through shared memory instead of re-read per voxel)
-//   launch_sdf_terms  the term as the closure needs it, FUSED: phi is never materialised.  The loss only reads
-//                     phi at the <= 8 voxels around each vertex, and phi(voxel) is a pure function of the voxel
-//                     index, so those voxels are evaluated on the fly while sampling.  That removes the
-//                     128^3 x 4 B = 8.4 MB grid write + gather per frame (2.1 GB per 256-frame closure) and
-//                     G^3 / (8 N) = 38x of the voxel work, with bit-identical sampled values.
+// Three entry points:
+//   sdf_grid_launch    the reference's op: phi[B,G,G,G] for normalised vertices (kept for callers that want the
+//                      grid; triangles staged through shared memory instead of re-read per voxel)
+//   launch_sdf_terms   the term for the batched reference chain (bbox / sample / finalize kernels): phi is never
+//                      materialised.  The loss only reads phi at the <= 8 voxels around each vertex, and phi(voxel)
+//                      is a pure function of the voxel index, so those voxels are evaluated on the fly while
+//                      sampling.  That removes the 128^3 x 4 B = 8.4 MB grid write + gather per frame (2.1 GB per
+//                      256-frame closure) and G^3 / (8 N) = 38x of the voxel work, with identical sampled values.
+//   launch_sdf_fused   the dense regime's kernel: the same sampling, preceded by conservative geometric tests
+//                      (chunk / cell / voxel against the cone and the plane of triangle 0), followed by the adjoint
+//                      of the few vertices that see a non-zero value, all in one launch (see sdf_fused_kernel)
 //
 // Reference quirks reproduced: voxel centres use dx = 2/(G-1) while grid_sample assumes 2/G;
 // the fitting code passes faces as [1,F,3] so the kernel loops over ONE triangle (sdf_all_faces = 0);

@@ -5,15 +5,18 @@
 // is the one dense contraction of the path: M = frames in flight, N = 20670, K = 207.  It is skinny in M
 // (<= a few hundred frames), so it is bound by streaming the 17 MB of posedirs from L2/HBM once per 128-frame
 // tile, not by tensor throughput; the kernel is therefore organised around keeping the A operand (the frames'
-// pose features, 112 KB) RESIDENT in shared memory for the CTA's whole life while posedirs tiles stream through a
-// TMA ring, and around fusing everything else of the vertex forward into the epilogue:
+// pose features, 112 KB; only the live 8-row groups are fetched when few frames are active) RESIDENT in shared memory
+// for the CTA's whole life while posedirs tiles stream through a TMA ring:
 //
-//   warp 0   TMA producer   A once (7 boxes 128x32), then B boxes 96x32 through a 6-stage mbarrier ring
+//   warp 0   TMA producer   A once (7 boxes 128x32, or 8-row boxes), then B boxes 96x32 through a 6-stage mbarrier ring
 //   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::tf32  M=128 N=96 K=8, fp32 accumulators in TMEM,
 //                           two accumulator buffers (2 x 96 columns) so tile i+1 runs under the epilogue of tile i
 //   warp 2   TMEM alloc / dealloc
-//   warps 4-7  epilogue     tcgen05.ld (lane = frame, 96 columns = 32 vertices x 3), + v_template + shapedirs.betas
-//                           in fp32, linear blend skinning (lbs.py:207-220), 8-byte stores of v_posed and verts
+//   warps 4-7  epilogue     tcgen05.ld (lane = frame, 96 columns = 32 vertices x 3), pose offsets stored TRANSPOSED
+//                           (frame fastest) so that a warp's 32 frames form one 128-byte line per column
+//
+// The rest of the vertex forward (template + shape blend shapes in fp32, linear blend skinning, box partials) is
+// skin_kernel / skin_small_kernel below: fused into this epilogue it ran in 128 threads and cost 10x the contraction.
 //
 // Precision: operands are pre-rounded to TF32 (cvt.rna), accumulation is fp32.  Pose offsets are a small
 // correction (<= a few % of a vertex coordinate), so their 2^-11 relative rounding stays < 1e-5 relative on the

@@ -480,6 +480,13 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
         pd = pn[0] * (tri[0] + 1.f) + pn[1] * (tri[1] + 1.f) + pn[2] * (tri[2] + 1.f);
         pm = 2e-3f * sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);      // conservative: |w| <= 2 sqrt 3, fp32 rounding
     }
+    // vertex-level early-out: the 8 voxel centres a vertex at `loc` can touch lie within +-vhalf of (loc + 1) G/(G-1) on
+    // every axis, so each plane function varies by at most vhalf * |n|_1 over them
+    const float vgs = (float)G / (float)(G - 1), vhalf = 2.02f / (float)(G - 1) + 1e-5f;
+    float vpad[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) vpad[q] = vhalf * (fabsf(cn[q][0]) + fabsf(cn[q][1]) + fabsf(cn[q][2]));
+    const float vpadp = vhalf * (fabsf(pn[0]) + fabsf(pn[1]) + fabsf(pn[2]));
     // ---- sampling: block (pidx * passes + pass) of 256 vertices per pass, one vertex per thread and pass.  Sums,
     //      vertex lists and adjoint partials are emitted PER BLOCK, so the arithmetic of a frame does not depend on
     //      how many blocks this launch gave to one CTA (i.e. not on how many other frames are still active): frames
@@ -547,70 +554,85 @@ sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vpos
                 i0[c] = (int)fl;
                 w1[c] = ix - fl;
             }
-            float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
-            // voxel centres of the 2 x 2 x 2 cell and, per cone plane, the per-axis parts of <centre + 1, normal>:
-            // a corner's three plane distances are then two adds each
-            float cx[2], cy[2], cz[2], px[3][2], py[3][2], pz[3][2];
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                const int ii = min(max(i0[0] + o, 0), G - 1), jj = min(max(i0[1] + o, 0), G - 1), kk = min(max(i0[2] + o, 0), G - 1);
-                if (tab) { cx[o] = ctab[ii]; cy[o] = ctab[jj]; cz[o] = ctab[kk]; }
-                else { float c3[3]; voxel_centre(ii, jj, kk, G, c3); cx[o] = c3[0]; cy[o] = c3[1]; cz[o] = c3[2]; }
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    px[q][o] = (cx[o] + 1.f) * cn[q][0]; py[q][o] = (cy[o] + 1.f) * cn[q][1]; pz[q][o] = (cz[o] + 1.f) * cn[q][2];
-                }
-            }
-            // whole-cell test first: the extreme plane distances over the 8 corners are sums of per-axis extremes; if
-            // one plane has every corner outside (negative) and another every corner on its positive side, no corner
-            // can be inside the cone -- true for almost every vertex -- and the corner loop is skipped
-            float qx[2], qy[2], qz[2];
-#pragma unroll
-            for (int o = 0; o < 2; ++o) { qx[o] = (cx[o] + 1.f) * pn[0]; qy[o] = (cy[o] + 1.f) * pn[1]; qz[o] = (cz[o] + 1.f) * pn[2]; }
-            bool cell_out = false;
+            bool vout = false;                             // no voxel this vertex touches can have phi != 0
             if (cull) {
-                // plane side of the whole cell
-                const float smaxp = fmaxf(qx[0], qx[1]) + fmaxf(qy[0], qy[1]) + fmaxf(qz[0], qz[1]) - pd;
-                const float sminp = fminf(qx[0], qx[1]) + fminf(qy[0], qy[1]) + fminf(qz[0], qz[1]) - pd;
-                if ((pd > pm && smaxp < -pm) || (pd < -pm && sminp > pm)) cell_out = true;
+                const float wc[3] = {(loc[0] + 1.f) * vgs, (loc[1] + 1.f) * vgs, (loc[2] + 1.f) * vgs};
                 bool any_neg = false, any_pos = false;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    const float smax = fmaxf(px[q][0], px[q][1]) + fmaxf(py[q][0], py[q][1]) + fmaxf(pz[q][0], pz[q][1]);
-                    const float smin = fminf(px[q][0], px[q][1]) + fminf(py[q][0], py[q][1]) + fminf(pz[q][0], pz[q][1]);
-                    any_neg = any_neg || (smax < -cm[q]);
-                    any_pos = any_pos || (smin > cm[q]);
+                    const float sq = cn[q][0] * wc[0] + cn[q][1] * wc[1] + cn[q][2] * wc[2];
+                    any_neg = any_neg || (sq + vpad[q] < -cm[q]);
+                    any_pos = any_pos || (sq - vpad[q] > cm[q]);
                 }
-                cell_out = cell_out || (any_neg && any_pos);
+                const float sp = pn[0] * wc[0] + pn[1] * wc[1] + pn[2] * wc[2] - pd;
+                vout = (any_neg && any_pos) || (pd > pm && sp + vpadp < -pm) || (pd < -pm && sp - vpadp > pm);
             }
+            float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
+            if (!vout) {
+                // voxel centres of the 2 x 2 x 2 cell and, per cone plane, the per-axis parts of <centre + 1, normal>:
+                // a corner's three plane distances are then two adds each
+                float cx[2], cy[2], cz[2], px[3][2], py[3][2], pz[3][2];
 #pragma unroll
-            for (int corner = 0; corner < 8; ++corner) {
-                if (cell_out) break;
-                const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
-                const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
-                if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
-                if (cull) {
-                    // phi != 0 needs the ray from the voxel centre to (-1,-1,-1) to cross triangle 0, i.e. the centre
-                    // inside the cone the triangle spans from that corner: on the same side of its three planes.
-                    // Conservative margin (|centre + 1| <= 2 sqrt 3): only voxels safely outside are skipped, every
-                    // other one is decided exactly by ray_hits.
-                    const float s1 = px[0][ox] + py[0][oy] + pz[0][oz];
-                    const float s2 = px[1][ox] + py[1][oy] + pz[1][oz];
-                    const float s3 = px[2][ox] + py[2][oy] + pz[2][oz];
-                    const bool neg = (s1 < -cm[0]) || (s2 < -cm[1]) || (s3 < -cm[2]);
-                    const bool pos = (s1 > cm[0]) || (s2 > cm[1]) || (s3 > cm[2]);
-                    if (neg && pos) continue;
-                    const float sp = qx[ox] + qy[oy] + qz[oz] - pd;
-                    if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
+                for (int o = 0; o < 2; ++o) {
+                    const int ii = min(max(i0[0] + o, 0), G - 1), jj = min(max(i0[1] + o, 0), G - 1), kk = min(max(i0[2] + o, 0), G - 1);
+                    if (tab) { cx[o] = ctab[ii]; cy[o] = ctab[jj]; cz[o] = ctab[kk]; }
+                    else { float c3[3]; voxel_centre(ii, jj, kk, G, c3); cx[o] = c3[0]; cy[o] = c3[1]; cz[o] = c3[2]; }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        px[q][o] = (cx[o] + 1.f) * cn[q][0]; py[q][o] = (cy[o] + 1.f) * cn[q][1]; pz[q][o] = (cz[o] + 1.f) * cn[q][2];
+                    }
                 }
-                const float cc[3] = {cx[ox], cy[oy], cz[oz]};
-                const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
-                if (p == 0.f) continue;
-                const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
-                val += p * wx * wy * wz;
-                dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
-                dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
-                dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
+                // whole-cell test first: the extreme plane distances over the 8 corners are sums of per-axis extremes; if
+                // one plane has every corner outside (negative) and another every corner on its positive side, no corner
+                // can be inside the cone -- true for almost every vertex -- and the corner loop is skipped
+                float qx[2], qy[2], qz[2];
+#pragma unroll
+                for (int o = 0; o < 2; ++o) { qx[o] = (cx[o] + 1.f) * pn[0]; qy[o] = (cy[o] + 1.f) * pn[1]; qz[o] = (cz[o] + 1.f) * pn[2]; }
+                bool cell_out = false;
+                if (cull) {
+                    // plane side of the whole cell
+                    const float smaxp = fmaxf(qx[0], qx[1]) + fmaxf(qy[0], qy[1]) + fmaxf(qz[0], qz[1]) - pd;
+                    const float sminp = fminf(qx[0], qx[1]) + fminf(qy[0], qy[1]) + fminf(qz[0], qz[1]) - pd;
+                    if ((pd > pm && smaxp < -pm) || (pd < -pm && sminp > pm)) cell_out = true;
+                    bool any_neg = false, any_pos = false;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const float smax = fmaxf(px[q][0], px[q][1]) + fmaxf(py[q][0], py[q][1]) + fmaxf(pz[q][0], pz[q][1]);
+                        const float smin = fminf(px[q][0], px[q][1]) + fminf(py[q][0], py[q][1]) + fminf(pz[q][0], pz[q][1]);
+                        any_neg = any_neg || (smax < -cm[q]);
+                        any_pos = any_pos || (smin > cm[q]);
+                    }
+                    cell_out = cell_out || (any_neg && any_pos);
+                }
+#pragma unroll
+                for (int corner = 0; corner < 8; ++corner) {
+                    if (cell_out) break;
+                    const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
+                    const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
+                    if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+                    if (cull) {
+                        // phi != 0 needs the ray from the voxel centre to (-1,-1,-1) to cross triangle 0, i.e. the centre
+                        // inside the cone the triangle spans from that corner: on the same side of its three planes.
+                        // Conservative margin (|centre + 1| <= 2 sqrt 3): only voxels safely outside are skipped, every
+                        // other one is decided exactly by ray_hits.
+                        const float s1 = px[0][ox] + py[0][oy] + pz[0][oz];
+                        const float s2 = px[1][ox] + py[1][oy] + pz[1][oz];
+                        const float s3 = px[2][ox] + py[2][oy] + pz[2][oz];
+                        const bool neg = (s1 < -cm[0]) || (s2 < -cm[1]) || (s3 < -cm[2]);
+                        const bool pos = (s1 > cm[0]) || (s2 > cm[1]) || (s3 > cm[2]);
+                        if (neg && pos) continue;
+                        const float sp = qx[ox] + qy[oy] + qz[oz] - pd;
+                        if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
+                    }
+                    const float cc[3] = {cx[ox], cy[oy], cz[oz]};
+                    const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
+                    if (p == 0.f) continue;
+                    const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
+                    val += p * wx * wy * wz;
+                    dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
+                    dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
+                    dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
+                }
             }
             float gdl = 0.f;
 #pragma unroll

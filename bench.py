@@ -392,9 +392,10 @@ def run_reference(args):
     import multiprocessing as mp
     import warnings
     warnings.filterwarnings("ignore")
-    # one process per PHYSICAL core (hyper-thread pairs share the FP units and the L2; with 64 logical CPUs busy a
-    # frame takes 3.3x its single-process time and a step would not fit the few-minutes budget)
-    cores = max(1, min((os.cpu_count() or 2) // 2, args.ref_workers))
+    # One process per 4 logical CPUs (32 on the 2 x 32-core / 128-thread host of the B200 boxes).  More does not help:
+    # measured on that host 64 processes give 76-94 frame-iterations/s in total (a frame then takes 80 s instead of 19 s
+    # alone -- the autograd graph of the oracle is memory-bound), and a step would not fit the few-minutes budget.
+    cores = max(1, min((os.cpu_count() or 4) // 4, args.ref_workers))
     V, sdf = args.views, bool(args.sdf)
     from oracle import sdf_oracle
     sdf_oracle.build()
@@ -434,7 +435,7 @@ def main():
     ap.add_argument("--sdf", type=int, default=1)
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--cpu-seconds", type=float, default=30.0)
-    ap.add_argument("--ref-workers", type=int, default=64)
+    ap.add_argument("--ref-workers", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

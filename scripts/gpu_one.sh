@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_vposer.py tests/test_gpu_dropin.py -x -q -m gpu > gpurun_out/k_vposer.txt 2>&1; tail -25 gpurun_out/k_vposer.txt
+nproc; lscpu | grep -E "Model name|Socket|Core|Thread" | head -5
+timeout 900 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/m_ref.txt 2> gpurun_out/m_ref.err; tail -c 700 gpurun_out/m_ref.txt; tail -2 gpurun_out/m_ref.err

@@ -367,6 +367,22 @@ def _fit_one_frame_cpu(args):
     return iters, evals, time.time() - t0
 
 
+def _warm_cpu_worker(V):
+    import torch
+    torch.set_num_threads(1)
+    from mvsmplfitting_b200 import synthetic as S
+    from oracle import closure_oracle as O
+    key = ("scene", V)
+    if key not in _CPU_CACHE:
+        model = S.make_model(0)
+        gmm = S.make_gmm(7)
+        cams = S.make_cameras(V)
+        _CPU_CACHE[key] = (model, cams, O.OracleModel.from_numpy(model), O.OraclePriors.gmm_from_dict(gmm),
+                           O.cams_to_torch(cams, torch.float32))
+    time.sleep(1.0)          # keep this worker busy until every other worker has taken its own warm-up task
+    return True
+
+
 def cpu_baseline_sample(V, sdf, max_seconds=30.0):
     """bounded sample: ONE frame, one host thread, full 4-stage fit (about 10-30 s of CPU work)"""
     import warnings
@@ -401,9 +417,8 @@ def run_reference(args):
     sdf_oracle.build()
     ctxm = mp.get_context("spawn")
     with ctxm.Pool(cores) as pool:
-        for w in range(args.warmup):
-            if w == 0:       # one warm-up round is enough to page everything in; the rest would only burn minutes
-                pool.map(_fit_one_frame_cpu, [(5000 + i, V, sdf) for i in range(cores)])
+        if args.warmup > 0:  # warm-up: every worker imports torch and builds the scene constants once (no fit: a fit is ~45 s)
+            pool.map(_warm_cpu_worker, [V] * cores, chunksize=1)
         it = ev = 0
         t0 = time.time()
         for s in range(args.steps):

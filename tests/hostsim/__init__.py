@@ -104,3 +104,15 @@ class HostSim:
             self.lib.hostsim_destroy(self.h)
         except Exception:
             pass
+
+
+def cont6d_to_aa(o6, daa, use_double=True):
+    """mvs_math.cuh cont6d_to_aa_fwd/_bwd run on the host: returns (aa [n,3], (d aa/d o)^T daa [n,6], branch [n])"""
+    lib = _build()
+    o6 = np.ascontiguousarray(o6, dtype=np.float64).reshape(-1, 6)
+    daa = np.ascontiguousarray(daa, dtype=np.float64).reshape(-1, 3)
+    n = o6.shape[0]
+    aa, d_o, br = np.zeros((n, 3)), np.zeros((n, 6)), np.zeros(n, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.hostsim_cont6d(ctypes.c_int(n), ctypes.c_int(int(use_double)), P(o6), P(daa), P(aa), P(d_o), P(br))
+    return aa, d_o, br

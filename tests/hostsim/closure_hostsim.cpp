@@ -259,4 +259,26 @@ void hostsim_eval(void* hv, int use_double, const HostLoss* lp, const double* gm
     if (use_double) run(h->d, *lp, gmm_means, gmm_prec, gmm_lognllw, x86, gt_uv, conf, jw, loss, grad, joints, verts);
     else run(h->f, *lp, gmm_means, gmm_prec, gmm_lognllw, x86, gt_uv, conf, jw, loss, grad, joints, verts);
 }
+// cont6d_to_aa_fwd / _bwd of mvs_math.cuh on n six-vectors: aa[n][3], d_o[n][6] = (d aa/d o)^T daa, branch[n]
+void hostsim_cont6d(int n, int use_double, const double* o6, const double* daa, double* aa, double* d_o, int* branch) {
+    for (int i = 0; i < n; ++i) {
+        if (use_double) {
+            mvs::Cont6dState<double> S; double a[3], g[6];
+            mvs::cont6d_to_aa_fwd<double>(o6 + 6 * i, a, S);
+            mvs::cont6d_to_aa_bwd<double>(S, daa + 3 * i, g);
+            for (int k = 0; k < 3; ++k) aa[3 * i + k] = a[k];
+            for (int k = 0; k < 6; ++k) d_o[6 * i + k] = g[k];
+            branch[i] = S.branch;
+        } else {
+            mvs::Cont6dState<float> S; float o[6], d[3], a[3], g[6];
+            for (int k = 0; k < 6; ++k) o[k] = (float)o6[6 * i + k];
+            for (int k = 0; k < 3; ++k) d[k] = (float)daa[3 * i + k];
+            mvs::cont6d_to_aa_fwd<float>(o, a, S);
+            mvs::cont6d_to_aa_bwd<float>(S, d, g);
+            for (int k = 0; k < 3; ++k) aa[3 * i + k] = a[k];
+            for (int k = 0; k < 6; ++k) d_o[6 * i + k] = g[k];
+            branch[i] = S.branch;
+        }
+    }
+}
 }

@@ -333,9 +333,16 @@ def gemm_flops(na: float) -> float:
 _CPU_CACHE = {}
 
 
+class _Deadline(Exception):
+    pass
+
+
 def _fit_one_frame_cpu(args):
-    """full 4-stage fit of ONE frame with the oracle (the reference's algorithm on CPU); returns counters"""
-    seed, V, sdf = args
+    """full 4-stage fit of ONE frame with the oracle (the reference's algorithm on CPU); returns counters.
+    An optional 4th element bounds the wall time: the fit is cut at the first closure evaluation past it and the
+    iterations completed so far are counted (bounded sample for the --impl reference arm)."""
+    seed, V, sdf = args[:3]
+    budget = args[3] if len(args) > 3 else None
     import torch
     torch.set_num_threads(1)
     from mvsmplfitting_b200 import synthetic as S
@@ -357,10 +364,15 @@ def _fit_one_frame_cpu(args):
         cfg = O.LossConfig(interpenetration=sdf, sdf_grid=128, **st)
 
         def fg(xx, cfg=cfg):
+            if budget is not None and time.time() - t0 > budget:
+                raise _Deadline()
             r = O.closure_eval(om, cfg, pri, ct, xx.numpy(), fr["gt_uv"][:, 0], fr["conf"][:, 0], fr["joint_weights"])
             return r["loss"], torch.tensor(r["grad"])
         opt = L.LBFGSOracle(x, fg, max_iter=30)
-        L.run_fitting(opt, 30, 1e-9, 1e-9)
+        try:
+            L.run_fitting(opt, 30, 1e-9, 1e-9)
+        except _Deadline:
+            return iters + opt.iters, evals + opt.evals, time.time() - t0
         x = opt.x
         iters += opt.iters
         evals += opt.evals
@@ -420,9 +432,11 @@ def run_reference(args):
         if args.warmup > 0:  # warm-up: every worker imports torch and builds the scene constants once (no fit: a fit is ~45 s)
             pool.map(_warm_cpu_worker, [V] * cores, chunksize=1)
         it = ev = 0
+        # the whole run is held to about --ref-seconds whatever K the caller picks: a step is cut after its share of it
+        step_budget = max(5.0, args.ref_seconds / max(1, args.steps))
         t0 = time.time()
         for s in range(args.steps):
-            res = pool.map(_fit_one_frame_cpu, [(7000 + 100 * s + i, V, sdf) for i in range(cores)])
+            res = pool.map(_fit_one_frame_cpu, [(7000 + 100 * s + i, V, sdf, step_budget) for i in range(cores)], chunksize=1)
             it += sum(r[0] for r in res)
             ev += sum(r[1] for r in res)
         dt = time.time() - t0
@@ -432,8 +446,10 @@ def run_reference(args):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": dict(workload_config(args.frames, V, sdf), parallelism="%d host processes x 1 thread" % cores),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "each step = %d frames (one per host core) x %d views, full 4-stage fit per frame, "
-                                      "oracle port of the reference (PyTorch CPU autograd + restated LBFGS/strong-Wolfe)" % (cores, V)},
+                            "sample": "each step = %d frames (one per worker) x %d views, the 4-stage fit of each frame run for at most "
+                                      "%.0f s (iterations completed by then are counted; a cut fit favours the cheaper early "
+                                      "stages, i.e. the CPU), oracle port of the reference (PyTorch CPU autograd + restated "
+                                      "LBFGS/strong-Wolfe)" % (cores, V, step_budget)},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "frame_closure_evals_per_s": ev / dt, "gpu_launches": 0}
     print(json.dumps(out))
@@ -451,6 +467,7 @@ def main():
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--cpu-seconds", type=float, default=30.0)
     ap.add_argument("--ref-workers", type=int, default=32)
+    ap.add_argument("--ref-seconds", type=float, default=240.0, help="wall-time bound of the --impl reference run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

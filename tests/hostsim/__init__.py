@@ -18,9 +18,10 @@ class HostLoss(ctypes.Structure):
 
 def _build():
     src = os.path.join(_HERE, "closure_hostsim.cpp")
-    hdr = os.path.join(_HERE, "..", "..", "mvsmplfitting_b200", "csrc", "mvs_math.cuh")
+    csrc = os.path.join(_HERE, "..", "..", "mvsmplfitting_b200", "csrc")
+    hdrs = [os.path.join(csrc, "mvs_math.cuh"), os.path.join(csrc, "mvs_init.cuh")]
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    if (not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    if (not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(q) for q in [src] + hdrs)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
                                "-o", _SO, src])
     return ctypes.CDLL(_SO)
@@ -116,3 +117,41 @@ def cont6d_to_aa(o6, daa, use_double=True):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     lib.hostsim_cont6d(ctypes.c_int(n), ctypes.c_int(int(use_double)), P(o6), P(daa), P(aa), P(d_o), P(br))
     return aa, d_o, br
+
+
+def _P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def triangulate(cams, uv, conf, use_double=True):
+    """mvs_init.cuh triangulate_point on the host.  cams dict (R [V,3,3], t, f, c), uv [V,K,2], conf [V,K] -> [K,3]"""
+    lib = _build()
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    uv = np.ascontiguousarray(uv, dtype=np.float32)
+    conf = np.ascontiguousarray(conf, dtype=np.float32)
+    V, K = conf.shape
+    X = np.zeros((K, 3))
+    R, t, f, c = f64(cams["R"]), f64(cams["t"]), f64(cams["f"]), f64(cams["c"])
+    lib.hostsim_triangulate(ctypes.c_int(V), ctypes.c_int(K), _P(R), _P(t), _P(f), _P(c), _P(uv), _P(conf),
+                            ctypes.c_int(int(use_double)), _P(X))
+    return X
+
+
+def umeyama(src, dst, estimate_scale, use_double=True):
+    """mvs_init.cuh umeyama_fit + rotmat_to_aa on the host -> (R [3,3], t [3], scale, aa [3]) or None if degenerate"""
+    lib = _build()
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.ascontiguousarray(dst, dtype=np.float64)
+    R, t, s, aa = np.zeros(9), np.zeros(3), np.zeros(1), np.zeros(3)
+    lib.hostsim_umeyama.restype = ctypes.c_int
+    ok = lib.hostsim_umeyama(ctypes.c_int(src.shape[0]), _P(src), _P(dst), ctypes.c_int(int(estimate_scale)),
+                             ctypes.c_int(int(use_double)), _P(R), _P(t), _P(s), _P(aa))
+    return (R.reshape(3, 3), t, float(s[0]), aa) if ok else None
+
+
+def rotmat_to_aa(R):
+    lib = _build()
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 9)
+    aa = np.zeros((R.shape[0], 3))
+    lib.hostsim_rotmat_to_aa(ctypes.c_int(R.shape[0]), _P(R), _P(aa))
+    return aa

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../mvsmplfitting_b200/csrc/mvs_math.cuh"
+#include "../../mvsmplfitting_b200/csrc/mvs_init.cuh"
 
 using namespace mvs;
 
@@ -280,5 +281,45 @@ void hostsim_cont6d(int n, int use_double, const double* o6, const double* daa, 
             branch[i] = S.branch;
         }
     }
+}
+// mvs_init.cuh on the host.  cams: R [V,9], t [V,3], f [V,2], c [V,2]; uv [V,K,2], conf [V,K] -> X [K,3]
+struct HostCamSet { int num_views; CamF cam[kMaxViews]; };
+void hostsim_triangulate(int V, int K, const double* cR, const double* ct, const double* cf, const double* cc,
+                         const float* uv, const float* conf, int use_double, double* X) {
+    HostCamSet cs; cs.num_views = V;
+    for (int v = 0; v < V; ++v) {
+        for (int i = 0; i < 9; ++i) cs.cam[v].R[i] = (float)cR[9 * v + i];
+        for (int i = 0; i < 3; ++i) cs.cam[v].t[i] = (float)ct[3 * v + i];
+        for (int i = 0; i < 2; ++i) { cs.cam[v].f[i] = (float)cf[2 * v + i]; cs.cam[v].c[i] = (float)cc[2 * v + i]; }
+    }
+    for (int k = 0; k < K; ++k) {
+        if (use_double) {
+            triangulate_point<double>(cs, uv + 2 * k, conf + k, 2L * K, (long)K, X + 3 * k);
+        } else {
+            float x[3];
+            triangulate_point<float>(cs, uv + 2 * k, conf + k, 2L * K, (long)K, x);
+            for (int i = 0; i < 3; ++i) X[3 * k + i] = x[i];
+        }
+    }
+}
+// returns 1 if a transform was found.  src, dst [n,3]; R [9] row-major, t [3], scale [1], aa [3] = rotmat_to_aa(R)
+int hostsim_umeyama(int n, const double* src, const double* dst, int estimate_scale, int use_double, double* R, double* t,
+                    double* scale, double* aa) {
+    if (use_double) {
+        if (!umeyama_fit<double>(src, dst, n, estimate_scale != 0, R, t, scale)) return 0;
+        rotmat_to_aa<double>(R, aa);
+        return 1;
+    }
+    float s[51], d[51], Rf[9], tf[3], sf, af[3];
+    for (int i = 0; i < 3 * n; ++i) { s[i] = (float)src[i]; d[i] = (float)dst[i]; }
+    if (!umeyama_fit<float>(s, d, n, estimate_scale != 0, Rf, tf, &sf)) return 0;
+    rotmat_to_aa<float>(Rf, af);
+    for (int i = 0; i < 9; ++i) R[i] = Rf[i];
+    for (int i = 0; i < 3; ++i) { t[i] = tf[i]; aa[i] = af[i]; }
+    *scale = sf;
+    return 1;
+}
+void hostsim_rotmat_to_aa(int n, const double* R, double* aa) {
+    for (int i = 0; i < n; ++i) rotmat_to_aa<double>(R + 9 * i, aa + 3 * i);
 }
 }

@@ -185,6 +185,26 @@ int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, cons
                  const float* joint_weights_host, int n_stages, const mvs_loss_config* stage_cfgs,
                  const mvs_lbfgs_config* opt_cfg, float* final_loss_host, mvs_lbfgs_stats* stats, void* stream);
 
+/* ---- initial guess for all frames of the batch (code/utils/init_guess.py:18-107 + fix_params :190-212, which
+ *      main.py:76-82 runs per frame in numpy before the solver): triangulates the K keypoints from the V >= 2 views
+ *      (code/utils/recompute3D.py:24-61, as written), aligns the model's rest joints (zero pose, zero shape,
+ *      scale = fixed_scale) to them with a similarity transform (code/utils/umeyama.py:18 -> the published
+ *      algorithm, Umeyama PAMI 1991; the file's own transposed-V variant depends on the LAPACK build's sign
+ *      convention, see oracle/init_oracle.py) and writes the parameter block the solver starts from:
+ *      betas 0, global_orient = axis-angle of R (cv2.Rodrigues, init_guess.py:86), body_pose 0 except the first six
+ *      entries = hip_seed (fix_params; the reference uses 1.0; ignored when the loss config has use_vposer = 2, where
+ *      the pose slots hold the latent code, which is zeroed as init_guess.py:96-98 does), transl = t, scale = s or
+ *      fixed_scale.  Frames whose detections are degenerate (rank < 2) get the translation of the centroids only.
+ *      params_dev [B,86] is overwritten; joints3d_dev [B,K,3] receives the triangulated keypoints (may be NULL).
+ *      Uses the keypoints and cameras already uploaded; asynchronous on `stream`. */
+typedef struct {
+    int estimate_scale;            /* not setting['fix_scale'] (init_guess.py:24) */
+    float fixed_scale;             /* setting['fixed_scale'] or 1 (init_guess.py:25) */
+    int use_torso;                 /* align on keypoints 5, 6, 11, 12 only (main.py:77 passes True) */
+    float hip_seed;                /* fix_params init_guess.py:198-201: 1.0 in the reference */
+} mvs_init_config;
+int mvs_init_guess(mvs_ctx* ctx, float* params_dev, float* joints3d_dev, const mvs_init_config* cfg, void* stream);
+
 /* ---- SDF grid: replaces the pybind op sdf.csrc.sdf(phi, faces, vertices) (sdf/sdf/csrc/sdf_cuda.cpp:14-28,
  *      kernel sdf_cuda_kernel.cu:242-335).  phi_dev [B,G,G,G] (written), faces_dev int32 [*,3],
  *      verts_dev [B,n_verts,3] normalised to [-1,1].  num_faces is what the kernel loops over

@@ -51,11 +51,17 @@ class LbfgsStats(ctypes.Structure):
                 ("rounds", ctypes.c_int), ("frames_nan", ctypes.c_int)]
 
 
+class InitConfig(ctypes.Structure):
+    """mvs_init_config (include/mvsmpl.h)"""
+    _fields_ = [("estimate_scale", ctypes.c_int), ("fixed_scale", ctypes.c_float), ("use_torso", ctypes.c_int),
+                ("hip_seed", ctypes.c_float)]
+
+
 EXPORTS = (
     "mvs_version", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
     "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
     "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
-    "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor",
+    "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor", "mvs_init_guess",
 )
 NUM_KERNEL_IDS = 18
 
@@ -92,6 +98,7 @@ def load() -> ctypes.CDLL:
     lib.mvs_lbfgs_run.argtypes = [vp, vp, vp, ctypes.POINTER(LbfgsConfig), ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_lbfgs_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LbfgsConfig), ci, ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_set_vposer.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mvs_init_guess.argtypes = [vp, vp, vp, ctypes.POINTER(InitConfig), vp]
     lib.mvs_fit.argtypes = [vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp, ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_fit_host.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp,
                                  ctypes.POINTER(LbfgsStats), vp]

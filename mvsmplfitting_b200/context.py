@@ -223,6 +223,17 @@ class FittingContext:
         return loss, grad, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
                                 frames_nan=st.frames_nan)
 
+    def init_guess(self, estimate_scale: bool = True, fixed_scale: float = 1.0, use_torso: bool = True,
+                   hip_seed: float = 1.0, want_joints3d: bool = True):
+        """Initial parameter block of every frame from the uploaded detections (mvs_init_guess: triangulation +
+        similarity alignment, init_guess.py:18-107 + fix_params :190-212).  Returns (params [B,86], joints3d [B,K,3])."""
+        params = torch.empty(self.B, 86, dtype=torch.float32, device=self.device)
+        j3 = torch.empty(self.B, self.K, 3, dtype=torch.float32, device=self.device) if want_joints3d else None
+        cfg = _lib.InitConfig(int(bool(estimate_scale)), float(fixed_scale), int(bool(use_torso)), float(hip_seed))
+        _lib.check(self.h, self.lib.mvs_init_guess(self.h, _ptr(params), _ptr(j3), ctypes.byref(cfg), self._stream()),
+                   "mvs_init_guess")
+        return params, j3
+
     def fit(self, params: torch.Tensor, stage_cfgs, opt_cfg=None):
         """All stages of a fit on device buffers (mvs_fit): params [B,86] CUDA float32, updated in place.  Frames move
         from stage to stage on their own; returns (final_loss [B], stats)."""

@@ -1,0 +1,73 @@
+"""GPU: mvs_init_guess (batched initial guess) through the C ABI against oracle/init_oracle.py, which is
+pinned to the reference's recompute3D / cv2.Rodrigues outputs (tests/test_init_golden.py).
+
+The kernel was written after this round's GPU minutes were spent: its arithmetic (mvs_init.cuh) is verified on the
+CPU by tests/test_hostsim_init.py, but the launch itself first meets hardware in the round-end run.  The device part
+therefore runs in a child process (a fault cannot take the other GPU tests' CUDA context with it) and the test is a
+non-strict xfail until a hardware run has been seen; it is the last GPU test file on purpose."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def worker(B, V, estimate_scale, use_torso):
+    import torch
+    sys.path.insert(0, ROOT)
+    from mvsmplfitting_b200 import synthetic as S
+    from mvsmplfitting_b200.context import FittingContext
+    model, cams = S.make_model(0), S.make_cameras(V)
+    fr = S.make_frames(model, cams, B, seed=900 + V)
+    ctx = FittingContext(0)
+    ctx.set_model(model)
+    ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
+    ctx.set_batch(B)
+    ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    n0 = ctx.launch_count()
+    params, j3 = ctx.init_guess(estimate_scale=estimate_scale, fixed_scale=1.0, use_torso=use_torso, hip_seed=1.0)
+    torch.cuda.synchronize()
+    out = dict(params=params.cpu().numpy().tolist(), j3=j3.cpu().numpy().tolist(), launches=int(ctx.launch_count() - n0))
+    ctx.close()
+    print("RESULT" + json.dumps(out))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first hardware run of a kernel added after the round's GPU budget was spent")
+@pytest.mark.parametrize("B,V,est,torso", [(37, 4, True, True), (64, 8, False, True), (5, 16, True, False)])
+def test_init_guess_matches_oracle(B, V, est, torso):
+    from mvsmplfitting_b200 import synthetic as S
+    from oracle import init_oracle as IO
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(V), str(int(est)), str(int(torso))],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1][6:])
+    params, j3 = np.array(out["params"]), np.array(out["j3"])
+    assert out["launches"] <= 8                                # seed + forward chain + init kernel
+    model, cams = S.make_model(0), S.make_cameras(V)
+    fr = S.make_frames(model, cams, B, seed=900 + V)
+    z = lambda n: np.zeros((1, n))
+    rest = S.model_keypoints_np(model, z(10), z(3), z(69), z(3), np.ones((1, 1)), "smpllsp")[0]
+    ext = np.tile(np.eye(4), (V, 1, 1))
+    ext[:, :3, :3], ext[:, :3, 3] = cams["R"], cams["t"]
+    intr = np.tile(np.eye(3), (V, 1, 1))
+    intr[:, 0, 0], intr[:, 1, 1], intr[:, 0, 2], intr[:, 1, 2] = cams["f"][:, 0], cams["f"][:, 1], cams["c"][:, 0], cams["c"][:, 1]
+    for b in range(B):
+        kps = [np.concatenate([fr["gt_uv"][v, b], fr["conf"][v, b][:, None]], axis=1) for v in range(V)]
+        o = IO.init_guess(ext, intr, kps, rest, est, 1.0, torso)
+        assert np.abs(j3[b] - o["joints3d"]).max() / np.abs(o["joints3d"]).max() < 1e-4          # parity bar
+        x = params[b]
+        assert np.abs(x[10:13] - o["global_orient"]).max() < 2e-3      # rest joints travel as float32
+        assert np.abs(x[82:85] - o["transl"]).max() < 2e-3 * max(1.0, np.abs(o["transl"]).max())
+        assert abs(x[85] - o["scale"]) < 1e-3 * o["scale"]
+        assert (x[:10] == 0).all() and (x[13:19] == 1).all() and (x[19:82] == 0).all()
+        # the guess is useful: the aligned torso lands on the triangulated torso
+        assert np.abs(x[82:85] - fr["gt"]["transl"][b]).max() < 0.5
+
+
+if __name__ == "__main__":
+    worker(int(sys.argv[1]), int(sys.argv[2]), bool(int(sys.argv[3])), bool(int(sys.argv[4])))

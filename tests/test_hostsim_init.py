@@ -88,3 +88,28 @@ def test_rotmat_to_aa_matches_cv2(gold):
             assert abs(np.linalg.norm(mine) - ang) < 1e-6 and min(np.abs(mine - r).max(), np.abs(mine + r).max()) < 1e-5
         else:
             assert np.abs(mine - r).max() < 1e-9 + 1e-7 * ang
+
+
+@pytest.mark.parametrize("V,est,torso", [(4, True, True), (8, False, True), (16, True, False)])
+def test_whole_initial_guess_matches_oracle(V, est, torso):
+    """the data flow of init_guess_kernel on the host: triangulate every keypoint, align the (torso) rest joints"""
+    from mvsmplfitting_b200 import synthetic as S
+    model, cams = S.make_model(0), S.make_cameras(V)
+    fr = S.make_frames(model, cams, 6, seed=900 + V)
+    z = lambda n: np.zeros((1, n))
+    rest = S.model_keypoints_np(model, z(10), z(3), z(69), z(3), np.ones((1, 1)), "smpllsp")[0].astype(np.float32)
+    ext = np.tile(np.eye(4), (V, 1, 1))
+    ext[:, :3, :3], ext[:, :3, 3] = cams["R"], cams["t"]
+    intr = np.tile(np.eye(3), (V, 1, 1))
+    intr[:, 0, 0], intr[:, 1, 1], intr[:, 0, 2], intr[:, 1, 2] = cams["f"][:, 0], cams["f"][:, 1], cams["c"][:, 0], cams["c"][:, 1]
+    sel = list(IO.TORSO) if torso else list(range(17))
+    for b in range(6):
+        kps = [np.concatenate([fr["gt_uv"][v, b], fr["conf"][v, b][:, None]], axis=1) for v in range(V)]
+        o = IO.init_guess(ext, intr, kps, rest, est, 1.0, torso)
+        j3 = HS.triangulate(cams, fr["gt_uv"][:, b], fr["conf"][:, b], True)
+        assert np.abs(j3 - o["joints3d"]).max() / np.abs(o["joints3d"]).max() < 1e-5
+        R, t, s, aa = HS.umeyama(rest[sel], j3[sel], est, True)
+        assert np.abs(aa - o["global_orient"]).max() < 1e-4 and np.abs(t - o["transl"]).max() < 1e-4
+        assert abs(s - (o["scale"] if est else 1.0)) < 1e-4
+        if torso:      # the point of the guess: the frame's true translation is recovered to a few cm
+            assert np.abs(t - fr["gt"]["transl"][b]).max() < 0.5

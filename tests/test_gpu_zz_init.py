@@ -43,7 +43,7 @@ def test_init_guess_matches_oracle(B, V, est, torso):
     from mvsmplfitting_b200 import synthetic as S
     from oracle import init_oracle as IO
     p = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(V), str(int(est)), str(int(torso))],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=180)
     assert p.returncode == 0, p.stderr[-2000:]
     out = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1][6:])
     params, j3 = np.array(out["params"]), np.array(out["j3"])

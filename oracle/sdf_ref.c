@@ -124,3 +124,39 @@ void sdf_ref_voxels(float* out, const int64_t* voxel_ids, long n, const int32_t*
         out[q] = voxel_phi(faces, verts, num_faces, G, i, j, k);
     }
 }
+
+/* ---- candidate-list evaluation (prototype of the accelerated all-faces mode) ----
+ * Same arithmetic as voxel_phi, but the distance minimum runs over dist_idx[dist_ptr[q] .. dist_ptr[q+1]) and the
+ * ray-parity count over ray_idx[ray_ptr[q] .. ray_ptr[q+1]) instead of all faces.  Returns min_d BEFORE the parity
+ * rule in out_d and the hit count in out_hits, so that the caller can decide whether the distance list was large
+ * enough (ring search) before combining them.  oracle/sdf_binned.py builds the lists and proves they reproduce the
+ * brute force bit for bit. */
+void sdf_ref_voxels_lists(float* out_d, int32_t* out_hits, const int64_t* voxel_ids, long n, const int32_t* faces,
+                          const float* verts, int G, const int64_t* dist_ptr, const int32_t* dist_idx,
+                          const int64_t* ray_ptr, const int32_t* ray_idx) {
+    const float dx = 2. / (G - 1);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long q = 0; q < n; ++q) {
+        long tid = voxel_ids[q];
+        int i = tid % G, j = (tid / G) % G, k = (tid / ((long)G * G)) % G;
+        const float c[3] = {(float)(-1 + (i + 0.5) * dx), (float)(-1 + (j + 0.5) * dx), (float)(-1 + (k + 0.5) * dx)};
+        float min_d = 1000;
+        for (int64_t e = dist_ptr[q]; e < dist_ptr[q + 1]; ++e) {
+            const int f = dist_idx[e];
+            float cp[3];
+            tri_closest(c, verts + 3 * faces[3 * f], verts + 3 * faces[3 * f + 1], verts + 3 * faces[3 * f + 2], cp);
+            float dist = distf(c, cp);
+            if (dist < min_d) min_d = dist;
+        }
+        int hits = 0;
+        float dir[3] = {-1.0f - c[0], -1.0f - c[1], -1.0f - c[2]};
+        for (int64_t e = ray_ptr[q]; e < ray_ptr[q + 1]; ++e) {
+            const int f = ray_idx[e];
+            float t;
+            if (ray_tri(c, dir, verts + 3 * faces[3 * f], verts + 3 * faces[3 * f + 1], verts + 3 * faces[3 * f + 2], &t) && t >= 0)
+                hits++;
+        }
+        out_d[q] = min_d;
+        out_hits[q] = hits;
+    }
+}

@@ -14,9 +14,9 @@ triangle that can change the result, so phi is bit-identical to the brute force:
       that touches no cell within Chebyshev ring r of the voxel's cell is farther than r * h (h = cell size).  Rings are
       added until the running minimum is below that bound -- next to the surface ring 1 is enough.
   (2) parity: every ray ends in the same point O, so a central projection from O maps each ray to a POINT and each
-      triangle to a triangle: s = (p - O) / sum(p - O), 2-D coordinates (s_y, s_z) in (0,1)^2.  Triangles are binned by
-      the (epsilon-padded) bounding box of their projection into an R x R grid; only the triangles in the bin of the
-      voxel's own projection can be hit.
+      triangle to a triangle: s = (p - O) / sum(p - O), 2-D coordinates (s_y, s_z) in (0,1)^2.  Triangles are
+      rasterised conservatively (epsilon-padded) into an R x R grid over the projected mesh; only the triangles in the
+      bin of the voxel's own projection can be hit.
 Both bin structures depend on the posed vertices and are rebuilt per closure evaluation (13 776 triangles: a counting
 sort in shared memory on the device)."""
 from __future__ import annotations
@@ -53,7 +53,7 @@ def _bin_boxes(lo, hi, n_bins):
 
 
 class BinnedSdf:
-    def __init__(self, faces, verts_norm, grid_size, cells=128, ray_bins=256, eps=1e-5):
+    def __init__(self, faces, verts_norm, grid_size, cells=128, ray_bins=256, eps=1e-5, raster=True):
         self.faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
         self.verts = np.ascontiguousarray(verts_norm, dtype=np.float32).reshape(-1, 3)
         self.G, self.C, self.R = int(grid_size), int(cells), int(ray_bins)
@@ -73,6 +73,28 @@ class BinnedSdf:
         lo = np.clip(np.floor((s.min(1) - eps - self.s_lo) * self.s_scale).astype(np.int64), 0, self.R - 1)
         hi = np.clip(np.floor((s.max(1) + eps - self.s_lo) * self.s_scale).astype(np.int64), 0, self.R - 1)
         own, it = _bin_boxes(lo, hi, self.R)
+        if raster:
+            # conservative rasterisation: keep (bin, triangle) only if the eps-padded bin rectangle is not separated from
+            # the projected triangle by one of the triangle's edge lines (the bounding-box axes are already tested)
+            bx, by = own // self.R, own % self.R
+            pad = eps * self.s_scale
+            x0, x1 = bx - pad[0], bx + 1 + pad[0]
+            y0, y1 = by - pad[1], by + 1 + pad[1]
+            t = (s[it] - self.s_lo) * self.s_scale                                       # [n,3,2] in bin units
+            keep = np.ones(len(own), dtype=bool)
+            area = (t[:, 1, 0] - t[:, 0, 0]) * (t[:, 2, 1] - t[:, 0, 1]) - (t[:, 1, 1] - t[:, 0, 1]) * (t[:, 2, 0] - t[:, 0, 0])
+            sgn = np.where(area >= 0, 1.0, -1.0)
+            for a in range(3):
+                p, q = t[:, a], t[:, (a + 1) % 3]
+                ex, ey = q[:, 0] - p[:, 0], q[:, 1] - p[:, 1]
+                # signed distance (times edge length) of the rectangle corner farthest INSIDE; all corners outside <=> max < 0
+                best = np.full(len(own), -np.inf)
+                for cx in (x0, x1):
+                    for cy in (y0, y1):
+                        best = np.maximum(best, sgn * (ex * (cy - p[:, 1]) - ey * (cx - p[:, 0])))
+                tol = 1e-9 + 4 * np.abs(pad).max() * (np.abs(ex) + np.abs(ey))
+                keep &= ~(best < -tol) | (np.abs(area) < 1e-12)                          # degenerate projections: keep
+            own, it = own[keep], it[keep]
         self.ray_ptr, self.ray_idx = _csr(own, it, self.R ** 2)
 
     @staticmethod

@@ -1,6 +1,6 @@
 """CPU: the culling scheme of the accelerated all-faces SDF mode (oracle/sdf_binned.py) reproduces the
 brute-force restatement of the reference kernel (oracle/sdf_ref.c, all 13 776 faces per voxel) BIT FOR BIT at the voxels
-the fused SDF term samples, with two orders of magnitude fewer triangle tests."""
+the fused SDF term samples, with more than two orders of magnitude fewer triangle tests."""
 import numpy as np
 import pytest
 
@@ -52,7 +52,7 @@ def test_binned_phi_is_the_brute_force_bit_for_bit(G, step, seed, syn_model):
     assert (brute > 0).sum() > 20                      # inside voxels exist, the parity rule is exercised
     F = faces.reshape(-1, 3).shape[0]
     tests = info["dist_candidates"].mean() + info["ray_candidates"].mean()
-    assert tests < 2 * F / 50                          # > 50x fewer triangle tests than 2 F per voxel
+    assert tests < 2 * F / 100                         # > 100x fewer triangle tests than 2 F per voxel
     assert info["ring"].max() <= (3 if G == 128 else 12)      # at the product's G = 128 the first ring almost always decides
     if G == 128:
         assert info["ring"].mean() < 1.2

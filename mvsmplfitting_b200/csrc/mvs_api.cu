@@ -127,7 +127,7 @@ const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelN
 
 int mvs_set_exec_mode(mvs_ctx* ctx, int mode) {
     if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
-    MVS_REQUIRE(ctx, mode >= 0 && mode <= 2, "mvs_set_exec_mode: mode must be 0, 1 or 2");
+    MVS_REQUIRE(ctx, mode >= 0 && mode <= 3, "mvs_set_exec_mode: mode must be 0, 1, 2 or 3");
     ctx->exec_mode = mode;
     return MVS_OK;
 }

@@ -272,6 +272,7 @@ int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st);                 // mvs_
 int launch_frame_fwd_dense(mvs_ctx* ctx, const float* x_dev, const void* lbfgs_state, int nstages, cudaStream_t st);   // mvs_resident.cu
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
+int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, cudaStream_t st);   // mvs_lbfgs.cu
 int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,
                     int n_verts, int G, cudaStream_t st);

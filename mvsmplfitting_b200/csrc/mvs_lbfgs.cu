@@ -314,6 +314,35 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     return MVS_OK;
 }
 
+// One closure evaluation through the dense-regime kernels (posedirs_gemm_tc -> skin -> sdf_fused -> frame_step with the
+// optimiser step switched off): mvs_closure in exec mode 3.  Exists so that parity tests can compare the loss and every
+// gradient segment of the kernels the optimiser actually runs with the SDF term on.
+int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, cudaStream_t st) {
+    const int B = ctx->ws.B;
+    int rc = ensure_state(ctx, static_cast<LbfgsState*>(ctx->lbfgs) ? static_cast<LbfgsState*>(ctx->lbfgs)->H : 100);
+    if (rc) return rc;
+    LbfgsState& S = *static_cast<LbfgsState*>(ctx->lbfgs);
+    Workspace& w = ctx->ws;
+    LbfgsCfg cfg{};
+    cfg.max_outer = 1; cfg.max_iter = 1; cfg.max_eval = 1; cfg.history = S.H; cfg.max_ls = 25; cfg.step_mode = 2; cfg.lr = 1.f;
+    S.lp_tab_host[0] = ctx->loss;
+    MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.lp_tab, S.lp_tab_host, sizeof(LossParams), cudaMemcpyHostToDevice, st));
+    MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
+    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, x_dev, B, 1));
+    w.na_bound = B;
+    if ((rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, 1, st))) return rc;
+    if ((rc = frame_step_begin_run(ctx, st))) return rc;
+    if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;
+    if ((rc = launch_sdf_fused(ctx, st))) return rc;
+    if ((rc = launch_frame_step(ctx, const_cast<float*>(x_dev) /* read only in this mode */, &S, &cfg, 1, st))) return rc;
+    if (loss_dev) MVS_CUDA_OK(ctx, cudaMemcpyAsync(loss_dev, S.loss_eval, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (grad_dev) MVS_CUDA_OK(ctx, cudaMemcpyAsync(grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));         // the pinned stage table is reused by the next call
+    if ((rc = tc_check_error(ctx))) return rc;
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
 // All stages of a fit.  Consecutive stages that run in the same regime are handed to ONE multi-stage run in which
 // every frame changes stage on its own (frames are independent problems, so a frame that converged need not wait at
 // the stage boundary for the slowest one; the per-frame arithmetic is the sequential schedule's).  exec_mode 2 keeps

@@ -1097,6 +1097,10 @@ frame_step_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ l
     asm volatile("cp.async.wait_all;");
     __syncthreads();
     PHASE_MARK(23);
+    if (cfg.step_mode == 2) {                          // closure only (mvs_closure in exec mode 3): no optimiser step
+        if (t == 0) L.loss_eval[b] = S.sc[2];
+        return;
+    }
     if (warp == 0) {
         FrameScalars s = fs0;
         LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval,

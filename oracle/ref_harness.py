@@ -1,7 +1,8 @@
-"""TEST INFRASTRUCTURE -- runs the UNMODIFIED reference (/root/reference) as the
-ground truth that pins the oracle.  Only usable in the authoring container
-(the GPU box has no /root/reference); used by oracle/make_golden.py to write
-tests/golden/*.npz and by tests marked `needs_reference`.
+"""TEST INFRASTRUCTURE -- runs the UNMODIFIED reference as the ground truth that pins the
+oracle.  The tree is /root/reference in the authoring container (used by oracle/make_golden*.py
+to write tests/golden/*.npz and by tests marked `needs_reference`) or, on the GPU box, the copy
+oracle/stage_reference.py placed under the git-ignored oracle/_ref/reference/ (bench.py --impl
+reference and the -m gpu tests that run the reference closure with its own SDF kernel).
 
 Nothing here is imported by the product package.
 
@@ -21,7 +22,19 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("MVS_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("MVS_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/code/smplx"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _pick_root()
 
 
 def available() -> bool:
@@ -56,6 +69,12 @@ def import_reference():
     code = os.path.join(REF_ROOT, "code")
     if code not in sys.path:
         sys.path.insert(0, code)
+    sdf_pkg = os.path.join(REF_ROOT, "sdf")                  # the reference's `sdf` package (sdf/sdf/sdf.py), unmodified;
+    if sdf_pkg not in sys.path:                              # its compiled half `sdf.csrc` = the reference kernel built by
+        sys.path.insert(0, sdf_pkg)                          # oracle/build_ref_sdf.sh (oracle/ref_sdf.py)
+    from oracle import ref_sdf
+    if ref_sdf.available():
+        ref_sdf.install_csrc_stub()
     with in_reference_dir():
         import smplx  # noqa: F401  (reference code/smplx)
         from smplx import body_models_scale, lbs
@@ -139,22 +158,35 @@ def set_model_params(ref_model, params: dict, frame: int):
 
 def reference_closure_eval(ref_model, ref_cams, frames: dict, frame: int, weights: dict,
                            body_pose_prior, dtype=torch.float32, params: dict | None = None,
-                           use_joints_conf=True, rho=100.0, fix_shape=False):
+                           use_joints_conf=True, rho=100.0, fix_shape=False, device="cpu",
+                           interpenetration=False, coll_loss_weight=0.0):
     """One fitting_func() of the reference for frame `frame` (fitting.py:162-203),
-    B = 1 as the reference requires.  Returns dict(loss, grads{...}, joints, proj, vertices)."""
+    B = 1 as the reference requires.  Returns dict(loss, grads{...}, joints, proj, vertices).
+    device="cuda": the reference's shipped mode (cfg_files/fit_smpl.yaml:19); interpenetration=True additionally needs the
+    reference's SDF kernel (oracle/_ref/libsdf_refcuda.so) and runs fitting.py:352-393 as written."""
     ns = import_reference()
+    dev = torch.device(device)
+    if next(ref_model.parameters()).device != dev:
+        ref_model.to(dev)
+        for cam in ref_cams:
+            cam.to(dev)
+        if body_pose_prior is not None and hasattr(body_pose_prior, "to"):
+            body_pose_prior.to(dev)
     p = params if params is not None else frames["init"]
     set_model_params(ref_model, p, frame)
     V = frames["gt_uv"].shape[0]
-    gt = torch.tensor(frames["gt_uv"][:, frame:frame + 1], dtype=dtype)          # [V,1,17,2]
-    conf = [torch.tensor(frames["conf"][v, frame:frame + 1], dtype=dtype) for v in range(V)]
-    jw = torch.tensor(frames["joint_weights"], dtype=dtype).unsqueeze(0)
+    gt = torch.tensor(frames["gt_uv"][:, frame:frame + 1], dtype=dtype, device=dev)          # [V,1,17,2]
+    conf = [torch.tensor(frames["conf"][v, frame:frame + 1], dtype=dtype, device=dev) for v in range(V)]
+    jw = torch.tensor(frames["joint_weights"], dtype=dtype, device=dev).unsqueeze(0)
     loss = ns.fitting.create_loss(
         "smplify", rho=rho, use_joints_conf=use_joints_conf, dtype=dtype,
         body_pose_prior=body_pose_prior, shape_prior=ns.prior.create_prior("l2"),
         angle_prior=ns.prior.create_prior("angle", dtype=dtype),
-        interpenetration=False, fix_shape=fix_shape)
-    loss.reset_loss_weights({k: torch.tensor(v, dtype=dtype) for k, v in weights.items()})
+        interpenetration=interpenetration, fix_shape=fix_shape).to(dev)
+    wd = dict(weights)
+    if interpenetration:
+        wd["coll_loss_weight"] = coll_loss_weight
+    loss.reset_loss_weights({k: torch.tensor(v, dtype=dtype, device=dev) for k, v in wd.items()})
     monitor = ns.fitting.FittingMonitor(maxiters=30, ftol=1e-9, gtol=1e-9)
     plist = [q for q in ref_model.parameters() if q.requires_grad]
     opt = torch.optim.SGD(plist, lr=0.0)
@@ -167,10 +199,10 @@ def reference_closure_eval(ref_model, ref_cams, frames: dict, frame: int, weight
     proj = torch.stack([cam(out.joints) for cam in ref_cams])[:, 0]
     return dict(
         loss=float(total),
-        grads={k: getattr(ref_model, k).grad.detach().numpy().copy().reshape(-1)
+        grads={k: getattr(ref_model, k).grad.detach().cpu().numpy().copy().reshape(-1)
                for k in ("betas", "global_orient", "body_pose", "transl", "scale")
                if getattr(ref_model, k).grad is not None},
-        joints=out.joints.detach().numpy()[0].copy(),
-        proj=proj.detach().numpy().copy(),
-        vertices=out.vertices.detach().numpy()[0].copy(),
+        joints=out.joints.detach().cpu().numpy()[0].copy(),
+        proj=proj.detach().cpu().numpy().copy(),
+        vertices=out.vertices.detach().cpu().numpy()[0].copy(),
     )

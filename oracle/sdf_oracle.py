@@ -3,9 +3,9 @@ term: the voxel kernel (oracle/sdf_ref.c, restating sdf/sdf/csrc/sdf_cuda_kernel
 plus the Python glue of code/utils/fitting.py:352-393 (bounding box, 1.2 x 0.5
 scale, no-grad normalisation, grid_sample with its defaults, squared weighted sum).
 
-Not a product path.  The reference SDF extension itself is unbuildable here
-(CUDA + removed ATen APIs), so parity of this term is pinned only by
-this line-by-line restatement ("parity unpinned" by any reference-run fixture).
+Not a product path.  Pinned on the GPU box against the reference's own kernel compiled
+unchanged (oracle/build_ref_sdf.sh -> oracle/_ref/libsdf_refcuda.so) by
+tests/test_gpu_sdf_refpin.py, voxel for voxel.
 """
 from __future__ import annotations
 
@@ -19,6 +19,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
 _LIB = None
+GRID_FN = None        # tests may plug in another voxeliser with sdf_grid's signature (the reference's own CUDA kernel,
+                      # oracle/ref_sdf.py) for penetration_loss; None = the C restatement below
 
 
 def build(force: bool = False) -> str:
@@ -79,7 +81,7 @@ def penetration_loss(vertices: torch.Tensor, faces: torch.Tensor, coll_loss_weig
     scale = (1 + 0.2) * 0.5 * (boxes[:, 1] - boxes[:, 0]).max(dim=-1)[0][:, None, None]
     with torch.no_grad():
         vn = (v - center) / scale
-        phi = sdf_grid(faces.numpy(), vn.to(torch.float32).numpy(), grid_size, all_faces=all_faces)
+        phi = (GRID_FN or sdf_grid)(faces.numpy(), vn.to(torch.float32).numpy(), grid_size, all_faces=all_faces)
         phi = torch.from_numpy(phi).to(v.dtype)
     local = (v - center[0].unsqueeze(0)) / scale[0].unsqueeze(0)
     grid = local.view(1, -1, 1, 1, 3)

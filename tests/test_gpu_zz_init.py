@@ -1,11 +1,8 @@
 """GPU: mvs_init_guess (batched initial guess) through the C ABI against oracle/init_oracle.py, which is
 pinned to the reference's recompute3D / cv2.Rodrigues outputs (tests/test_init_golden.py).
 
-The kernel was written when this round's GPU minutes were almost spent: its arithmetic (mvs_init.cuh) is verified on
-the CPU by tests/test_hostsim_init.py and ONE hardware run (scripts/init_time.py 64 4, profiles/r01_init_guess.txt)
-matched the oracle to 6e-8, but the three configurations below first meet hardware in the round-end run.  The device
-part therefore runs in a child process (a fault cannot take the other GPU tests' CUDA context with it) and the test is
-a non-strict xfail until that run has been seen; it is the last GPU test file on purpose."""
+The arithmetic (mvs_init.cuh) is also verified on the CPU by tests/test_hostsim_init.py.  The device part runs in a child
+process (historical: the kernel first met hardware in round 1's closing run, where all three configurations passed)."""
 import json
 import os
 import subprocess
@@ -38,7 +35,6 @@ def worker(B, V, estimate_scale, use_torso):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="configurations not yet run on hardware (one other configuration was: profiles/r01_init_guess.txt)")
 @pytest.mark.parametrize("B,V,est,torso", [(37, 4, True, True), (64, 8, False, True), (5, 16, True, False)])
 def test_init_guess_matches_oracle(B, V, est, torso):
     from mvsmplfitting_b200 import synthetic as S

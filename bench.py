@@ -2,7 +2,7 @@
 """bench.py -- L-BFGS iterations/s of the multi-view SMPL fitting hot path.
 
     python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
-    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle port)
+    python bench.py --impl reference --steps K --warmup W    (the UNMODIFIED reference on the host cores; --ref-device cuda: on torch-CUDA)
 
 Workload (BASELINE.json configs[3], the config the metric is quoted on): per GPU 256 frames x 8
 calibrated views of the synthetic SMPL-shaped model (6890 verts, 207 pose blend shapes), GMM(6) +
@@ -329,129 +329,133 @@ def gemm_flops(na: float) -> float:
     return 2.0 * na * 207 * 20670
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-_CPU_CACHE = {}
+# ----------------------------------------------------------------------------- the reference arm
+# The reference itself (staged unmodified under oracle/_ref/reference by oracle/stage_reference.py, or /root/reference in the
+# authoring container), driven through its own utils/non_linear_solver.non_linear_solver by oracle/ref_fit.py.
+_REF_CACHE = {}
 
 
-class _Deadline(Exception):
-    pass
+def _ref_scene(V, device):
+    key = (V, device)
+    if key not in _REF_CACHE:
+        import torch
+        if device == "cpu":
+            torch.set_num_threads(1)
+        from mvsmplfitting_b200 import synthetic as S
+        from oracle import ref_fit as RF
+        model, gmm, cams = S.make_model(0), S.make_gmm(7), S.make_cameras(V)
+        _REF_CACHE[key] = (model, cams, RF.build_scene(model, gmm, cams, device=device))
+    return _REF_CACHE[key]
 
 
-def _fit_one_frame_cpu(args):
-    """full 4-stage fit of ONE frame with the oracle (the reference's algorithm on CPU); returns counters.
-    An optional 4th element bounds the wall time: the fit is cut at the first closure evaluation past it and the
-    iterations completed so far are counted (bounded sample for the --impl reference arm)."""
-    seed, V, sdf = args[:3]
-    budget = args[3] if len(args) > 3 else None
-    import torch
-    torch.set_num_threads(1)
+def _ref_fit_one(args):
+    """complete 4-stage fit of ONE frame by the unmodified reference; returns (iterations, closure evals, seconds)"""
+    seed, V, sdf, device = args
+    import warnings
+    warnings.filterwarnings("ignore")
     from mvsmplfitting_b200 import synthetic as S
-    from oracle import closure_oracle as O
-    from oracle import lbfgs_oracle as L
-    key = ("scene", V)
-    if key not in _CPU_CACHE:         # model constants are built once per worker process and are not part of the timed fit
-        model = S.make_model(0)
-        gmm = S.make_gmm(7)
-        cams = S.make_cameras(V)
-        _CPU_CACHE[key] = (model, cams, O.OracleModel.from_numpy(model), O.OraclePriors.gmm_from_dict(gmm),
-                           O.cams_to_torch(cams, torch.float32))
-    model, cams, om, pri, ct = _CPU_CACHE[key]
+    from oracle import ref_fit as RF
+    model, cams, sc = _ref_scene(V, device)
     fr = S.make_frames(model, cams, 1, seed=seed)
-    x = torch.tensor(S.pack_params(fr["init"])[0])
-    iters = evals = 0
     t0 = time.time()
-    for st in stage_table():
-        cfg = O.LossConfig(interpenetration=sdf, sdf_grid=128, **st)
-
-        def fg(xx, cfg=cfg):
-            if budget is not None and time.time() - t0 > budget:
-                raise _Deadline()
-            r = O.closure_eval(om, cfg, pri, ct, xx.numpy(), fr["gt_uv"][:, 0], fr["conf"][:, 0], fr["joint_weights"])
-            return r["loss"], torch.tensor(r["grad"])
-        opt = L.LBFGSOracle(x, fg, max_iter=30)
-        try:
-            L.run_fitting(opt, 30, 1e-9, 1e-9)
-        except _Deadline:
-            return iters + opt.iters, evals + opt.evals, time.time() - t0
-        x = opt.x
-        iters += opt.iters
-        evals += opt.evals
-    return iters, evals, time.time() - t0
+    r = RF.fit_frame(sc, fr, 0, S.STAGE_WEIGHTS, interpenetration=bool(sdf))
+    return r["iterations"], r["evals"], time.time() - t0
 
 
-def _warm_cpu_worker(V):
-    import torch
-    torch.set_num_threads(1)
-    from mvsmplfitting_b200 import synthetic as S
-    from oracle import closure_oracle as O
-    key = ("scene", V)
-    if key not in _CPU_CACHE:
-        model = S.make_model(0)
-        gmm = S.make_gmm(7)
-        cams = S.make_cameras(V)
-        _CPU_CACHE[key] = (model, cams, O.OracleModel.from_numpy(model), O.OraclePriors.gmm_from_dict(gmm),
-                           O.cams_to_torch(cams, torch.float32))
-    time.sleep(1.0)          # keep this worker busy until every other worker has taken its own warm-up task
-    return True
+def _ref_warm(args):
+    V, device, do_fit = args
+    import warnings
+    warnings.filterwarnings("ignore")
+    _ref_scene(V, device)
+    dt = _ref_fit_one((999, V, 0, device))[2] if do_fit else 0.0
+    time.sleep(0.5)          # keep this worker busy until every other worker has taken its own warm-up task
+    return dt
 
 
 def cpu_baseline_sample(V, sdf, max_seconds=30.0):
-    """bounded sample: ONE frame, one host thread, full 4-stage fit (about 10-30 s of CPU work)"""
+    """bounded sample on one host core: complete 4-stage fits of 2 frames by the unmodified reference, SDF term off (the
+    reference's SDF term is a CUDA kernel: it has no CPU path), about 10-30 s of CPU work"""
     import warnings
     warnings.filterwarnings("ignore")
     try:
-        it, ev, dt = _fit_one_frame_cpu((1000, V, sdf))
+        from oracle import ref_harness as RH
+        if not RH.available():
+            return {"error": "reference tree not staged (python -m oracle.stage_reference)"}
+        it = ev = 0
+        t0 = time.time()
+        n = 0
+        for seed in (1000, 1001):
+            r = _ref_fit_one((seed, V, 0, "cpu"))
+            it += r[0]; ev += r[1]; n += 1
+            if time.time() - t0 > max_seconds:
+                break
+        dt = time.time() - t0
     except Exception as e:  # the GPU arm must not die because the checker could not run
         return {"error": repr(e)}
-    return {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "1 frame x %d views, full 4-stage fit, oracle/closure_oracle.py + oracle/lbfgs_oracle.py "
-                      "(PyTorch CPU autograd restatement of the reference), 1 thread; %d iterations, %d closure evals in %.1f s"
-                      % (V, it, ev, dt),
+    return {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "%d frame(s) x %d views, complete 4-stage fits by the UNMODIFIED reference (utils/non_linear_solver.py driving "
+                      "fitting.py / lbfgs_ls.py, torch CPU, 1 thread), SDF term off (CUDA-only in the reference); %d iterations, "
+                      "%d closure evals in %.1f s" % (n, V, it, ev, dt),
             "frame_closure_evals_per_s": ev / dt}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is a
-    Python package that cannot travel to the GPU box and its SMPL pickle is licence-gated), one process
-    per host core, one frame per process per step."""
+    """--impl reference: the reference's own implementation of the path (code/utils/non_linear_solver.py -> fitting.py,
+    lbfgs_ls.py, smplx/, camera.py, prior.py, unmodified) on the box's host cores, one process per physical core, one
+    thread each (the reference is batch-1: frames are its only parallelism).  --ref-device cuda runs the same code on
+    torch-CUDA (its shipped mode, cfg_files/fit_smpl.yaml:19) with its own SDF kernel: the secondary arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     import warnings
     warnings.filterwarnings("ignore")
-    # One process per 4 logical CPUs (32 on the 2 x 32-core / 128-thread host of the B200 boxes).  More does not help:
-    # measured on that host 64 processes give 76-94 frame-iterations/s in total (a frame then takes 80 s instead of 19 s
-    # alone -- the autograd graph of the oracle is memory-bound), and a step would not fit the few-minutes budget.
-    cores = max(1, min((os.cpu_count() or 4) // 4, args.ref_workers))
-    V, sdf = args.views, bool(args.sdf)
-    from oracle import sdf_oracle
-    sdf_oracle.build()
+    from oracle import ref_harness as RH
+    if not RH.available():
+        print(json.dumps({"impl": "reference", "unavailable": "reference tree not staged under oracle/_ref/reference "
+                                                              "(python -m oracle.stage_reference in the authoring container)"}))
+        return
+    V = args.views
+    on_cuda = args.ref_device == "cuda"
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):      # one thread per worker process, from their start
+        os.environ[k] = "1" if not on_cuda else os.environ.get(k, "8")
+    # the reference's SDF term is a CUDA kernel (sdf/sdf/csrc): on the CPU arm the term is off, on the CUDA arm it follows --sdf
+    sdf = bool(args.sdf) and on_cuda
+    cores = 1 if on_cuda else max(1, min((os.cpu_count() or 2) // 2, args.ref_workers))
     ctxm = mp.get_context("spawn")
     with ctxm.Pool(cores) as pool:
-        if args.warmup > 0:  # warm-up: every worker imports torch and builds the scene constants once (no fit: a fit is ~45 s)
-            pool.map(_warm_cpu_worker, [V] * cores, chunksize=1)
-        it = ev = 0
-        # the whole run is held to about --ref-seconds whatever K the caller picks: a step is cut after its share of it
-        step_budget = max(5.0, args.ref_seconds / max(1, args.steps))
+        # warm-up: every worker imports torch + the reference and builds the scene; with W >= 1 it also runs one complete
+        # fit, whose duration sizes the timed sample (a fit is ~10 s: W fits per worker would not fit the time budget)
+        t_fit = pool.map(_ref_warm, [(V, args.ref_device, args.warmup > 0)] * cores, chunksize=1)
+        t_f = max(1e-3, float(np.mean(t_fit))) if args.warmup > 0 else 12.0
+        # bounded sample: F complete frame fits per step, sized so that K steps fill about --ref-seconds on `cores` workers;
+        # every fit runs to completion (no wall-time cut), fits are dispatched without a barrier between steps
+        F = int(max(1, min(args.frames, np.floor(args.ref_seconds * cores / (max(1, args.steps) * t_f)))))
+        jobs = [(7000 + i, V, int(sdf), args.ref_device) for i in range(args.steps * F)]
         t0 = time.time()
-        for s in range(args.steps):
-            res = pool.map(_fit_one_frame_cpu, [(7000 + 100 * s + i, V, sdf, step_budget) for i in range(cores)], chunksize=1)
-            it += sum(r[0] for r in res)
-            ev += sum(r[1] for r in res)
+        res = list(pool.imap_unordered(_ref_fit_one, jobs, chunksize=1))
         dt = time.time() - t0
+    it, ev = sum(r[0] for r in res), sum(r[1] for r in res)
     val = it / dt
+    cfg = dict(workload_config(args.frames, V, sdf),
+               parallelism=("1 process, torch-CUDA (cuda:0)" if on_cuda else "%d host processes x 1 thread" % cores),
+               reference_arm="UNMODIFIED reference (oracle/_ref/reference: utils/non_linear_solver.py, fitting.py, lbfgs_ls.py, smplx/, "
+                             "camera.py, prior.py) on %s; %s; each step = %d complete frame fits (bounded sample of the %d-frame "
+                             "workload, no wall-time cut)" % (
+                                 "torch-CUDA with its own SDF kernel (sdf_cuda_kernel.cu compiled unchanged)" if on_cuda else "torch CPU",
+                                 "SDF term as configured" if on_cuda else "SDF term OFF: it is a CUDA-only kernel in the reference, "
+                                 "this is the only mode the reference can run on host cores (compare with aux_no_sdf of the GPU arm)",
+                                 F, args.frames))
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": dict(workload_config(args.frames, V, sdf), parallelism="%d host processes x 1 thread" % cores),
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "each step = %d frames (one per worker) x %d views, the 4-stage fit of each frame run for at most "
-                                      "%.0f s (iterations completed by then are counted; a cut fit favours the cheaper early "
-                                      "stages, i.e. the CPU), oracle port of the reference (PyTorch CPU autograd + restated "
-                                      "LBFGS/strong-Wolfe)" % (cores, V, step_budget)},
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": "%d steps x %d complete 4-stage frame fits x %d views by the unmodified reference, %s; "
+                                      "mean fit %.1f s; %d iterations, %d closure evals in %.1f s" % (
+                                          args.steps, F, V, cfg["parallelism"], float(np.mean([r[2] for r in res])), it, ev, dt)},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "frame_closure_evals_per_s": ev / dt, "gpu_launches": 0}
+           "frame_closure_evals_per_s": ev / dt, "evals_per_iteration": ev / max(it, 1),
+           "iterations_per_frame": it / max(len(res), 1), "gpu_launches": 0}
     print(json.dumps(out))
 
 
@@ -466,8 +470,10 @@ def main():
     ap.add_argument("--sdf", type=int, default=1)
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--cpu-seconds", type=float, default=30.0)
-    ap.add_argument("--ref-workers", type=int, default=32)
-    ap.add_argument("--ref-seconds", type=float, default=240.0, help="wall-time bound of the --impl reference run")
+    ap.add_argument("--ref-workers", type=int, default=32, help="host processes of the reference arm (capped at the physical cores; "
+                    "32 on the 64-core B200 hosts: more saturate the memory system, measured in round 1)")
+    ap.add_argument("--ref-seconds", type=float, default=200.0, help="target wall time of the --impl reference run (sizes the sample)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: host cores (default) or torch-CUDA")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

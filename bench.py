@@ -194,7 +194,8 @@ def run_ours(args):
     share = ctx.profile_read()
     ctx.profile(0)
     dom = max(share, key=lambda k: share[k][0]) if share else "vertex_fwd"
-    names = [ctx.lib.mvs_kernel_name(k).decode() for k in range(18)]
+    from mvsmplfitting_b200 import _lib as _L
+    names = [ctx.lib.mvs_kernel_name(k).decode() for k in range(_L.NUM_KERNEL_IDS)]
     dom_mask = 1 << names.index(dom)
 
     sampler = ClockSampler(local)

@@ -138,14 +138,14 @@ struct FrameBox {                     // bounding box of one frame's mesh (fitti
 // 16: 76 -- the few expensive blocks near the cone must not pile up in one CTA, and small CTAs balance better than the
 // shorter prologue of large ones saves.
 constexpr int kSdfMaxPasses = 8;
-inline int sdf_passes_for(int na, int nblocks, int cta_slots) {
+__host__ __device__ inline int sdf_passes_for(int na, int nblocks, int cta_slots) {
     return (long long)na * nblocks > 2LL * cta_slots ? 2 : 1;
 }
 
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
-    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_SKIN, KID_COUNT
+    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_SKIN, KID_DENSE_ROUNDS, KID_COUNT
 };
 static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
 
@@ -176,6 +176,7 @@ struct mvs_ctx {
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
     mvs::Profiler prof;
     void* tc = nullptr;              // tensor-core path state (mvs_tc.cu)
+    void* dense = nullptr;           // persistent dense-round state (mvs_dense.cu)
 };
 
 namespace mvs {
@@ -266,12 +267,19 @@ int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
 int tc_check_error(mvs_ctx* ctx);
+float* tc_poffT(mvs_ctx* ctx);                 // [3N][ldA] pose offsets of the tensor-core contraction (allocated on first use)
+int tc_prepare(mvs_ctx* ctx);                  // tensor maps + pose-offset buffer (idempotent)
 int launch_frame_step(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
                       cudaStream_t st);
 int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st);                 // mvs_resident.cu
 int launch_frame_fwd_dense(mvs_ctx* ctx, const float* x_dev, const void* lbfgs_state, int nstages, cudaStream_t st);   // mvs_resident.cu
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
+// mvs_dense.cu: the dense rounds of a run as one persistent cooperative kernel
+bool dense_persistent_available(const mvs_ctx* ctx);
+int run_dense_persistent(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
+                         long long max_rounds, cudaStream_t st);
+long long dense_last_rounds(const mvs_ctx* ctx);
 int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, cudaStream_t st);   // mvs_lbfgs.cu
 int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,

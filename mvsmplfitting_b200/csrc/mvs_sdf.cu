@@ -20,81 +20,9 @@
 #include <cstdlib>
 #include "mvs_internal.cuh"
 #include "mvs_lbfgs_core.cuh"
+#include "mvs_sdf_dev.cuh"
 
 namespace mvs {
-
-// ---------------------------------------------------------------------------------- geometry (float, as the reference)
-__device__ __forceinline__ float dist3(const float* a, const float* b) {
-    const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
-    return sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-}
-__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-
-// sdf_cuda_kernel.cu:73-92
-__device__ __forceinline__ float segment_distance(const float* x0, const float* x1, const float* x2, float* r) {
-    const float dx[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-    const float m2 = dot3(dx, dx);
-    float s12 = (dot3(x2, dx) - dot3(x0, dx)) / m2;
-    s12 = s12 < 0.f ? 0.f : (s12 > 1.f ? 1.f : s12);
-    r[0] = s12 * x1[0] + (1.f - s12) * x2[0];
-    r[1] = s12 * x1[1] + (1.f - s12) * x2[1];
-    r[2] = s12 * x1[2] + (1.f - s12) * x2[2];
-    return dist3(x0, r);
-}
-// sdf_cuda_kernel.cu:155-237 (closest point), returns the distance
-__device__ __forceinline__ float triangle_distance(const float* x0, const float* x1, const float* x2, const float* x3) {
-    float x13[3], x23[3], x03[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { x13[i] = x1[i] - x3[i]; x23[i] = x2[i] - x3[i]; x03[i] = x0[i] - x3[i]; }
-    const float m13 = dot3(x13, x13), m23 = dot3(x23, x23), d = dot3(x13, x23);
-    const float invdet = 1.f / fmaxf(m13 * m23 - d * d, 1e-30f);
-    const float a = dot3(x13, x03), b = dot3(x23, x03);
-    const float w23 = invdet * (m23 * a - d * b);
-    const float w31 = invdet * (m13 * b - d * a);
-    const float w12 = 1.f - w23 - w31;
-    float r[3];
-    if (w23 >= 0.f && w31 >= 0.f && w12 >= 0.f) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = w23 * x1[i] + w31 * x2[i] + w12 * x3[i];
-        return dist3(x0, r);
-    }
-    float r2[3], d1, d2;
-    if (w23 > 0.f) { d1 = segment_distance(x0, x1, x2, r); d2 = segment_distance(x0, x1, x3, r2); }
-    else if (w31 > 0.f) { d1 = segment_distance(x0, x1, x2, r); d2 = segment_distance(x0, x2, x3, r2); }
-    else { d1 = segment_distance(x0, x1, x3, r); d2 = segment_distance(x0, x2, x3, r2); }
-    // the reference returns the closest POINT and the caller re-measures the distance to it (:281-282)
-    return (d1 < d2) ? dist3(x0, r) : dist3(x0, r2);
-}
-// sdf_cuda_kernel.cu:95-150: ray from the voxel centre towards (-1,-1,-1); hit counted iff t >= 0
-__device__ __forceinline__ bool ray_hits(const float* c, const float* v0, const float* v1, const float* v2) {
-    const float dir[3] = {-1.f - c[0], -1.f - c[1], -1.f - c[2]};
-    float e1[3], e2[3], tv[3], pv[3], qv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { e1[i] = v1[i] - v0[i]; e2[i] = v2[i] - v0[i]; }
-    pv[0] = dir[1] * e2[2] - dir[2] * e2[1];
-    pv[1] = dir[2] * e2[0] - dir[0] * e2[2];
-    pv[2] = dir[0] * e2[1] - dir[1] * e2[0];
-    const float det = dot3(e1, pv);
-    if (det > -1e-6 && det < 1e-6) return false;
-    const float inv_det = (float)(1.0 / (double)det);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) tv[i] = c[i] - v0[i];
-    const float u = dot3(tv, pv) * inv_det;
-    if (u < 0.f || u > 1.f) return false;
-    qv[0] = tv[1] * e1[2] - tv[2] * e1[1];
-    qv[1] = tv[2] * e1[0] - tv[0] * e1[2];
-    qv[2] = tv[0] * e1[1] - tv[1] * e1[0];
-    const float v = dot3(dir, qv) * inv_det;
-    if (v < 0.f || (u + v) > 1.f) return false;
-    const float t = dot3(e2, qv) * inv_det;
-    return t >= 0.f;
-}
-__device__ __forceinline__ void voxel_centre(int i, int j, int k, int G, float* c) {     // sdf_cuda_kernel.cu:260-263
-    const float dx = (float)(2. / (G - 1));
-    c[0] = (float)(-1 + (i + 0.5) * dx);
-    c[1] = (float)(-1 + (j + 0.5) * dx);
-    c[2] = (float)(-1 + (k + 0.5) * dx);
-}
 
 // ---------------------------------------------------------------------------------- the reference op: full grid
 constexpr int kSdfThreads = 512;
@@ -338,462 +266,17 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
     o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
 }
 
-// ---------------------------------------------------------------------------------- dense regime, v4: fused adjoint
-// sdf_fused_kernel: P CTAs per frame, 1, 2 or 4 blocks of 256 vertices each.  Per CTA: fold the skinning kernel's box partials (all
-// threads), sample phi at the <= 8 voxels around each vertex, compact the vertices with a non-zero sample gradient
-// (deterministic order: warp, pass, lane) and -- because with the as-written semantics that list holds a handful of
-// vertices -- run the adjoint of the vertex stage for exactly those vertices right here:
-//     d v_posed = T_3x3^T g,   dA_j += W[n,j] [g (x) v_posed | g],   dPhi += d v_posed . Qk[rows of n]
-// with g = d value / d local (UNIT scale; the frame factor cg/scale is linear and applied by frame_step once the
-// frame's total is known).
-constexpr int kSdfFThreads = 256;
-constexpr int kSdfFChunk = 128;                              // list entries per adjoint pass
-
-__device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, const int* __restrict__ faces,
-                                              const float* __restrict__ vf, const float* tr, const FrameBox& fb,
-                                              const float* tri0) {
-    if (num_faces == 1) {
-        if (!ray_hits(c, tri0, tri0 + 3, tri0 + 6)) return 0.f;
-        return triangle_distance(c, tri0, tri0 + 3, tri0 + 6);
-    }
-    int hits = 0;
-    float min_d = 1000.f;
-    for (int f = 0; f < num_faces; ++f) {
-        float p[9];
-#pragma unroll
-        for (int r = 0; r < 9; ++r)
-            p[r] = ((vf[3 * faces[3 * f + r / 3] + r % 3] + tr[r % 3]) - fb.centre[r % 3]) / fb.scale;
-        const float dd = triangle_distance(c, p, p + 3, p + 6);
-        if (dd < min_d) min_d = dd;
-        if (ray_hits(c, p, p + 3, p + 6)) ++hits;
-    }
-    return (hits % 2 == 0) ? 0.f : min_d;
-}
-
 __global__ void __launch_bounds__(kSdfFThreads, 3)
-sdf_fused_kernel(const float* __restrict__ verts, const float* __restrict__ vposed, const float* __restrict__ slot_tr,
-                 const int* __restrict__ na_ptr, int N, int nbox, const float* __restrict__ bboxp,
-                 const int* __restrict__ faces, int num_faces, int f0, int f1, int f2, int G,
-                 const float* __restrict__ At, int ldA, const int* __restrict__ ell_j, const float* __restrict__ ell_w,
-                 int KW, const float* __restrict__ Wd, const float* __restrict__ Qk, float* __restrict__ parts5,
-                 float* __restrict__ part, int* __restrict__ pflag, FrameBox* __restrict__ boxout, int passes,
-                 float* __restrict__ gcoord) {
+sdf_fused_kernel(SdfFusedArgs ar, const int* __restrict__ na_ptr, int passes) {
     pdl_wait();
-    const int slot = blockIdx.y, pidx = blockIdx.x;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // every load of the prologue is addressed by the slot alone (no slot -> frame -> state chain): one round trip
-    const float* vf = verts + (size_t)slot * N * 3;
-    const int na = *na_ptr;
-    const float4 tr4 = *reinterpret_cast<const float4*>(slot_tr + 4 * slot);
-    float traw[9];
-    {
-        const int fid[3] = {f0, f1, f2};
-#pragma unroll
-        for (int q = 0; q < 9; ++q) traw[q] = vf[3 * fid[q / 3] + q % 3];
-    }
-    if (slot >= na) return;
-    if (pidx * passes * kSdfFThreads >= N) return;
-    const float tr[3] = {tr4.x, tr4.y, tr4.z};
-    __shared__ float s_wb[8][6];
-    __shared__ int s_wi[8][6];
-    __shared__ float ctab[256];
-    __shared__ float s_red[kSdfMaxPasses][8][5];
-    __shared__ int s_wcnt[kSdfMaxPasses][8], s_woff[kSdfMaxPasses][9];
-    __shared__ unsigned s_mask[kSdfMaxPasses][8];
-    __shared__ int seg_n[kSdfFThreads];               // one block's vertices with a non-zero sample gradient
-    __shared__ float seg_g[kSdfFThreads * 3];
-    __shared__ float sA[kSkinFloats];
-    __shared__ int c_n[kSdfFChunk];
-    __shared__ float c_dv[kSdfFChunk * 3], c_vp[kSdfFChunk * 3], c_dvp[kSdfFChunk * 3];
-    __shared__ float s_dphi[8][kFeatPad];
-    __shared__ float s_ch[256][6];                    // the skinning kernel's per-64-vertex boxes (pre-transl lo | hi)
-    // ---- bounding box: every thread takes one partial, warps fold with shuffles (ties -> lowest vertex index)
-    {
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-        int ilo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, ihi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-        for (int tl = t; tl < nbox; tl += kSdfFThreads) {
-            const float* bp = bboxp + ((size_t)slot * nbox + tl) * 12;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float l2 = bp[c], h2 = bp[3 + c];
-                const int il2 = __float_as_int(bp[6 + c]), ih2 = __float_as_int(bp[9 + c]);
-                if (l2 < lo[c] || (l2 == lo[c] && il2 < ilo[c])) { lo[c] = l2; ilo[c] = il2; }
-                if (h2 > hi[c] || (h2 == hi[c] && ih2 < ihi[c])) { hi[c] = h2; ihi[c] = ih2; }
-                if (tl < 256) { s_ch[tl][c] = l2; s_ch[tl][3 + c] = h2; }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { warp_argmin(lo[c], ilo[c]); warp_argmax(hi[c], ihi[c]); }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { s_wb[warp][c] = lo[c]; s_wb[warp][3 + c] = hi[c]; s_wi[warp][c] = ilo[c]; s_wi[warp][3 + c] = ihi[c]; }
-        }
-        if (t < G && t < 256) ctab[t] = (float)(-1 + (t + 0.5) * (double)(float)(2. / (G - 1)));   // voxel_centre, tabulated
-    }
-    __syncthreads();
-    // every warp folds the eight warp boxes itself (each lane holds one of them): no second barrier
-    FrameBox fb;
-    {
-        const int wsrc = lane & 7;
-        float lo[3], hi[3];
-        int ilo[3], ihi[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { lo[c] = s_wb[wsrc][c]; hi[c] = s_wb[wsrc][3 + c]; ilo[c] = s_wi[wsrc][c]; ihi[c] = s_wi[wsrc][3 + c]; }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { warp_argmin(lo[c], ilo[c]); warp_argmax(hi[c], ihi[c]); }
-        float ext = -1.f;
-        fb.cmax = 0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            // the partials are on pre-transl vertices; fl(v + tr) is monotone in v, so min/max and their
-            // arg-indices commute with the translation (body_models_scale.py:403)
-            const float lc = lo[c] + tr[c], hc = hi[c] + tr[c];
-            fb.centre[c] = (lc + hc) / 2.f;
-            fb.ilo[c] = ilo[c]; fb.ihi[c] = ihi[c];
-            const float e = hc - lc;
-            if (e > ext) { ext = e; fb.cmax = c; }
-        }
-        fb.scale = 0.6f * ext;
-        fb.pad = 0.f;
-        if (pidx == 0 && t == 0) boxout[slot] = fb;
-    }
-    // triangle 0 in box coordinates (fitting.py:362-363) and the cone it spans from the corner (-1,-1,-1): per thread,
-    // in registers (identical values in every thread)
-    float tri[9], cn[3][3], cm[3];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) tri[q] = ((traw[q] + tr[q % 3]) - fb.centre[q % 3]) / fb.scale;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const float* a = &tri[3 * q];
-        const float* bb = &tri[3 * ((q + 1) % 3)];
-        const float ea[3] = {a[0] + 1.f, a[1] + 1.f, a[2] + 1.f}, eb[3] = {bb[0] + 1.f, bb[1] + 1.f, bb[2] + 1.f};
-        cn[q][0] = ea[1] * eb[2] - ea[2] * eb[1]; cn[q][1] = ea[2] * eb[0] - ea[0] * eb[2]; cn[q][2] = ea[0] * eb[1] - ea[1] * eb[0];
-        cm[q] = 3.5e-4f * sqrtf(cn[q][0] * cn[q][0] + cn[q][1] * cn[q][1] + cn[q][2] * cn[q][2]);
-    }
-    // plane of triangle 0 in the same shifted coordinates (w = centre + 1, the corner is the origin): the ray from a
-    // voxel centre to the corner can only cross the triangle if the two lie on opposite sides of this plane, i.e.
-    // <pn, w> - pd has the sign of pd.  Voxels between the corner and the triangle pass the cone test but fail this one.
-    float pn[3], pd, pm;
-    {
-        const float e1[3] = {tri[3] - tri[0], tri[4] - tri[1], tri[5] - tri[2]}, e2[3] = {tri[6] - tri[0], tri[7] - tri[1], tri[8] - tri[2]};
-        pn[0] = e1[1] * e2[2] - e1[2] * e2[1]; pn[1] = e1[2] * e2[0] - e1[0] * e2[2]; pn[2] = e1[0] * e2[1] - e1[1] * e2[0];
-        pd = pn[0] * (tri[0] + 1.f) + pn[1] * (tri[1] + 1.f) + pn[2] * (tri[2] + 1.f);
-        pm = 2e-3f * sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);      // conservative: |w| <= 2 sqrt 3, fp32 rounding
-    }
-    // vertex-level early-out: the 8 voxel centres a vertex at `loc` can touch lie within +-vhalf of (loc + 1) G/(G-1) on
-    // every axis, so each plane function varies by at most vhalf * |n|_1 over them
-    const float vgs = (float)G / (float)(G - 1), vhalf = 2.02f / (float)(G - 1) + 1e-5f;
-    float vpad[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) vpad[q] = vhalf * (fabsf(cn[q][0]) + fabsf(cn[q][1]) + fabsf(cn[q][2]));
-    const float vpadp = vhalf * (fabsf(pn[0]) + fabsf(pn[1]) + fabsf(pn[2]));
-    // ---- sampling: block (pidx * passes + pass) of 256 vertices per pass, one vertex per thread and pass.  Sums,
-    //      vertex lists and adjoint partials are emitted PER BLOCK, so the arithmetic of a frame does not depend on
-    //      how many blocks this launch gave to one CTA (i.e. not on how many other frames are still active): frames
-    //      stay bit-for-bit independent problems.  All passes are sampled before the first barrier.
-    const bool cull = (num_faces == 1);
-    const bool tab = (G <= 256);
-    const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
-    // Chunk-level cull: the skinning kernel left the box of every 64 consecutive vertices.  The voxel centres a vertex
-    // at `loc` can touch lie within (loc + 1) G/(G-1) +- 2/(G-1) (+1 shifted); if that whole box is on the negative
-    // side of one cone plane and on the positive side of another, no vertex of the chunk can see a voxel with
-    // phi != 0: value and gradient are exactly zero and its two warps skip loads, divisions, corners.  Lane p of a
-    // warp tests the warp's chunk of pass p once; the pass loop reads the verdict with a shuffle.
-    bool my_skip = false;
-    if (lane < passes) {
-        const int chunk = ((pidx * passes + lane) * kSdfFThreads + warp * 32) / 64;
-        if (cull && nbox <= 256 && chunk < nbox) {
-            const float gs = (float)G / (float)(G - 1), pad = 2.02f / (float)(G - 1) + 1e-5f;
-            float wlo[3], whi[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float l_lo = ((s_ch[chunk][c] + tr[c]) - fb.centre[c]) / fb.scale;
-                const float l_hi = ((s_ch[chunk][3 + c] + tr[c]) - fb.centre[c]) / fb.scale;
-                wlo[c] = (l_lo + 1.f) * gs - pad; whi[c] = (l_hi + 1.f) * gs + pad;
-            }
-            bool all_neg = false, all_pos = false;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                float smin = 0.f, smax = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float a = cn[q][c] * wlo[c], b2 = cn[q][c] * whi[c];
-                    smin += fminf(a, b2); smax += fmaxf(a, b2);
-                }
-                all_neg = all_neg || (smax < -cm[q]);
-                all_pos = all_pos || (smin > cm[q]);
-            }
-            my_skip = all_neg && all_pos;
-        }
-    }
-    float vcur[3] = {0.f, 0.f, 0.f};                   // this pass' vertex; the next one is fetched a pass ahead
-    {
-        const int n0 = pidx * passes * kSdfFThreads + t;
-        if (n0 < N) { vcur[0] = vf[3 * n0]; vcur[1] = vf[3 * n0 + 1]; vcur[2] = vf[3 * n0 + 2]; }
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < passes; ++pass) {
-        const int blk = pidx * passes + pass;
-        if (blk >= nblocks) { if (lane == 0) s_wcnt[pass][warp] = 0; continue; }
-        const int n = blk * kSdfFThreads + t;
-        const float vme[3] = {vcur[0], vcur[1], vcur[2]};
-        if (pass + 1 < passes && n + kSdfFThreads < N) {
-            vcur[0] = vf[3 * (n + kSdfFThreads)]; vcur[1] = vf[3 * (n + kSdfFThreads) + 1]; vcur[2] = vf[3 * (n + kSdfFThreads) + 2];
-        }
-        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float gcv[3] = {0.f, 0.f, 0.f};
-        const bool skip = __shfl_sync(0xffffffffu, (int)my_skip, pass) != 0;
-        if (n < N && !skip) {
-            float loc[3], w1[3];
-            int i0[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                loc[c] = ((vme[c] + tr[c]) - fb.centre[c]) / fb.scale;
-                const float ix = ((loc[c] + 1.f) * G - 1.f) / 2.f;
-                const float fl = floorf(ix);
-                i0[c] = (int)fl;
-                w1[c] = ix - fl;
-            }
-            bool vout = false;                             // no voxel this vertex touches can have phi != 0
-            if (cull) {
-                const float wc[3] = {(loc[0] + 1.f) * vgs, (loc[1] + 1.f) * vgs, (loc[2] + 1.f) * vgs};
-                bool any_neg = false, any_pos = false;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float sq = cn[q][0] * wc[0] + cn[q][1] * wc[1] + cn[q][2] * wc[2];
-                    any_neg = any_neg || (sq + vpad[q] < -cm[q]);
-                    any_pos = any_pos || (sq - vpad[q] > cm[q]);
-                }
-                const float sp = pn[0] * wc[0] + pn[1] * wc[1] + pn[2] * wc[2] - pd;
-                vout = (any_neg && any_pos) || (pd > pm && sp + vpadp < -pm) || (pd < -pm && sp - vpadp > pm);
-            }
-            float val = 0.f, dix[3] = {0.f, 0.f, 0.f};
-            if (!vout) {
-                // voxel centres of the 2 x 2 x 2 cell and, per cone plane, the per-axis parts of <centre + 1, normal>:
-                // a corner's three plane distances are then two adds each
-                float cx[2], cy[2], cz[2], px[3][2], py[3][2], pz[3][2];
-#pragma unroll
-                for (int o = 0; o < 2; ++o) {
-                    const int ii = min(max(i0[0] + o, 0), G - 1), jj = min(max(i0[1] + o, 0), G - 1), kk = min(max(i0[2] + o, 0), G - 1);
-                    if (tab) { cx[o] = ctab[ii]; cy[o] = ctab[jj]; cz[o] = ctab[kk]; }
-                    else { float c3[3]; voxel_centre(ii, jj, kk, G, c3); cx[o] = c3[0]; cy[o] = c3[1]; cz[o] = c3[2]; }
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        px[q][o] = (cx[o] + 1.f) * cn[q][0]; py[q][o] = (cy[o] + 1.f) * cn[q][1]; pz[q][o] = (cz[o] + 1.f) * cn[q][2];
-                    }
-                }
-                // whole-cell test first: the extreme plane distances over the 8 corners are sums of per-axis extremes; if
-                // one plane has every corner outside (negative) and another every corner on its positive side, no corner
-                // can be inside the cone -- true for almost every vertex -- and the corner loop is skipped
-                float qx[2], qy[2], qz[2];
-#pragma unroll
-                for (int o = 0; o < 2; ++o) { qx[o] = (cx[o] + 1.f) * pn[0]; qy[o] = (cy[o] + 1.f) * pn[1]; qz[o] = (cz[o] + 1.f) * pn[2]; }
-                bool cell_out = false;
-                if (cull) {
-                    // plane side of the whole cell
-                    const float smaxp = fmaxf(qx[0], qx[1]) + fmaxf(qy[0], qy[1]) + fmaxf(qz[0], qz[1]) - pd;
-                    const float sminp = fminf(qx[0], qx[1]) + fminf(qy[0], qy[1]) + fminf(qz[0], qz[1]) - pd;
-                    if ((pd > pm && smaxp < -pm) || (pd < -pm && sminp > pm)) cell_out = true;
-                    bool any_neg = false, any_pos = false;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const float smax = fmaxf(px[q][0], px[q][1]) + fmaxf(py[q][0], py[q][1]) + fmaxf(pz[q][0], pz[q][1]);
-                        const float smin = fminf(px[q][0], px[q][1]) + fminf(py[q][0], py[q][1]) + fminf(pz[q][0], pz[q][1]);
-                        any_neg = any_neg || (smax < -cm[q]);
-                        any_pos = any_pos || (smin > cm[q]);
-                    }
-                    cell_out = cell_out || (any_neg && any_pos);
-                }
-#pragma unroll
-                for (int corner = 0; corner < 8; ++corner) {
-                    if (cell_out) break;
-                    const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
-                    const int ii = i0[0] + ox, jj = i0[1] + oy, kk = i0[2] + oz;
-                    if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
-                    if (cull) {
-                        // phi != 0 needs the ray from the voxel centre to (-1,-1,-1) to cross triangle 0, i.e. the centre
-                        // inside the cone the triangle spans from that corner: on the same side of its three planes.
-                        // Conservative margin (|centre + 1| <= 2 sqrt 3): only voxels safely outside are skipped, every
-                        // other one is decided exactly by ray_hits.
-                        const float s1 = px[0][ox] + py[0][oy] + pz[0][oz];
-                        const float s2 = px[1][ox] + py[1][oy] + pz[1][oz];
-                        const float s3 = px[2][ox] + py[2][oy] + pz[2][oz];
-                        const bool neg = (s1 < -cm[0]) || (s2 < -cm[1]) || (s3 < -cm[2]);
-                        const bool pos = (s1 > cm[0]) || (s2 > cm[1]) || (s3 > cm[2]);
-                        if (neg && pos) continue;
-                        const float sp = qx[ox] + qy[oy] + qz[oz] - pd;
-                        if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
-                    }
-                    const float cc[3] = {cx[ox], cy[oy], cz[oz]};
-                    const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
-                    if (p == 0.f) continue;
-                    const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
-                    val += p * wx * wy * wz;
-                    dix[0] += p * (ox ? 1.f : -1.f) * wy * wz;
-                    dix[1] += p * wx * (oy ? 1.f : -1.f) * wz;
-                    dix[2] += p * wx * wy * (oz ? 1.f : -1.f);
-                }
-            }
-            float gdl = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                gcv[c] = dix[c] * (0.5f * G);
-                acc[1 + c] = gcv[c]; gdl += gcv[c] * loc[c];
-            }
-            acc[0] = val;
-            acc[4] = gdl;
-        }
-        const bool nz = (gcv[0] != 0.f) || (gcv[1] != 0.f) || (gcv[2] != 0.f);
-        const unsigned nzm = __ballot_sync(0xffffffffu, nz);
-        if (nz) {                                          // rare: parked in global scratch until the adjoint phase
-            float* gp = gcoord + ((size_t)slot * N + n) * 3;
-            gp[0] = gcv[0]; gp[1] = gcv[1]; gp[2] = gcv[2];
-        }
-        // almost every warp is outside the cone: all-zero contributions need no shuffle tree (adding zeros is exact)
-        if (__ballot_sync(0xffffffffu, acc[0] != 0.f || nz)) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                float a = acc[q];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0) s_red[pass][warp][q] = a;
-            }
-        } else if (lane < 5) {
-            s_red[pass][warp][lane] = 0.f;
-        }
-        if (lane == 0) { s_wcnt[pass][warp] = __popc(nzm); s_mask[pass][warp] = nzm; }
-    }
-    __syncthreads();
-    if (t < 5 * passes) {
-        const int pass = t / 5, q = t % 5, blk = pidx * passes + pass;
-        if (blk < nblocks) {
-            float a = 0.f;
-            for (int w2 = 0; w2 < 8; ++w2) a += s_red[pass][w2][q];
-            parts5[((size_t)slot * nblocks + blk) * 5 + q] = a;
-        }
-    } else if (t >= 128 && t < 128 + passes) {
-        const int pass = t - 128, blk = pidx * passes + pass;
-        int o = 0;
-        if (blk < nblocks) {
-            for (int w2 = 0; w2 < 8; ++w2) { s_woff[pass][w2] = o; o += s_wcnt[pass][w2]; }
-            pflag[(size_t)slot * nblocks + blk] = o > 0 ? 1 : 0;
-        }
-        s_woff[pass][8] = o;
-    }
-    __syncthreads();
-    // ---- adjoint of the vertex stage for the listed vertices of each block (unit frame factor); rare
-    bool have_A = false;
-#pragma unroll 1
-    for (int pass = 0; pass < passes; ++pass) {
-        const int blk = pidx * passes + pass;
-        const int total = s_woff[pass][8];
-        if (total == 0) continue;
-        __syncthreads();                                   // the previous block's adjoint is done with seg_* / c_*
-        const unsigned nzm = s_mask[pass][warp];
-        if (nzm & (1u << lane)) {                          // ascending vertex order: (warp, lane)
-            const int pos = s_woff[pass][warp] + __popc(nzm & ((1u << lane) - 1u));
-            seg_n[pos] = blk * kSdfFThreads + t;
-            const float* gp = gcoord + ((size_t)slot * N + blk * kSdfFThreads + t) * 3;       // written by this thread
-            seg_g[3 * pos] = gp[0]; seg_g[3 * pos + 1] = gp[1]; seg_g[3 * pos + 2] = gp[2];
-        }
-        if (!have_A) {
-            for (int e = t; e < kSkinFloats; e += kSdfFThreads) sA[e] = At[(size_t)e * ldA + slot];
-            have_A = true;
-        }
-        float accA0 = 0.f, accA1 = 0.f;
-        float accP[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // d Phi[lane + 32 i], this warp's share of the columns
-        for (int e0 = 0; e0 < total; e0 += kSdfFChunk) {
-            const int cnt = min(kSdfFChunk, total - e0);
-            __syncthreads();
-            if (t < cnt) {
-                const int src = e0 + t;
-                const int nn = seg_n[src];
-                c_n[t] = nn;
-                const float d0 = seg_g[3 * src], d1 = seg_g[3 * src + 1], d2 = seg_g[3 * src + 2];
-                float Gm[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) Gm[c] = 0.f;
-                for (int e = 0; e < KW; ++e) {
-                    const float w = ell_w[(size_t)nn * KW + e];
-                    if (w != 0.f) {
-                        const float* Aj = &sA[12 * ell_j[(size_t)nn * KW + e]];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) Gm[3 * r + c] = fmaf(w, Aj[4 * r + c], Gm[3 * r + c]);
-                    }
-                }
-                c_dv[3 * t] = d0; c_dv[3 * t + 1] = d1; c_dv[3 * t + 2] = d2;
-                c_dvp[3 * t] = Gm[0] * d0 + Gm[3] * d1 + Gm[6] * d2;
-                c_dvp[3 * t + 1] = Gm[1] * d0 + Gm[4] * d1 + Gm[7] * d2;
-                c_dvp[3 * t + 2] = Gm[2] * d0 + Gm[5] * d1 + Gm[8] * d2;
-                const float* vpn = vposed + ((size_t)slot * N + nn) * 3;
-                c_vp[3 * t] = vpn[0]; c_vp[3 * t + 1] = vpn[1]; c_vp[3 * t + 2] = vpn[2];
-            }
-            __syncthreads();
-            {   // dA: thread t owns entry t (and 256 + t for t < 32)
-                const int j0 = t / 12, r0 = (t % 12) / 4, cc0 = t % 4;
-                const int e1 = t + kSdfFThreads, j1 = e1 / 12, r1 = (e1 % 12) / 4, cc1 = e1 % 4;
-                const bool two = t < kSkinFloats - kSdfFThreads;
-#pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    const float* wrow = Wd + (size_t)c_n[i] * kJoints;
-                    const float w0 = __ldg(wrow + j0);
-                    const float w1v = two ? __ldg(wrow + j1) : 0.f;
-                    if (w0 != 0.f) {
-                        const float wd = w0 * c_dv[3 * i + r0];
-                        accA0 = (cc0 < 3) ? fmaf(wd, c_vp[3 * i + cc0], accA0) : accA0 + wd;
-                    }
-                    if (w1v != 0.f) {
-                        const float wd = w1v * c_dv[3 * i + r1];
-                        accA1 = (cc1 < 3) ? fmaf(wd, c_vp[3 * i + cc1], accA1) : accA1 + wd;
-                    }
-                }
-            }
-            // d Phi: a warp takes every 8th column and reads its whole Qk row (7 coalesced loads per lane, two columns
-            // = 14 independent loads in flight); the eight warps' shares are folded in a fixed order below
-            for (int col = warp; col < 3 * cnt; col += 16) {
-                const int colb = col + 8;
-                const bool hb = colb < 3 * cnt;
-                const float* ra = Qk + (size_t)(3 * c_n[col / 3] + col % 3) * kFeatPad + lane;
-                const float* rb = Qk + (size_t)(3 * c_n[(hb ? colb : col) / 3] + (hb ? colb : col) % 3) * kFeatPad + lane;
-                float qa[7], qb[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) { qa[i] = __ldg(ra + 32 * i); qb[i] = __ldg(rb + 32 * i); }
-                const float da = c_dvp[col], db = hb ? c_dvp[colb] : 0.f;
-#pragma unroll
-                for (int i = 0; i < 7; ++i) { accP[i] = fmaf(da, qa[i], accP[i]); accP[i] = fmaf(db, qb[i], accP[i]); }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 7; ++i) s_dphi[warp][lane + 32 * i] = accP[i];
-        __syncthreads();
-        float* o = part + ((size_t)slot * nblocks + blk) * kPartFloats;
-        o[t] = accA0;
-        if (t < kSkinFloats - kSdfFThreads) o[kSdfFThreads + t] = accA1;
-        if (t < kFeatPad) {
-            float a = 0.f;
-#pragma unroll
-            for (int w2 = 0; w2 < 8; ++w2) a += s_dphi[w2][t];
-            o[kSkinFloats + t] = a;
-        }
-    }
+    __shared__ SdfFusedSmem sm;
+    sdf_fused_body(sm, ar, *na_ptr, (int)blockIdx.y, (int)blockIdx.x, passes);
 }
 
-int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
+int ensure_sdf_fused_ws(mvs_ctx* ctx) {
     Workspace& w = ctx->ws;
-    const DevModel& m = ctx->m;
-    const LossParams& lp = ctx->loss;
-    const int B = w.B, N = m.N;
-    const int nb = w.na_bound > 0 ? w.na_bound : B;    // host-side upper bound of the active-frame count
+    const int B = w.B, N = ctx->m.N;
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
-    // 256-vertex blocks per CTA (1 at the tail, 2 in the bulk; see sdf_passes_for)
-    int passes = sdf_passes_for(nb, nblocks, 3 * ctx->sm_count);
-    {   // tuning knob (experiments only): MVS_SDF_PASSES=n forces n blocks per CTA
-        static const int forced = getenv("MVS_SDF_PASSES") ? atoi(getenv("MVS_SDF_PASSES")) : 0;
-        if (forced >= 1 && forced <= kSdfMaxPasses) passes = forced;
-    }
-    const int nparts = (nblocks + passes - 1) / passes;
     int rc;
     if (!w.sdf_gcoord && (rc = dev_alloc(ctx, &w.sdf_gcoord, (size_t)B * N * 3))) return rc;
     if (!w.sdf_parts5) {
@@ -806,14 +289,42 @@ int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
         if ((rc = dev_alloc(ctx, &raw, (size_t)B * sizeof(FrameBox)))) return rc;
         w.sdf_box = raw;
     }
+    return MVS_OK;
+}
+
+SdfFusedArgs make_sdf_fused_args(mvs_ctx* ctx) {
+    Workspace& w = ctx->ws;
+    const DevModel& m = ctx->m;
+    const LossParams& lp = ctx->loss;
+    SdfFusedArgs a;
+    a.verts = w.verts; a.poffT = tc_poffT(ctx); a.Phi = w.Phi; a.ST = m.ST; a.slot_tr = w.slot_tr;
+    a.N = m.N; a.nbox = (m.N + 63) / 64; a.bboxp = w.bboxp; a.faces = m.faces; a.num_faces = lp.sdf_all_faces ? m.F : 1;
+    a.f0 = m.tri0[0]; a.f1 = m.tri0[1]; a.f2 = m.tri0[2]; a.G = lp.sdf_grid;
+    a.At = w.At; a.ldA = w.ldA; a.ell_j = m.ell_j; a.ell_w = m.ell_w; a.KW = m.KW; a.Wd = m.Wd; a.Qk = m.Qk;
+    a.parts5 = w.sdf_parts5; a.part = w.sdf_part; a.pflag = w.sdf_pflag; a.boxout = reinterpret_cast<FrameBox*>(w.sdf_box);
+    a.gcoord = w.sdf_gcoord;
+    return a;
+}
+
+int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
+    Workspace& w = ctx->ws;
+    const DevModel& m = ctx->m;
+    const int B = w.B, N = m.N;
+    const int nb = w.na_bound > 0 ? w.na_bound : B;    // host-side upper bound of the active-frame count
+    const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
+    // 256-vertex blocks per CTA (1 at the tail, 2 in the bulk; see sdf_passes_for)
+    int passes = sdf_passes_for(nb, nblocks, 3 * ctx->sm_count);
+    {   // tuning knob (experiments only): MVS_SDF_PASSES=n forces n blocks per CTA
+        static const int forced = getenv("MVS_SDF_PASSES") ? atoi(getenv("MVS_SDF_PASSES")) : 0;
+        if (forced >= 1 && forced <= kSdfMaxPasses) passes = forced;
+    }
+    const int nparts = (nblocks + passes - 1) / passes;
+    int rc = ensure_sdf_fused_ws(ctx);
+    if (rc) return rc;
     dim3 g(nparts, nb);
+    const SdfFusedArgs sa = make_sdf_fused_args(ctx);
     MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
-               MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel, g, dim3(kSdfFThreads), 0, st, (const float*)w.verts, (const float*)w.vposed,
-                                           (const float*)w.slot_tr, (const int*)w.na, N, (N + 63) / 64, (const float*)w.bboxp,
-                                           (const int*)m.faces, lp.sdf_all_faces ? m.F : 1, m.tri0[0], m.tri0[1], m.tri0[2],
-                                           lp.sdf_grid, (const float*)w.At, w.ldA, (const int*)m.ell_j, (const float*)m.ell_w, m.KW,
-                                           (const float*)m.Wd, (const float*)m.Qk, w.sdf_parts5, w.sdf_part, w.sdf_pflag,
-                                           reinterpret_cast<FrameBox*>(w.sdf_box), passes, w.sdf_gcoord)));
+               MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel, g, dim3(kSdfFThreads), 0, st, sa, (const int*)w.na, passes)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

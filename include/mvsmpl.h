@@ -224,16 +224,10 @@ int mvs_set_exec_mode(mvs_ctx* ctx, int mode);
  *      stream around every launch whose kernel id bit is set in `mask` (0 = off, the default).
  *      mvs_profile_read synchronises the device, adds up the elapsed times since the last mvs_profile call
  *      and writes, for kernel id k < MVS_NUM_KERNEL_IDS, ms[k] and launches[k]. */
-#define MVS_NUM_KERNEL_IDS 19
+#define MVS_NUM_KERNEL_IDS 18
 int mvs_profile(mvs_ctx* ctx, unsigned mask);
 int mvs_profile_read(mvs_ctx* ctx, double* ms, long long* launches);
 const char* mvs_kernel_name(int kernel_id);
-/* The dense rounds (stages with the SDF term) run as ONE persistent kernel, so per-launch events see a single launch; the
- * kernel times its own phases instead: ns6[0..3] = accumulated wall time (ns, as seen by CTA 0, barrier waits included) of
- * the contraction / skinning / SDF / per-frame phases, ns6[4] = sum over rounds of the active-frame counts (frame-rounds),
- * ns6[5] = the whole kernel (ns), *rounds = rounds executed, all since the
- * previous call (which resets the counters). */
-int mvs_dense_phase_times(mvs_ctx* ctx, double* ns6, long long* rounds);
 
 #ifdef __cplusplus
 }

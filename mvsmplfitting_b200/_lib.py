@@ -61,9 +61,9 @@ EXPORTS = (
     "mvs_version", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
     "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
     "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
-    "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor", "mvs_init_guess", "mvs_dense_phase_times",
+    "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor", "mvs_init_guess",
 )
-NUM_KERNEL_IDS = 19
+NUM_KERNEL_IDS = 18
 
 _lib = None
 
@@ -107,7 +107,6 @@ def load() -> ctypes.CDLL:
     lib.mvs_set_anchor.argtypes = [vp, vp, vp, ci, vp]
     lib.mvs_profile.argtypes = [vp, ctypes.c_uint]
     lib.mvs_profile_read.argtypes = [vp, vp, vp]
-    lib.mvs_dense_phase_times.argtypes = [vp, vp, vp]
     lib.mvs_kernel_name.argtypes = [ci]
     lib.mvs_kernel_name.restype = ctypes.c_char_p
     for name in EXPORTS:

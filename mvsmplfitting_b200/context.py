@@ -303,16 +303,5 @@ class FittingContext:
         _lib.check(self.h, self.lib.mvs_profile_read(self.h, ms, cnt), "mvs_profile_read")
         return {self.lib.mvs_kernel_name(k).decode(): (ms[k], int(cnt[k])) for k in range(n) if cnt[k]}
 
-    def dense_phase_times(self) -> dict:
-        """{phase: ms} of the persistent dense-round kernel since the last call (wall time seen by CTA 0) + rounds"""
-        ns = (ctypes.c_double * 6)()
-        rounds = ctypes.c_longlong()
-        _lib.check(self.h, self.lib.mvs_dense_phase_times(self.h, ns, ctypes.byref(rounds)), "mvs_dense_phase_times")
-        names = ("gemm", "skin", "sdf", "frame", None, "kernel")
-        out = {n: ns[i] * 1e-6 for i, n in enumerate(names) if n}
-        out["rounds"] = int(rounds.value)
-        out["frame_rounds"] = int(ns[4])
-        return out
-
     def launch_count(self) -> int:
         return int(self.lib.mvs_launch_count(self.h))

@@ -121,8 +121,7 @@ int mvs_create(int device, mvs_ctx** out) {
 
 static const char* kKernelNames[KID_COUNT] = {
     "frame_fwd", "vertex_fwd", "sdf_bbox", "sdf_sample", "sdf_finalize", "keypoint_loss", "vertex_bwd", "frame_bwd",
-    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_fused", "frame_step", "posedirs_gemm_tc", "skin",
-    "dense_rounds"};
+    "lbfgs_advance", "lbfgs_compact", "sdf_grid", "misc", "closure_resident", "lbfgs_resident", "sdf_fused", "frame_step", "posedirs_gemm_tc", "skin"};
 
 const char* mvs_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
 
@@ -415,7 +414,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.fidx, B))) return rc;
     if ((rc = dev_alloc(ctx, &w.na, 1))) return rc;
     if ((rc = dev_alloc(ctx, &w.Phi, (size_t)w.ldA * kFeatPad))) return rc;
-    if ((rc = dev_alloc(ctx, &w.PhiTc, (size_t)w.ldA * kFeatPad))) return rc;
+    if ((rc = dev_alloc(ctx, &w.PhiTc, (size_t)2 * w.ldA * kFeatPad))) return rc;
     if ((rc = dev_alloc(ctx, &w.bboxp, (size_t)B * ((m.N + 63) / 64) * 12))) return rc;
     if ((rc = dev_alloc(ctx, &w.At, (size_t)kSkinFloats * w.ldA))) return rc;
     if ((rc = dev_alloc(ctx, &w.gchain, (size_t)B * kJoints * 3))) return rc;
@@ -432,7 +431,7 @@ int mvs_set_batch(mvs_ctx* ctx, int B) {
     if ((rc = dev_alloc(ctx, &w.grad_scratch, (size_t)B * kParams))) return rc;
     MVS_CUDA_OK(ctx, cudaMemset(w.At, 0, (size_t)kSkinFloats * w.ldA * sizeof(float)));
     MVS_CUDA_OK(ctx, cudaMemset(w.Phi, 0, (size_t)w.ldA * kFeatPad * sizeof(float)));
-    MVS_CUDA_OK(ctx, cudaMemset(w.PhiTc, 0, (size_t)w.ldA * kFeatPad * sizeof(float)));
+    MVS_CUDA_OK(ctx, cudaMemset(w.PhiTc, 0, (size_t)2 * w.ldA * kFeatPad * sizeof(float)));
     MVS_LAUNCH(ctx, KID_MISC, 0, iota_kernel<<<(B + 255) / 256, 256>>>(w.fidx, B, w.na));
     MVS_CUDA_OK(ctx, cudaDeviceSynchronize());
     return MVS_OK;

@@ -83,10 +83,11 @@ frame_fwd_kernel(const float* __restrict__ x, const int* __restrict__ fidx, cons
         else if (k < kPoseBasis + kBetas) v = s.x[kOffBetas + k - kPoseBasis];
         else v = (k == kFeat - 1) ? 1.0f : 0.0f;
         Phi[(size_t)slot * kFeatPad + k] = v;
-        if (PhiTc) {                 // A operand of the tensor-core contraction: pose feature only, TF32 (rna)
-            float r = 0.f;
-            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
-            PhiTc[(size_t)slot * kFeatPad + k] = r;
+        if (PhiTc) {                 // A operand of the tensor-core contraction: pose feature only, v = hi + lo, both TF32
+            float hi = 0.f, lo = 0.f;
+            if (k < kPoseBasis) tf32_split(v, hi, lo);
+            PhiTc[(size_t)slot * kFeatPad + k] = hi;
+            PhiTc[((size_t)ldA + slot) * kFeatPad + k] = lo;
         }
     }
     if (t < kJoints) {
@@ -760,7 +761,10 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
                frame_fwd_kernel<<<B, kFrameThreads, 0, st>>>(x_dev, w.fidx, w.na, par, m.Jt, m.JS, w.Phi, w.PhiTc, w.At, w.ldA,
                                                              w.gchain, w.slot_tr));
     if (dense) {
-        int rc = launch_vertex_fwd_dense(ctx, st);
+        // with the SDF term this chain is the plain-fp32 cross-check of the dense-regime kernels: the sampled distances are
+        // voxel-sized numbers, TF32 pose offsets would cost them 1e-5 .. 1e-4 relative (the dense-regime kernels re-evaluate
+        // the vertices that matter in fp32 instead, mvs_sdf_dev.cuh)
+        int rc = launch_vertex_fwd_dense(ctx, st, !sdf_on);
         if (rc) return rc;
     } else {
         dim3 g2((nv + kTileV - 1) / kTileV, ftiles);
@@ -831,10 +835,10 @@ int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st) {
     return MVS_OK;
 }
 
-int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st) {
+int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st, bool allow_tc) {
     DevModel& m = ctx->m;
     Workspace& w = ctx->ws;
-    if (tc_available(ctx)) return launch_vertex_fwd_tc(ctx, st);     // tcgen05 / TMA path (mvs_tc.cu)
+    if (allow_tc && tc_available(ctx)) return launch_vertex_fwd_tc(ctx, st);     // tcgen05 / TMA path (mvs_tc.cu)
     if (!ctx->attr_done) {
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertFwdSmem));
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vertex_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertBwdSmem));

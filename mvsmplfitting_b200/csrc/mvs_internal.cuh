@@ -91,7 +91,7 @@ struct Workspace {
     int* fidx = nullptr;              // [B] active list: slot -> frame
     int* na = nullptr;                // [1] number of active slots
     float* Phi = nullptr;             // [ldA][224]
-    float* PhiTc = nullptr;           // [ldA][224] pose feature rounded to TF32 (A operand of the tensor-core contraction)
+    float* PhiTc = nullptr;           // [2][ldA][224] pose feature split into TF32 hi | lo parts (A operand of the tensor-core contraction)
     float* At = nullptr;              // [288][ldA]   skinning transforms, frame fastest
     float* gchain = nullptr;          // [B][24][3]   posed chain joints (model_type 'smpl')
     float* pose_cache = nullptr;      // [B][864] per FRAME: R | J | Gam | g | A of the pending trial point (frame_step -> frame_step)
@@ -145,7 +145,7 @@ __host__ __device__ inline int sdf_passes_for(int na, int nblocks, int cta_slots
 enum KernelId {
     KID_FRAME_FWD = 0, KID_VERTEX_FWD, KID_SDF_BBOX, KID_SDF_SAMPLE, KID_SDF_FINALIZE, KID_KEYPOINT, KID_VERTEX_BWD,
     KID_FRAME_BWD, KID_LBFGS_ADVANCE, KID_LBFGS_COMPACT, KID_SDF_GRID, KID_MISC, KID_RESIDENT_CLOSURE, KID_RESIDENT_LBFGS,
-    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_SKIN, KID_DENSE_ROUNDS, KID_COUNT
+    KID_SDF_FRAME, KID_FRAME_STEP, KID_VERTEX_FWD_TC, KID_SKIN, KID_COUNT
 };
 static_assert(KID_COUNT == MVS_NUM_KERNEL_IDS, "kernel id table out of sync with mvsmpl.h");
 
@@ -176,7 +176,6 @@ struct mvs_ctx {
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
     mvs::Profiler prof;
     void* tc = nullptr;              // tensor-core path state (mvs_tc.cu)
-    void* dense = nullptr;           // persistent dense-round state (mvs_dense.cu)
 };
 
 namespace mvs {
@@ -220,6 +219,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// v = hi + lo with hi = TF32(v) (round to nearest, ties away) and lo = TF32(v - hi); v - hi is exact in fp32.  The tensor-core
+// contraction multiplies hi*hi + lo*hi + hi*lo (error-compensated "3xTF32"): the dropped lo*lo term is 2^-22 of a product.
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    hi = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+    lo = __uint_as_float(u);
+}
+
 // Warp-wide extreme of a float with the arg-index of its first occurrence ("ties -> lowest vertex index", like
 // torch.min / max on CPU) in two redux.sync instructions: floats are mapped to unsigned keys of the same order
 // (-0 is folded into +0 first, so equal floats have equal keys).
@@ -259,7 +268,7 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg
                           const void* lp_tab_host, int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st);
 // dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
-int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st);                                   // mvs_closure.cu
+int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st, bool allow_tc = true);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
 int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st);   // mvs_sdf.cu
 // mvs_tc.cu: tcgen05 / TMA dense vertex forward
@@ -275,11 +284,6 @@ int frame_step_begin_run(mvs_ctx* ctx, cudaStream_t st);                 // mvs_
 int launch_frame_fwd_dense(mvs_ctx* ctx, const float* x_dev, const void* lbfgs_state, int nstages, cudaStream_t st);   // mvs_resident.cu
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int history);
 bool hybrid_available_for(const mvs_ctx* ctx, const LossParams& lp);
-// mvs_dense.cu: the dense rounds of a run as one persistent cooperative kernel
-bool dense_persistent_available(const mvs_ctx* ctx);
-int run_dense_persistent(mvs_ctx* ctx, float* params_dev, const void* lbfgs_state, const void* lbfgs_cfg, int nstages,
-                         long long max_rounds, cudaStream_t st);
-long long dense_last_rounds(const mvs_ctx* ctx);
 int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, cudaStream_t st);   // mvs_lbfgs.cu
 int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out);      // mvs_api.cu: validation + conversion
 int sdf_grid_launch(mvs_ctx* ctx, float* phi, const int* faces, int num_faces, const float* verts, int batch,

@@ -218,28 +218,6 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
                                                "reference chain (exec mode 1, mvs_lbfgs_step): use use_vposer = 1 there");
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
-    if (!step_mode && hybrid_available(ctx) && dense_persistent_available(ctx)) {
-        // opt-in experiment (MVS_DENSE_PERSISTENT=1): the dense rounds as ONE persistent cooperative kernel (mvs_dense.cu);
-        // bit-identical to the four-launch rounds below, measured slower (see dense_persistent_available)
-        const long long max_rounds = ((long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8) * nst;
-        w.na_bound = B;
-        if ((rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, nst, st))) return rc;       // Phi / transforms of every frame, slot = frame
-        if ((rc = frame_step_begin_run(ctx, st))) return rc;
-        if ((rc = run_dense_persistent(ctx, params_dev, &S, &cfg, nst, max_rounds, st))) return rc;
-        if ((rc = tc_check_error(ctx))) return rc;
-        MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
-        if (last_grad_dev)
-            MVS_CUDA_OK(ctx, cudaMemcpyAsync(last_grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
-        MVS_CUDA_OK(ctx, cudaMemcpyAsync(th, S.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
-        if (stats) {
-            stats->frame_iterations += th[0]; stats->frame_evals += th[1]; stats->frames_nan += (int)th[2];
-            stats->rounds += (int)dense_last_rounds(ctx);
-        }
-        MVS_CUDA_OK(ctx, cudaGetLastError());
-        return MVS_OK;
-    }
     if (!step_mode && hybrid_available(ctx)) {
         // dense regime (SDF term on): four launches per round -- pose blend shapes of the active frames (tcgen05
         // GEMM), skinning + box partials, the SDF term with the adjoint of its (short) vertex list, and the per-frame
@@ -354,13 +332,9 @@ int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, floa
     w.na_bound = B;
     if ((rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, 1, st))) return rc;
     if ((rc = frame_step_begin_run(ctx, st))) return rc;
-    if (dense_persistent_available(ctx)) {               // one round of the persistent kernel, optimiser step off
-        if ((rc = run_dense_persistent(ctx, const_cast<float*>(x_dev) /* read only in this mode */, &S, &cfg, 1, 1, st))) return rc;
-    } else {
-        if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;
-        if ((rc = launch_sdf_fused(ctx, st))) return rc;
-        if ((rc = launch_frame_step(ctx, const_cast<float*>(x_dev) /* read only in this mode */, &S, &cfg, 1, st))) return rc;
-    }
+    if ((rc = launch_vertex_fwd_dense(ctx, st))) return rc;
+    if ((rc = launch_sdf_fused(ctx, st))) return rc;
+    if ((rc = launch_frame_step(ctx, const_cast<float*>(x_dev) /* read only in this mode */, &S, &cfg, 1, st))) return rc;
     if (loss_dev) MVS_CUDA_OK(ctx, cudaMemcpyAsync(loss_dev, S.loss_eval, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (grad_dev) MVS_CUDA_OK(ctx, cudaMemcpyAsync(grad_dev, S.g_eval, (size_t)B * kParams * sizeof(float), cudaMemcpyDeviceToDevice, st));
     MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));         // the pinned stage table is reused by the next call

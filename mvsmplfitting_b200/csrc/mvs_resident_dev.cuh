@@ -791,10 +791,11 @@ __device__ __forceinline__ void next_pose_forward(ResidentSmem& S, const Residen
         else if (k < kPoseBasis + kBetas) v = S.x[kOffBetas + k - kPoseBasis];
         else v = (k == kFeat - 1) ? 1.0f : 0.0f;
         Phi[(size_t)slot * kFeatPad + k] = v;
-        if (PhiTc) {
-            float r = 0.f;
-            if (k < kPoseBasis) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); r = __uint_as_float(u); }
-            PhiTc[(size_t)slot * kFeatPad + k] = r;
+        if (PhiTc) {                 // A operand of the tensor-core contraction: v = hi + lo, both TF32 (tf32_split)
+            float hi = 0.f, lo = 0.f;
+            if (k < kPoseBasis) tf32_split(v, hi, lo);
+            PhiTc[(size_t)slot * kFeatPad + k] = hi;
+            PhiTc[((size_t)ldA + slot) * kFeatPad + k] = lo;
         }
     }
     __syncthreads();

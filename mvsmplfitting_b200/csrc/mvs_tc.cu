@@ -18,10 +18,13 @@
 // The rest of the vertex forward (template + shape blend shapes in fp32, linear blend skinning, box partials) is
 // skin_kernel / skin_small_kernel below: fused into this epilogue it ran in 128 threads and cost 10x the contraction.
 //
-// Precision: operands are pre-rounded to TF32 (cvt.rna), accumulation is fp32.  Pose offsets are a small
-// correction (<= a few % of a vertex coordinate), so their 2^-11 relative rounding stays < 1e-5 relative on the
-// vertices -- an order of magnitude inside the 1e-4 parity bar (tests/test_gpu_tc.py checks against the fp32
-// SIMT kernel and the oracle).  The template and the shape blend shapes are NOT sent through TF32.
+// Precision: error-compensated "3xTF32".  Both operands are split into two TF32 numbers (x = hi + lo, lo = TF32(x - hi)) and
+// the tensor cores accumulate hi*hi + lo*hi + hi*lo in fp32 (the dropped lo*lo term is 2^-22 of a product), i.e. the pose
+// offsets come out with fp32-class accuracy.  Plain TF32 (round 1) left 1e-6 absolute on a vertex: harmless for the joints,
+// but the SDF samples are voxel-sized distances, so it was a 1e-5 .. 1e-4 relative error of the interpenetration term and
+// pushed its gradient past the 1e-4 parity bar (profiles/r02_sdf_pin_diag_before.json).  The tensor pipe was 1 % busy, so
+// the 3x MMA count is free; the price is operand traffic (B hi + B lo, and the A lo chunks stream through the ring).
+// The template and the shape blend shapes are NOT sent through the tensor cores.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -46,9 +49,9 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = base;                                        // 7 x [128 rows][128 B], 1024-aligned
-    unsigned char* sB = sA + (size_t)kTcKCh * kTcABytes;             // 6 x [96 rows][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kTcStages * kTcBBytes);
+    unsigned char* sA = base;                                        // A hi: 7 x [128 rows][128 B], 1024-aligned, resident
+    unsigned char* sR = sA + (size_t)kTcKCh * kTcABytes;             // ring: kTcStages x (A lo chunk 16 KB | B hi chunk 12 KB | B lo chunk 12 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)kTcStages * kTcStageBytes);
     uint64_t* a_full = bars;                      // [1]
     uint64_t* b_full = bars + 1;                  // [stages]
     uint64_t* b_empty = b_full + kTcStages;       // [stages]
@@ -94,9 +97,11 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             // as posedirs itself; at the tail of a fit only a few of its 128 rows are live, and those are fetched as
             // 8-row boxes (one swizzle atom each: same shared-memory image).  Rows that are not loaded hold whatever
             // was there: their accumulator rows are never read.
+            // lo parts: rows ldA.. of the A array, rows ncols.. of the posedirs array (same tensor maps, row offset)
             const int live_rows = min(kTcBM, na - m0);
-            if (live_rows <= 32) {
-                const int groups = (live_rows + 7) / 8;
+            const bool small = live_rows <= 32;
+            const int groups = (live_rows + 7) / 8;
+            if (small) {
                 mbar_expect_tx(a_full, kTcKCh * groups * 8 * kTcBK * 4);
                 for (int kc = 0; kc < kTcKCh; ++kc)
                     for (int gq = 0; gq < groups; ++gq)
@@ -105,12 +110,22 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 mbar_expect_tx(a_full, kTcKCh * kTcABytes);
                 for (int kc = 0; kc < kTcKCh; ++kc) tma_load_2d(sA + (size_t)kc * kTcABytes, &map_a, kc * kTcBK, m0, a_full);
             }
+            const uint32_t stage_bytes = (small ? groups * 8 * kTcBK * 4 : kTcABytes) + 2 * kTcBBytes;
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 for (int kc = 0; kc < kTcKCh; ++kc) {
                     if (!mbar_wait(&b_empty[stage], phase ^ 1, err_flag)) return;
-                    mbar_expect_tx(&b_full[stage], kTcBBytes);
-                    tma_load_2d(sB + (size_t)stage * kTcBBytes, &map_b, kc * kTcBK, tile * kTcBN, &b_full[stage]);
+                    unsigned char* sAl = sR + (size_t)stage * kTcStageBytes;
+                    unsigned char* sBh = sAl + kTcABytes;
+                    unsigned char* sBl = sBh + kTcBBytes;
+                    mbar_expect_tx(&b_full[stage], stage_bytes);
+                    if (small) {
+                        for (int gq = 0; gq < groups; ++gq) tma_load_2d(sAl + (size_t)gq * 1024, &map_a8, kc * kTcBK, ldA + m0 + 8 * gq, &b_full[stage]);
+                    } else {
+                        tma_load_2d(sAl, &map_a, kc * kTcBK, ldA + m0, &b_full[stage]);
+                    }
+                    tma_load_2d(sBh, &map_b, kc * kTcBK, tile * kTcBN, &b_full[stage]);
+                    tma_load_2d(sBl, &map_b, kc * kTcBK, ncols + tile * kTcBN, &b_full[stage]);
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -130,12 +145,15 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 for (int kc = 0; kc < kTcKCh; ++kc) {
                     if (!mbar_wait(&b_full[stage], phase, err_flag)) return;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sA + (size_t)kc * kTcABytes);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)stage * kTcBBytes);
+                    const uint32_t ah = smem_u32(sA + (size_t)kc * kTcABytes);
+                    const uint32_t al = smem_u32(sR + (size_t)stage * kTcStageBytes);
+                    const uint32_t bh = al + kTcABytes, bl = bh + kTcBBytes;
 #pragma unroll
-                    for (int k = 0; k < kTcBK / 8; ++k)
-                        umma_tf32(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                                  (kc | k) ? 1u : 0u);
+                    for (int k = 0; k < kTcBK / 8; ++k) {              // hi*hi, then the two correction products
+                        umma_tf32(d_tmem, umma_desc_k_sw128(ah + k * 32), umma_desc_k_sw128(bh + k * 32), idesc, (kc | k) ? 1u : 0u);
+                        umma_tf32(d_tmem, umma_desc_k_sw128(al + k * 32), umma_desc_k_sw128(bh + k * 32), idesc, 1u);
+                        umma_tf32(d_tmem, umma_desc_k_sw128(ah + k * 32), umma_desc_k_sw128(bl + k * 32), idesc, 1u);
+                    }
                     umma_commit(&b_empty[stage]);                    // frees the B slot when these MMAs retire
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
@@ -198,7 +216,7 @@ skin_small_kernel(SkinArgs ar, const int* __restrict__ na_ptr) {
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
     CUtensorMap map_a, map_a8, map_b;
-    float* Qtc = nullptr;       // [3N][224] TF32-rounded posedirs rows (columns >= 207 zero)
+    float* Qtc = nullptr;       // [2][3N][224] posedirs rows split into TF32 hi | lo parts (columns >= 207 zero)
     float* poffT = nullptr;     // [3N][ldA] pose offsets, frame fastest (output of the tensor-core contraction)
     int* err = nullptr;
     bool ready = false;
@@ -239,9 +257,14 @@ int tc_upload_model(mvs_ctx* ctx, const float* Qk_host) {
     TcState* T = new TcState();
     ctx->tc = T;
     const size_t n = (size_t)3 * ctx->m.N * kFeatPad;
-    std::vector<float> q(n);
-    for (size_t i = 0; i < n; ++i) q[i] = (i % kFeatPad) < (size_t)kPoseBasis ? round_tf32(Qk_host[i]) : 0.f;
-    int rc = dev_upload(ctx, &T->Qtc, q.data(), n);
+    std::vector<float> q(2 * n);                 // hi rows, then lo rows: posedirs = hi + lo, both TF32 (hi - x is exact in fp32)
+    for (size_t i = 0; i < n; ++i) {
+        const bool pose = (i % kFeatPad) < (size_t)kPoseBasis;
+        const float hi = pose ? round_tf32(Qk_host[i]) : 0.f;
+        q[i] = hi;
+        q[n + i] = pose ? round_tf32(Qk_host[i] - hi) : 0.f;
+    }
+    int rc = dev_upload(ctx, &T->Qtc, q.data(), 2 * n);
     if (rc) return rc;
     if ((rc = dev_alloc(ctx, &T->err, 1))) return rc;
     MVS_CUDA_OK(ctx, cudaMemset(T->err, 0, sizeof(int)));
@@ -259,9 +282,9 @@ int tc_prepare(mvs_ctx* ctx) {
     if (!T) return set_error(ctx, MVS_ERR_INVALID, "tensor-core path not initialised (mvs_set_model)");
     if (!T->ready) {
         int rc;
-        if ((rc = encode_map(ctx, &T->map_a, w.PhiTc, (uint64_t)w.ldA, kTcBM))) return rc;
-        if ((rc = encode_map(ctx, &T->map_a8, w.PhiTc, (uint64_t)w.ldA, 8))) return rc;
-        if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)3 * m.N, kTcBN))) return rc;
+        if ((rc = encode_map(ctx, &T->map_a, w.PhiTc, (uint64_t)2 * w.ldA, kTcBM))) return rc;       // hi rows, then lo rows
+        if ((rc = encode_map(ctx, &T->map_a8, w.PhiTc, (uint64_t)2 * w.ldA, 8))) return rc;
+        if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)2 * 3 * m.N, kTcBN))) return rc;
         if ((rc = dev_alloc(ctx, &T->poffT, (size_t)3 * m.N * w.ldA))) return rc;
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(posedirs_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmem));

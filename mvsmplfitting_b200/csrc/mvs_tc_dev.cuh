@@ -11,11 +11,12 @@ constexpr int kTcBM = 128;            // frames per CTA (UMMA M)
 constexpr int kTcBN = kTileC;         // 96 columns = 32 vertices (UMMA N)
 constexpr int kTcBK = 32;             // floats per 128-byte swizzle row
 constexpr int kTcKCh = kFeatPad / kTcBK;   // 7 K chunks
-constexpr int kTcStages = 6;
+constexpr int kTcStages = 2;             // ring stages of (A lo chunk | B hi chunk | B lo chunk)
 constexpr int kTcABytes = kTcBM * kTcBK * 4;   // 16 KB
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;   // 12 KB
 constexpr int kTcThreads = 256;
-constexpr size_t kTcSmem = 1024 /*align slack*/ + (size_t)kTcKCh * kTcABytes + (size_t)kTcStages * kTcBBytes + 256;
+constexpr int kTcStageBytes = kTcABytes + 2 * kTcBBytes;     // 40 KB
+constexpr size_t kTcSmem = 1024 /*align slack*/ + (size_t)kTcKCh * kTcABytes + (size_t)kTcStages * kTcStageBytes + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -96,7 +96,7 @@ def test_dense_regime_closure_matches_oracle(all_faces, grid, B, syn_model, syn_
     n0 = ctx.launch_count()
     final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=1, max_iter=1))
     assert st["frame_iterations"] == B
-    assert ctx.dense_phase_times()["rounds"] > 0 or ctx.launch_count() - n0 > 8          # dense rounds, not one resident launch
+    assert ctx.launch_count() - n0 > 8          # dense rounds, not one resident launch
     om = O.OracleModel.from_numpy(syn_model, dtype=torch.float32)
     pri = O.OraclePriors.gmm_from_dict(syn_gmm, torch.float32)
     cfg = O.LossConfig(interpenetration=True, coll_loss_weight=cw, sdf_grid=grid, sdf_all_faces=all_faces, **w)

@@ -12,8 +12,10 @@ the autograd restatement in oracle/smooth_oracle.py): the temporal smoothness en
 is minimised by block-Jacobi sweeps: within a sweep every frame sees its two neighbours frozen, which
 turns E_s into a per-frame quadratic anchor  2 lam || x_t - mean(neighbours) ||^2 (+ const) that the
 closure kernels evaluate (mvs_set_anchor), so frames stay independent inside a sweep.  Between sweeps
-ranks exchange ONE boundary frame with each neighbour (344 B halo) and all-reduce ONE scalar, the global
-smoothness energy -- the only collective on the path, as the north-star asks.
+ranks exchange ONE boundary frame with each neighbour (344 B halo) and all-reduce two scalars in ONE call (the global
+smoothness energy and the sum of the frames' own losses = the joint objective) -- the only collective on the path, as the
+north-star asks.  Block-Jacobi is a fixed-point iteration of the joint problem's stationarity conditions; its convergence on
+a 64-frame chain is recorded in profiles/r02_cfg5_convergence.json (scripts/cfg5_convergence.py).
 """
 from __future__ import annotations
 
@@ -113,7 +115,7 @@ class SequenceFitter:
         self.B = self.stop - self.start
 
     def fit(self, x0_local: torch.Tensor, gt_uv_local, conf_local, joint_weights, stage_cfgs, opt_cfg=None,
-            smooth_weight: float = 0.0, sweeps: int = 1, mask: torch.Tensor | None = None):
+            smooth_weight: float = 0.0, sweeps: int = 1, mask: torch.Tensor | None = None, time_comm: bool = False):
         """x0_local [B,86] (CUDA, updated in place); detections of this rank's frames.  Returns per-sweep stats;
         with smooth_weight > 0 also the global smoothness energy after every sweep."""
         ctx = self.ctx
@@ -138,8 +140,30 @@ class SequenceFitter:
                 for k in tot:
                     tot[k] += st[k]
             if smooth_weight > 0:
+                # joint objective after this sweep: sum of the frames' own losses (anchor off, last stage's weights) + E_s.
+                # ONE all-reduce of two doubles; its device time is reported per sweep (comm_ms).
+                ctx.set_anchor(None)
+                ctx.set_loss(config=stage_cfgs[-1])
+                own = ctx.closure(x, want_grad=False)["loss"].double().sum()
+                ev = None
+                if time_comm and torch.cuda.is_available():
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 left, _ = exchange_halo(x, self.group)
-                tot["smooth_energy"] = float(smoothness_energy(x, left, smooth_weight, mask, self.group))
+                m = mask.to(x.device)
+                e = ((x[1:] - x[:-1]) * m).pow(2).sum()
+                if left is not None:
+                    e = e + ((x[0] - left) * m).pow(2).sum()
+                red = torch.stack([smooth_weight * e.double(), own])
+                if dist.is_initialized() and self.world > 1:
+                    dist.all_reduce(red, op=dist.ReduceOp.SUM, group=self.group)
+                if ev:
+                    ev[1].record()
+                    torch.cuda.synchronize()
+                    tot["comm_ms"] = ev[0].elapsed_time(ev[1])
+                tot["smooth_energy"] = float(red[0])
+                tot["fit_energy"] = float(red[1])
+                tot["joint_energy"] = float(red[0] + red[1])
             out.append(tot)
         ctx.set_anchor(None)
         return out

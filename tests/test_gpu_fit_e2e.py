@@ -81,7 +81,7 @@ def test_four_stage_fit_with_sdf_matches_live_reference_run(syn_model, syn_gmm):
     if not (RH.available() and ref_sdf.available()):
         pytest.skip("reference tree / SDF kernel not staged (python -m oracle.stage_reference)")
     from oracle import ref_fit as RF
-    B, V = 8, 8
+    B, V = 16, 8
     cams = S.make_cameras(V)
     fr = S.make_frames(syn_model, cams, B, seed=4200)
     X0 = S.pack_params(fr["init"])
@@ -108,11 +108,11 @@ def test_four_stage_fit_with_sdf_matches_live_reference_run(syn_model, syn_gmm):
     _record("sdf", rec)
     print(json.dumps({k: rec[k] for k in ("iterations_per_frame", "evals_per_frame")}), "final-loss rel: median %.3g max %.3g" % (
         np.median(rel_final), rel_final.max()))
-    # 8 frames: the means carry the sampling noise of a chaotic stopping rule (see the module docstring).  With the SDF term
+    # 16 frames: the means carry the sampling noise of a chaotic stopping rule (see the module docstring).  With the SDF term
     # the objective is also DISCONTINUOUS (phi jumps where a voxel's inside / outside parity changes), so single frames may
     # end in different basins (measured: 4-6 of 8 frames within 2 %, the others 10 % .. 84 % apart, some better and some
     # worse than the reference): the test pins the bulk and the absence of a bias, not the outliers.
     assert abs(it - ref_it) / ref_it < 0.20, (it, ref_it)
-    assert abs(ev - ref_ev) / ref_ev < 0.25, (ev, ref_ev)
+    assert abs(ev - ref_ev) / ref_ev < 0.35, (ev, ref_ev)       # heavy-tailed: single frames spend 200-300 evaluations in one stage
     assert np.median(rel_final) < 0.06 and (rel_final < 0.05).sum() >= B // 2
     assert abs(np.mean(np.log(final / ref_final))) < 0.15

@@ -70,16 +70,15 @@ def closure_with_vposer(model, cams, fr, frame, weights, vp, z, dtype):
     return float(total), g, out.joints.detach().numpy()[0].copy(), bp.detach().numpy()[0].copy()
 
 
-def main():
-    assert H.available(), "reference tree missing"
-    w = S.make_vposer(11)
+def write_fixture(name, w, vp_for, n_codes=24):
     rng = np.random.RandomState(5)
     # latent codes: typical (unit normal) and large ones that push rotations past 90 / 180 degrees (all four
     # quaternion branches of rotation_matrix_to_quaternion)
-    Z = np.concatenate([rng.normal(0, 1.0, size=(24, 32)), rng.normal(0, 6.0, size=(24, 32))]).astype(np.float32)
+    Z = np.concatenate([rng.normal(0, 1.0, size=(n_codes, 32)), rng.normal(0, 6.0, size=(n_codes, 32))]).astype(np.float32)
+    Z[0] = 0.0                                  # decode(0): the known answer of SURVEY 8c for the shipped snapshot (max |aa| = 0.8225)
     out = dict(Z=Z)
     for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
-        vp = reference_vposer(w, dtype)
+        vp = vp_for(dtype)
         with torch.no_grad():
             aa = vp.decode(torch.tensor(Z, dtype=dtype), output_type="aa").reshape(Z.shape[0], -1).numpy()
         out["aa_" + tag] = aa
@@ -94,7 +93,7 @@ def main():
         wts = stage_weights(stage)
         out["w%d" % stage] = np.array([wts["data_weight"], wts["body_pose_weight"], wts["shape_weight"], wts["bending_prior_weight"]])
         for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
-            vp = reference_vposer(w, dtype)
+            vp = vp_for(dtype)
             for b in range(2):
                 total, g, joints, bp = closure_with_vposer(model, cams, fr, b, wts, vp, zc[b], dtype)
                 pre = "s%d_b%d_%s_" % (stage, b, tag)
@@ -103,9 +102,20 @@ def main():
                 out[pre + "body_pose"] = bp
                 for k, v in g.items():
                     out[pre + "g_" + k] = v
-    np.savez_compressed(os.path.join(GOLD, "vposer_s11.npz"), **out)
-    print("wrote vposer_s11.npz:", {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("s")})
-    print("stage-3 frame-0 loss f32/f64:", out["s3_b0_f32_loss"], out["s3_b0_f64_loss"])
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print("wrote %s:" % name, {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("s")})
+    print("stage-3 frame-0 loss f32/f64:", out["s3_b0_f32_loss"], out["s3_b0_f64_loss"], " max|decode(0)| =", np.abs(out["aa_f32"][0]).max())
+
+
+def main():
+    assert H.available(), "reference tree missing"
+    w = S.make_vposer(11)
+    write_fixture("vposer_s11.npz", w, lambda dtype: reference_vposer(w, dtype))
+    # the snapshot the reference ships (priors/snapshots/poser_epoch091.pkl) through its own loader; the fixture holds inputs
+    # and outputs only -- the weights stay in the reference tree (tests read them from there / from oracle/_ref/reference)
+    real = H.load_reference_vposer()
+    wr = H.vposer_weights_numpy(real)
+    write_fixture("vposer_real.npz", wr, lambda dtype: reference_vposer(wr, dtype), n_codes=12)
 
 
 if __name__ == "__main__":

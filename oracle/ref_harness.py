@@ -206,3 +206,34 @@ def reference_closure_eval(ref_model, ref_cams, frames: dict, frame: int, weight
         proj=proj.detach().cpu().numpy().copy(),
         vertices=out.vertices.detach().cpu().numpy()[0].copy(),
     )
+
+
+def load_reference_vposer(device="cpu"):
+    """The reference's own VPoser (code/model/VPoser.py) with the snapshot it ships (priors/snapshots/poser_epoch091.pkl),
+    through its own loader code/utils/prior.py:23-54.  The pickle is a whole legacy module (torch 0.4 era): loading it needs
+    `weights_only=False` and a stand-in for the long-gone torch.nn.backends.thnn."""
+    import functools
+    ns = import_reference()
+    _stub("configer", Configer=object)
+    thnn = _stub("torch.nn.backends.thnn", _get_thnn_function_backend=lambda: None)
+    if not hasattr(torch.nn, "backends"):
+        torch.nn.backends = _stub("torch.nn.backends")
+    torch.nn.backends.thnn = thnn
+    with in_reference_dir():
+        from utils import prior as ref_prior_utils
+        orig_load = torch.load
+        torch.load = functools.partial(orig_load, weights_only=False, map_location="cpu")      # the snapshot was saved from a CUDA device
+        try:
+            import contextlib as _cl, io as _io
+            with _cl.redirect_stdout(_io.StringIO()):
+                vp = ref_prior_utils.load_vposer(os.path.join(REF_ROOT, "priors"))
+        finally:
+            torch.load = orig_load
+    return vp.to(device)
+
+
+def vposer_weights_numpy(vp) -> dict:
+    g = lambda layer, what: getattr(getattr(vp, layer), what).detach().float().cpu().numpy()
+    return dict(fc1_w=g("bodyprior_dec_fc1", "weight"), fc1_b=g("bodyprior_dec_fc1", "bias"),
+                fc2_w=g("bodyprior_dec_fc2", "weight"), fc2_b=g("bodyprior_dec_fc2", "bias"),
+                out_w=g("bodyprior_dec_out", "weight"), out_b=g("bodyprior_dec_out", "bias"))

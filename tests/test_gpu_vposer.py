@@ -13,11 +13,14 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vposer_s11.npz")
 
 
-def _ctx(model, c, B):
+REAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vposer_real.npz")
+
+
+def _ctx(model, c, B, weights=None):
     from mvsmplfitting_b200.context import FittingContext
     ctx = FittingContext(0)
     ctx.set_model(model)
-    ctx.set_vposer(S.make_vposer(11))
+    ctx.set_vposer(S.make_vposer(11) if weights is None else weights)
     ctx.set_cameras(c["cam_R"], c["cam_t"], c["cam_f"], c["cam_c"])
     ctx.set_batch(B)
     ctx.set_keypoints(c["gt_uv"], c["conf"], c["joint_weights"])
@@ -47,6 +50,27 @@ def test_closure_with_device_vposer_matches_reference(stage, syn_model):
                              ("pose_embedding", (13, 45))):
             assert G.relmax(g[b, a:e], c[pre + "g_" + name]) < 2e-4, (stage, b, name)
         assert (g[b, 45:82] == 0).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("stage", [3, 0])
+def test_closure_with_the_shipped_snapshot_matches_reference(stage, syn_model):
+    """the decoder weights of the reference's own priors/snapshots/poser_epoch091.pkl (read from the staged tree
+    oracle/_ref/reference by the reference's loader; the fixture holds inputs / outputs only)"""
+    from tests.test_vposer_golden import _real_weights
+    c = np.load(REAL)
+    ctx = _ctx(syn_model, c, 2, weights=_real_weights())
+    dw, bpw, sw, bend = [float(v) for v in c["w%d" % stage]]
+    ctx.set_loss(body_prior="l2", use_vposer=2, data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend)
+    out = ctx.closure(torch.tensor(_x_with_latent(c), device="cuda"), want_joints=True)
+    loss, g, joints = out["loss"].cpu().numpy(), out["grad"].cpu().numpy(), out["joints"].cpu().numpy()
+    for b in range(2):
+        pre = "s%d_b%d_f32_" % (stage, b)
+        assert abs(loss[b] - float(c[pre + "loss"])) / abs(float(c[pre + "loss"])) < 1e-4
+        assert G.relmax(joints[b], c[pre + "joints"]) < 1e-4
+        for name, (a, e) in (("betas", (0, 10)), ("global_orient", (10, 13)), ("transl", (82, 85)), ("scale", (85, 86)),
+                             ("pose_embedding", (13, 45))):
+            assert G.relmax(g[b, a:e], c[pre + "g_" + name]) < 2e-4, (stage, b, name)
     ctx.close()
 
 

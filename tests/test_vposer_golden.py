@@ -90,3 +90,38 @@ def test_device_math_of_the_rotation_head_matches_autograd(tmp_path):
     assert np.abs(res[:, :3] - aa.detach().numpy()).max() < 1e-11
     assert np.abs(res[:, 3:9] - x6.grad.numpy()).max() < 1e-9 * max(1.0, np.abs(x6.grad.numpy()).max())
     assert set(res[:, 9].astype(int).tolist()) == {0, 1, 2, 3}
+
+
+REAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vposer_real.npz")
+
+
+def _real_weights():
+    """decoder weights of the snapshot the reference ships (priors/snapshots/poser_epoch091.pkl), read through the reference's
+    own loader from /root/reference or the staged copy under oracle/_ref/reference; the fixture itself holds no weights"""
+    import pytest
+    from oracle import ref_harness as RH
+    if not RH.available() or not os.path.exists(os.path.join(RH.REF_ROOT, "priors", "snapshots", "poser_epoch091.pkl")):
+        pytest.skip("reference snapshot not present (python -m oracle.stage_reference)")
+    return RH.vposer_weights_numpy(RH.load_reference_vposer())
+
+
+def test_shipped_snapshot_known_answer_and_restatement(syn_model):
+    """decode(0) of the shipped snapshot has max |axis-angle| = 0.8225; restatement + oracle closure with the real
+    weights against the unmodified reference class / closure (fixture vposer_real.npz)."""
+    c = np.load(REAL)
+    assert (c["Z"][0] == 0).all() and abs(np.abs(c["aa_f32"][0]).max() - 0.8225) < 1e-4
+    w = _real_weights()
+    aa = VO.decode_aa(w, torch.tensor(c["Z"], dtype=torch.float64)).numpy()
+    assert np.abs(aa - c["aa_f64"]).max() < 1e-10 * max(1.0, np.abs(c["aa_f64"]).max())
+    assert abs(np.abs(aa[0]).max() - 0.8225) < 1e-4
+    cams = dict(R=c["cam_R"], t=c["cam_t"], f=c["cam_f"], c=c["cam_c"])
+    dw, bpw, sw, bend = [float(v) for v in c["w3"]]
+    om = O.OracleModel.from_numpy(syn_model, dtype=torch.float64)
+    cfg = O.LossConfig(data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend, use_vposer=True)
+    for b in range(2):
+        r = O.closure_eval_vposer(om, cfg, O.OraclePriors(kind="l2"), O.cams_to_torch(cams, torch.float64), c["X"][b],
+                                  c["closure_Z"][b], w, c["gt_uv"][:, b], c["conf"][:, b], c["joint_weights"])
+        pre = "s3_b%d_f64_" % b
+        assert abs(r["loss"] - float(c[pre + "loss"])) / abs(float(c[pre + "loss"])) < 1e-9
+        for k in ("betas", "global_orient", "transl", "scale", "pose_embedding"):
+            assert G.relmax(r["g_" + k], c[pre + "g_" + k]) < 1e-9, (b, k)

@@ -76,8 +76,8 @@ int mvs_set_gmm_prior(mvs_ctx* ctx, int num_gaussians, const float* means, const
  * With them a loss configuration may set use_vposer = 2: the pose is VPoser.decode(z, 'aa') (VPoser.py:218-232 and
  * fitting.py:121-123) evaluated ON THE DEVICE inside the closure, z = the first 32 entries of the body_pose slot of the
  * 86-vector (entries 32..68 of the slot are ignored and get zero gradient), the body prior is |z|^2 * body_pose_weight^2
- * (fitting.py:327-329).  Implemented in the frame-resident closure / optimiser and in the dense (SDF) rounds; not in the
- * batched reference chain (exec mode 1, mvs_lbfgs_step, closures that ask for vertices). */
+ * (fitting.py:327-329).  Implemented in the frame-resident closure / optimiser and in the dense (SDF) rounds, which
+ * mvs_lbfgs_step uses as well; not in the batched reference chain (exec mode 1, closures that ask for vertices). */
 int mvs_set_vposer(mvs_ctx* ctx, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                    const float* out_w, const float* out_b);
 

@@ -55,7 +55,7 @@ __global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params
 
 __global__ void __launch_bounds__(32)
 lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, const int* __restrict__ fidx,
-                     const int* __restrict__ na_ptr) {
+                     const int* __restrict__ na_ptr, int pose_len) {
     const int slot = blockIdx.x;
     if (slot >= *na_ptr) return;
     const int b = fidx[slot];
@@ -80,7 +80,7 @@ lbfgs_advance_kernel(LbfgsState S, LbfgsCfg cfg, float* __restrict__ params, con
 
     LbfgsPtrs P{x, g, d, prev_g, x_init, g_prev, bg0, bg1, hy, hs, ro, al, x_eval, g_new, S.H,
                 S.gram + (size_t)b * kGramFloats, scratch};
-    lbfgs_advance_core(s, P, f_new, cfg, lane);
+    lbfgs_advance_core(s, P, f_new, cfg, lane, pose_len);
     __syncwarp();
     if (lane == 0) S.sc[b] = s;
 }
@@ -213,12 +213,17 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         MVS_CUDA_OK(ctx, cudaGetLastError());
         return MVS_OK;
     }
-    if (ctx->loss.use_vposer == 2 && (step_mode || !hybrid_available(ctx)))
+    // use_vposer = 2 (VPoser decode on the device) exists in the frame-resident closure and in the dense-regime kernels, not in
+    // the SIMT reference chain.  mvs_lbfgs_step therefore runs its one step() per call through the dense rounds when the SDF
+    // term is on, and through launch_closure's frame-resident kernel + lbfgs_advance_kernel otherwise.
+    const bool vp2 = ctx->loss.use_vposer == 2;
+    const bool sdf_on = ctx->loss.interpenetration && ctx->loss.coll_loss_weight > 0.f;
+    if (vp2 && (sdf_on ? !hybrid_available(ctx) : !resident_closure_available(ctx)))
         return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) is not implemented in the batched "
-                                               "reference chain (exec mode 1, mvs_lbfgs_step): use use_vposer = 1 there");
+                                               "reference chain (exec mode 1): use use_vposer = 1 there");
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
     MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
-    if (!step_mode && hybrid_available(ctx)) {
+    if ((!step_mode || vp2) && hybrid_available(ctx)) {
         // dense regime (SDF term on): four launches per round -- pose blend shapes of the active frames (tcgen05
         // GEMM), skinning + box partials, the SDF term with the adjoint of its (short) vertex list, and the per-frame
         // closure adjoint + optimiser step + next pose forward.  Finished frames are compacted out once per chunk.
@@ -288,7 +293,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         for (int r = 0; r < chunk; ++r) {
             rc = launch_closure(ctx, S.x_eval, S.loss_eval, S.g_eval, nullptr, nullptr, nullptr, st);
             if (rc) return rc;
-            MVS_LAUNCH(ctx, KID_LBFGS_ADVANCE, st, lbfgs_advance_kernel<<<B, 32, 0, st>>>(S, cfg, params_dev, w.fidx, w.na));
+            MVS_LAUNCH(ctx, KID_LBFGS_ADVANCE, st, lbfgs_advance_kernel<<<B, 32, 0, st>>>(S, cfg, params_dev, w.fidx, w.na, vp2 ? 32 : kOffTransl - kOffPose));
             MVS_LAUNCH(ctx, KID_LBFGS_COMPACT, st, lbfgs_compact_kernel<<<1, 1024, 0, st>>>(S, B, w.fidx, w.na));
             ++rounds;
         }

@@ -117,8 +117,10 @@ __device__ __forceinline__ float group_dot(const float* a, const float* b, int s
 
 // One warp walks ONE frame's optimiser from "closure result (f_new, g_new) available" to its next closure
 // request (x_eval written, s.phase says what is pending) or to PH_DONE.  Pointers may be global or shared.
+// pose_len: entries of the pose slot that belong to the optimised tensor -- 69 (body_pose) or 32 (pose_embedding, use_vposer = 2);
+// only run_fitting's gtol test looks at tensors one by one.
 __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsPtrs& P, const float f_new,
-                                                   const LbfgsCfg& cfg, const int lane) {
+                                                   const LbfgsCfg& cfg, const int lane, const int pose_len = kOffTransl - kOffPose) {
     float* const x = P.x; float* const g = P.g; float* const d = P.d; float* const prev_g = P.prev_g;
     float* const x_init = P.x_init; float* const g_prev = P.g_prev; float* const bg0 = P.bg0; float* const bg1 = P.bg1;
     float* const hy = P.hy; float* const hs = P.hs; float* const ro = P.ro; float* const al = P.al;
@@ -417,7 +419,7 @@ __device__ __forceinline__ void lbfgs_advance_core(FrameScalars& s, const LbfgsP
             }
             {   // all(abs(max(grad_tensor)) < gtol) on the grads left by the LAST closure call (fitting.py:115-117)
                 const int seg_a[5] = {kOffBetas, kOffOrient, kOffPose, kOffTransl, kOffScale};
-                const int seg_e[5] = {kOffOrient, kOffPose, kOffTransl, kOffScale, kParams};
+                const int seg_e[5] = {kOffOrient, kOffPose, kOffPose + pose_len, kOffScale, kParams};
                 bool all_small = true;
                 for (int sg = 0; sg < 5; ++sg) {
                     float m = -3.0e38f;

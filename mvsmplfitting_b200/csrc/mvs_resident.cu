@@ -119,7 +119,7 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
         PHASE_MARK(23);
         if (warp == 0) {
             FrameScalars s = S.fs;
-            lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
+            lbfgs_advance_core(s, P, S.sc[2], cfg, lane, S.lp.use_vposer == 2 ? 32 : kOffTransl - kOffPose);
             if (s.evals - stage_ev0 >= eval_cap && s.phase != PH_DONE) { s.phase = PH_DONE; s.nan_flag = 1; }
             if (s.phase == PH_DONE && s.stage + 1 < nstages) {          // this frame moves on to its next stage
                 next_stage_scalars(s);

@@ -964,7 +964,7 @@ __device__ __forceinline__ void frame_step_body(unsigned char* smem_raw, const F
         FrameScalars s = fs0;
         LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval,
                     S.lg_new, L.H, S.gram, S.tl_scratch};
-        lbfgs_advance_core(s, P, S.sc[2], cfg, lane);
+        lbfgs_advance_core(s, P, S.sc[2], cfg, lane, S.lp.use_vposer == 2 ? 32 : kOffTransl - kOffPose);
         __syncwarp();
         if (s.phase == PH_DONE && s.stage + 1 < nstages) {      // this frame moves on to its next stage
             next_stage_scalars(s);

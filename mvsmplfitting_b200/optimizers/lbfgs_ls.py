@@ -4,7 +4,6 @@
 mvs_lbfgs_run in libmvsmpl): one independent problem per frame, state kept across step() calls."""
 from __future__ import annotations
 
-import torch
 from torch.optim import Optimizer
 
 
@@ -25,7 +24,6 @@ class LBFGS(Optimizer):
                                "(optim_factory.py:50-52)")
         self._params = self.param_groups[0]["params"]
         self._fresh = True
-        self._host_fallback = None
         self.stats = dict(frame_iterations=0, frame_evals=0, rounds=0)
 
     def lbfgs_config(self, ctx, max_outer=1, ftol=0.0, gtol=0.0):
@@ -40,15 +38,11 @@ class LBFGS(Optimizer):
         if not isinstance(closure, FittingClosure):
             raise TypeError("mvsmplfitting_b200 LBFGS.step needs the closure made by "
                             "FittingMonitor.create_fitting_closure (the optimiser runs on the GPU)")
-        if closure.use_vposer:
-            # pose lives in VPoser's latent space: PyTorch decodes it, so the host drives the iteration
-            if self._host_fallback is None:
-                g = self.param_groups[0]
-                self._host_fallback = torch.optim.LBFGS(self._params, lr=g["lr"], max_iter=g["max_iter"],
-                                                        max_eval=g["max_eval"], tolerance_grad=g["tolerance_grad"],
-                                                        tolerance_change=g["tolerance_change"],
-                                                        history_size=g["history_size"], line_search_fn="strong_wolfe")
-            return self._host_fallback.step(closure)
+        if closure.use_vposer and not closure.vposer_native:
+            # the iteration runs on the GPU, so the decoder has to as well (mvs_set_vposer, use_vposer = 2): that needs the
+            # reference's decoder layers (model/VPoser.py:190-197) and a 32-d latent code.  No host-driven fallback.
+            raise NotImplementedError("LBFGS.step with use_vposer=True needs a VPoser module with the reference's decoder "
+                                      "layers (bodyprior_dec_fc1 / fc2 / out) and a [B,32] pose_embedding")
         x = closure.gather_params()
         closure.sync_loss_config()
         loss, grad, st = closure.ctx.lbfgs_step(x, self.lbfgs_config(closure.ctx), reset=self._fresh)

@@ -93,6 +93,41 @@ def test_lbfgs_in_latent_space(syn_model):
     ctx.close()
 
 
+@pytest.mark.parametrize("sdf", [False, True])
+def test_lbfgs_step_in_latent_space(sdf, syn_model):
+    """mvs_lbfgs_step with use_vposer = 2 (one LBFGS.step per call, state persistent): k calls walk the same path as
+    mvs_lbfgs_run with max_outer = k and the monitor's tests off; the value returned is the loss at entry of the step."""
+    c = np.load(GOLD)
+    dw, bpw, sw, bend = [float(v) for v in c["w3"]]
+    kw = dict(body_prior="l2", use_vposer=2, data_weight=dw, body_pose_weight=bpw, shape_weight=sw, bending_prior_weight=bend)
+    if sdf:
+        kw.update(interpenetration=True, coll_loss_weight=1000.0, sdf_grid=128)
+    X0 = _x_with_latent(c)
+    ctx = _ctx(syn_model, c, 2)
+    ctx.set_loss(**kw)
+    xr = torch.tensor(X0, device="cuda")
+    ctx.lbfgs_run(xr, ctx.make_lbfgs_config(max_outer=3, max_iter=8, ftol=0.0, gtol=0.0))
+    l_run = ctx.closure(xr, want_grad=False)["loss"].cpu().numpy()
+    ctx.close()
+    ctx = _ctx(syn_model, c, 2)
+    ctx.set_loss(**kw)
+    xs = torch.tensor(X0, device="cuda")
+    l_entry0 = ctx.closure(xs, want_grad=False)["loss"].cpu().numpy()
+    cfg = ctx.make_lbfgs_config(max_outer=1, max_iter=8)
+    entry = []
+    for k in range(3):
+        loss, grad, st = ctx.lbfgs_step(xs, cfg, reset=(k == 0))
+        entry.append(loss.cpu().numpy().copy())
+        assert st["frame_iterations"] > 0 and torch.isfinite(grad).all()
+        assert (grad[:, 45:82] == 0).all()
+    assert np.abs(entry[0] - l_entry0).max() / np.abs(l_entry0).max() < 2e-4
+    assert (entry[1] < entry[0]).all() and (entry[2] <= entry[1]).all()
+    l_step = ctx.closure(xs, want_grad=False)["loss"].cpu().numpy()
+    assert np.abs(l_step - l_run).max() / np.abs(l_run).max() < 1e-3, (l_step, l_run)
+    assert np.array_equal(xs.cpu().numpy()[:, 45:82], X0[:, 45:82])
+    ctx.close()
+
+
 def test_device_vposer_guards(syn_model):
     from mvsmplfitting_b200.context import FittingContext
     from mvsmplfitting_b200._lib import MvsError
@@ -207,7 +242,12 @@ def test_dropin_closure_native_decode_equals_host_decode(syn_model, syn_gmm, tmp
             assert abs(total - float(c["s3_b0_f32_loss"])) / float(c["s3_b0_f32_loss"]) < 1e-4
             assert G.relmax(res[True][1].reshape(-1), c["s3_b0_f32_g_pose_embedding"]) < 2e-4
             z0 = emb.detach().clone()
+            entry = float(opt.step(closure))                 # one LBFGS.step on the device, in latent space
+            assert abs(entry - total) / total < 1e-5 and not torch.equal(emb.detach(), z0) and float(closure()) < total
             final = mon.run_fitting(opt, closure, params, model, use_vposer=True, pose_embedding=emb, vposer=vp)
             assert final <= total and not torch.equal(emb.detach(), z0)
+        else:
+            with pytest.raises(NotImplementedError):         # no host-driven optimiser: the decoder must be on the device
+                opt.step(closure)
     assert abs(res[True][0] - res[False][0]) / res[False][0] < 1e-4
     assert G.relmax(res[True][1], res[False][1]) < 2e-4 and G.relmax(res[True][2], res[False][2]) < 2e-4

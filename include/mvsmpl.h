@@ -187,7 +187,8 @@ int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, cons
 
 /* ---- initial guess for all frames of the batch (code/utils/init_guess.py:18-107 + fix_params :190-212, which
  *      main.py:76-82 runs per frame in numpy before the solver): triangulates the K keypoints from the V >= 2 views
- *      (code/utils/recompute3D.py:24-61, as written), aligns the model's rest joints (zero pose, zero shape,
+ *      (code/utils/recompute3D.py:24-61, as written; with ONE view the rest joints are pushed along the optical axis by the
+ *      depth guess of init_guess.py:54-78 instead, as written), aligns the model's rest joints (zero pose, zero shape,
  *      scale = fixed_scale) to them with a similarity transform (code/utils/umeyama.py:18 -> the published
  *      algorithm, Umeyama PAMI 1991; the file's own transposed-V variant depends on the LAPACK build's sign
  *      convention, see oracle/init_oracle.py) and writes the parameter block the solver starts from:
@@ -196,12 +197,21 @@ int mvs_fit_host(mvs_ctx* ctx, float* params_host, const float* gt_uv_host, cons
  *      the pose slots hold the latent code, which is zeroed as init_guess.py:96-98 does), transl = t, scale = s or
  *      fixed_scale.  Frames whose detections are degenerate (rank < 2) get the translation of the centroids only.
  *      params_dev [B,86] is overwritten; joints3d_dev [B,K,3] receives the triangulated keypoints (may be NULL).
- *      Uses the keypoints and cameras already uploaded; asynchronous on `stream`. */
+ *      Uses the keypoints and cameras already uploaded; asynchronous on `stream`.  The rest joints are computed once per
+ *      context and fixed_scale (seed + the 3-kernel geometry chain) and cached: a call is one launch afterwards.
+ *      The warm start of sequences (load_init, init_guess.py:137-166) is a parameter copy and has no entry point: pass the
+ *      previous result as params to mvs_fit with skip_stages (below). */
 typedef struct {
     int estimate_scale;            /* not setting['fix_scale'] (init_guess.py:24) */
     float fixed_scale;             /* setting['fixed_scale'] or 1 (init_guess.py:25) */
     int use_torso;                 /* align on keypoints 5, 6, 11, 12 only (main.py:77 passes True) */
     float hip_seed;                /* fix_params init_guess.py:198-201: 1.0 in the reference */
+    int umeyama_as_written;        /* 0: the published Umeyama algorithm (default).  1: what code/utils/umeyama.py computes: its
+                                      full-rank branch multiplies by the transpose of numpy's V^H (:67) -- a product that depends
+                                      on the sign convention of the LAPACK build; evaluated here with "largest-magnitude
+                                      component of every right singular vector positive" -- plus its two-candidate patch and
+                                      the translation taken from the negated candidate (:77-107).  Like sdf_all_faces = 0, the
+                                      switch exists for parity with the file, not because the result is a better fit. */
 } mvs_init_config;
 int mvs_init_guess(mvs_ctx* ctx, float* params_dev, float* joints3d_dev, const mvs_init_config* cfg, void* stream);
 

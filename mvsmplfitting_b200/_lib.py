@@ -54,7 +54,7 @@ class LbfgsStats(ctypes.Structure):
 class InitConfig(ctypes.Structure):
     """mvs_init_config (include/mvsmpl.h)"""
     _fields_ = [("estimate_scale", ctypes.c_int), ("fixed_scale", ctypes.c_float), ("use_torso", ctypes.c_int),
-                ("hip_seed", ctypes.c_float)]
+                ("hip_seed", ctypes.c_float), ("umeyama_as_written", ctypes.c_int)]
 
 
 EXPORTS = (

@@ -224,12 +224,15 @@ class FittingContext:
                                 frames_nan=st.frames_nan)
 
     def init_guess(self, estimate_scale: bool = True, fixed_scale: float = 1.0, use_torso: bool = True,
-                   hip_seed: float = 1.0, want_joints3d: bool = True):
-        """Initial parameter block of every frame from the uploaded detections (mvs_init_guess: triangulation +
-        similarity alignment, init_guess.py:18-107 + fix_params :190-212).  Returns (params [B,86], joints3d [B,K,3])."""
+                   hip_seed: float = 1.0, want_joints3d: bool = True, umeyama_as_written: bool = False):
+        """Initial parameter block of every frame from the uploaded detections (mvs_init_guess: triangulation -- or the
+        single-view depth guess -- + similarity alignment, init_guess.py:18-107 + fix_params :190-212).
+        umeyama_as_written: evaluate code/utils/umeyama.py as written (see include/mvsmpl.h) instead of the published
+        algorithm.  Returns (params [B,86], joints3d [B,K,3])."""
         params = torch.empty(self.B, 86, dtype=torch.float32, device=self.device)
         j3 = torch.empty(self.B, self.K, 3, dtype=torch.float32, device=self.device) if want_joints3d else None
-        cfg = _lib.InitConfig(int(bool(estimate_scale)), float(fixed_scale), int(bool(use_torso)), float(hip_seed))
+        cfg = _lib.InitConfig(int(bool(estimate_scale)), float(fixed_scale), int(bool(use_torso)), float(hip_seed),
+                              int(bool(umeyama_as_written)))
         _lib.check(self.h, self.lib.mvs_init_guess(self.h, _ptr(params), _ptr(j3), ctypes.byref(cfg), self._stream()),
                    "mvs_init_guess")
         return params, j3

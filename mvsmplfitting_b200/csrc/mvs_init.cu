@@ -24,22 +24,31 @@ __global__ void init_seed_kernel(float* __restrict__ params, int B, float scale)
     params[i] = (i % kParams == kOffScale) ? scale : 0.f;
 }
 
-// params [B,86] (seeded by init_seed_kernel; rewritten here), rest [B,K,3] rest joints of every frame,
+// params [B,86] (written completely), rest [K,3] rest joints of the model (the same for every frame),
 // gt_uv [V,B,K,2], conf [V,B,K]; joints3d [B,K,3] or nullptr
 __global__ void __launch_bounds__(128) init_guess_kernel(float* __restrict__ params, const float* __restrict__ rest,
                                                          CamSet cams, const float* __restrict__ gt_uv,
                                                          const float* __restrict__ conf, int B, int K, int estimate_scale,
-                                                         float fixed_scale, int use_torso, float hip_seed,
+                                                         float fixed_scale, int use_torso, float hip_seed, int as_written,
                                                          float* __restrict__ joints3d) {
     __shared__ double s_dst[4][kMaxKeypoints * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
     if (b >= B) return;                                   // whole warps leave together; only __syncwarp below
     double* dst = s_dst[warp];
+    float* x = params + (size_t)b * kParams;
+    for (int i = lane; i < kParams; i += 32) x[i] = 0.f;
     if (lane < K) {
         double X[3];
-        triangulate_point<double>(cams, gt_uv + ((size_t)b * K + lane) * 2, conf + (size_t)b * K + lane, (long)B * K * 2,
-                                  (long)B * K, X);
+        if (cams.num_views == 1) {                        // init_guess.py:54-78: depth guess along the optical axis
+            double rj[kMaxKeypoints * 3];
+            for (int i = 0; i < K * 3; ++i) rj[i] = (double)rest[i];
+            const double d = single_view_depth<double>(cams.cam[0], rj, gt_uv + (size_t)b * K * 2, conf + (size_t)b * K);
+            for (int c = 0; c < 3; ++c) X[c] = rj[3 * lane + c] + d * (double)cams.cam[0].R[6 + c];
+        } else {
+            triangulate_point<double>(cams, gt_uv + ((size_t)b * K + lane) * 2, conf + (size_t)b * K + lane, (long)B * K * 2,
+                                      (long)B * K, X);
+        }
         dst[3 * lane] = X[0]; dst[3 * lane + 1] = X[1]; dst[3 * lane + 2] = X[2];
         if (joints3d) {
             float* o = joints3d + ((size_t)b * K + lane) * 3;
@@ -54,13 +63,12 @@ __global__ void __launch_bounds__(128) init_guess_kernel(float* __restrict__ par
     for (int i = 0; i < n; ++i) {
         const int k = use_torso ? torso[i] : i;
         for (int c = 0; c < 3; ++c) {
-            src[3 * i + c] = (double)rest[((size_t)b * K + k) * 3 + c];
+            src[3 * i + c] = (double)rest[k * 3 + c];
             sel[3 * i + c] = dst[3 * k + c];
         }
     }
     double R[9], t[3], sc = 1.0, aa[3] = {0.0, 0.0, 0.0};
-    float* x = params + (size_t)b * kParams;
-    if (umeyama_fit<double>(src, sel, n, estimate_scale != 0, R, t, &sc)) {
+    if (umeyama_fit<double>(src, sel, n, estimate_scale != 0, R, t, &sc, as_written != 0)) {
         rotmat_to_aa<double>(R, aa);
     } else {                                              // degenerate detections (the reference raises): translate only
         sc = 1.0;
@@ -87,28 +95,38 @@ extern "C" int mvs_init_guess(mvs_ctx* ctx, float* params_dev, float* joints3d_d
     if (!(ctx->have_model && ctx->have_cams && ctx->have_kp && ctx->ws.B > 0))
         return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: model, cameras, batch and keypoints must be set first");
     if (!params_dev || !cfg) return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: NULL argument");
-    if (ctx->cams.num_views < 2)
-        return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: triangulation needs at least 2 views (the reference's "
-                                               "single-view depth guess, init_guess.py:54-78, is not part of this path)");
     const int K = ctx->m.K, B = ctx->ws.B;
     if (cfg->use_torso && K < 13) return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: use_torso needs keypoints 5, 6, 11, 12");
     if (!(cfg->fixed_scale > 0.f)) return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: fixed_scale must be positive");
     MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     Workspace& w = ctx->ws;
-    float* rest = w.grad_scratch;                          // [B,86] scratch of the closure; K*3 <= 86 floats per frame
-    static_assert(kMaxKeypoints * 3 <= 96, "rest-joint scratch");
     if (K * 3 > kParams) return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: more than 28 keypoints");
-    MVS_LAUNCH(ctx, KID_MISC, st, init_seed_kernel<<<(B * kParams + 255) / 256, 256, 0, st>>>(params_dev, B, cfg->fixed_scale));
-    const int vposer = ctx->loss.use_vposer;               // the rest pose is body_pose = 0 whatever the pose encoding
-    ctx->loss.use_vposer = 0;
-    const int rc = launch_closure(ctx, params_dev, nullptr, nullptr, rest, nullptr, nullptr, st, true);
-    ctx->loss.use_vposer = vposer;
-    if (rc) return rc;
+    if (ctx->cams.num_views == 1 && K < 13)
+        return set_error(ctx, MVS_ERR_INVALID, "mvs_init_guess: the single-view depth guess needs keypoints 5, 6, 11, 12");
+    // Rest joints (zero pose, zero shape, scale = fixed_scale; init_guess.py:29-52) are a property of the model: computed once
+    // per context and scale with the library's own forward pass (seed + the 3-kernel geometry chain), then cached, so that a
+    // call is ONE launch afterwards.
+    if (!ctx->rest_joints) {
+        int rc = dev_alloc(ctx, &ctx->rest_joints, (size_t)kMaxKeypoints * 3);
+        if (rc) return rc;
+    }
+    if (ctx->rest_scale != cfg->fixed_scale) {
+        float* rest = w.grad_scratch;                      // [B,86] scratch of the closure; K*3 <= 86 floats per frame
+        MVS_LAUNCH(ctx, KID_MISC, st, init_seed_kernel<<<(B * kParams + 255) / 256, 256, 0, st>>>(params_dev, B, cfg->fixed_scale));
+        const int vposer = ctx->loss.use_vposer;           // the rest pose is body_pose = 0 whatever the pose encoding
+        ctx->loss.use_vposer = 0;
+        const int rc = launch_closure(ctx, params_dev, nullptr, nullptr, rest, nullptr, nullptr, st, true);
+        ctx->loss.use_vposer = vposer;
+        if (rc) return rc;
+        MVS_CUDA_OK(ctx, cudaMemcpyAsync(ctx->rest_joints, rest, (size_t)K * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        ctx->rest_scale = cfg->fixed_scale;
+    }
     MVS_LAUNCH(ctx, KID_MISC, st,
-               init_guess_kernel<<<(B + 3) / 4, 128, 0, st>>>(params_dev, rest, ctx->cams, w.gt_uv, w.conf, B, K,
+               init_guess_kernel<<<(B + 3) / 4, 128, 0, st>>>(params_dev, ctx->rest_joints, ctx->cams, w.gt_uv, w.conf, B, K,
                                                               cfg->estimate_scale, cfg->fixed_scale, cfg->use_torso,
-                                                              vposer == 2 ? 0.f : cfg->hip_seed, joints3d_dev));
+                                                              ctx->loss.use_vposer == 2 ? 0.f : cfg->hip_seed,
+                                                              cfg->umeyama_as_written, joints3d_dev));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -4,10 +4,12 @@
 //
 // Reference (file:line of /root/reference/code):
 //   * triangulation            utils/recompute3D.py:24-61  (as written, incl. the float32 rounding of AtA at :52)
-//   * similarity alignment     utils/umeyama.py:18-109     -> the PUBLISHED algorithm (Umeyama, PAMI 1991, eq. 38-43)
-//                              that file says it restates.  Its own full-rank branch multiplies by the transpose of
-//                              numpy's V^H (:67); that product depends on the sign convention of the LAPACK build and
-//                              is not reproducible by any other SVD.  See oracle/init_oracle.py.
+//   * similarity alignment     utils/umeyama.py:18-109     -> by default the PUBLISHED algorithm (Umeyama, PAMI 1991,
+//                              eq. 38-43) that file says it restates.  Its own full-rank branch multiplies by the
+//                              transpose of numpy's V^H (:67); that product depends on the sign convention of the LAPACK
+//                              build.  umeyama_fit(as_written = true) evaluates the file's expression with a fixed sign
+//                              convention.  See oracle/init_oracle.py.
+//   * single-view depth guess  utils/init_guess.py:54-78
 //   * matrix -> axis-angle     cv2.Rodrigues as called at utils/init_guess.py:86
 //   * torso joints, scale      utils/init_guess.py:80-93
 #pragma once
@@ -143,7 +145,18 @@ template <class T> MVS_HD void jacobi_eig3(const T* S, T* lam, T* V) {
 // (eq. 41-42).  The right singular vectors come from the Jacobi eigen-decomposition of A^T A, u0, u1 from A v / sig
 // (re-orthonormalised), so nothing is divided by the smallest singular value (torso points are nearly coplanar).
 // Returns false (outputs untouched) if the points are degenerate (rank(A) < 2), umeyama.py:61-62.
-template <class T> MVS_HD bool umeyama_fit(const T* src, const T* dst, int n, bool estimate_scale, T* R, T* t, T* scale) {
+//
+// as_written = true evaluates what code/utils/umeyama.py computes instead (the `umeyama_as_written` switch of
+// mvs_init_config, like sdf_all_faces = 0 for the SDF term):
+//   * full rank: rot = U diag(d) (V^H)^T (umeyama.py:67 transposes the V^H numpy.linalg.svd returned).  That product is NOT
+//     invariant under the sign freedom of singular pairs (u_i, v_i) -> (-u_i, -v_i), so the file's output depends on the
+//     LAPACK build behind numpy; here the pairs are fixed by "the largest-magnitude component of v_i is positive" (the
+//     convention oracle/init_oracle.py: svd_sign_normalised applies to numpy's factors).  Rank 2: U V^H as published (:61-66);
+//   * the two-candidate patch (:77-107): the rotation with its first two columns negated replaces it when that lowers
+//     |scale * rot * src + t - dst|, and -- `rot` being a view of T -- the returned translation is ALWAYS computed from
+//     the negated one (:100).
+template <class T> MVS_HD bool umeyama_fit(const T* src, const T* dst, int n, bool estimate_scale, T* R, T* t, T* scale,
+                                           bool as_written = false) {
     T sm[3] = {T(0), T(0), T(0)}, dm[3] = {T(0), T(0), T(0)};
     for (int i = 0; i < n; ++i)
 #pragma unroll
@@ -203,10 +216,66 @@ template <class T> MVS_HD bool umeyama_fit(const T* src, const T* dst, int n, bo
         for (int c = 0; c < 3; ++c) R[3 * r + c] = u0[r] * V[3 * c] + u1[r] * V[3 * c + 1] + u2[r] * V[3 * c + 2];
     const T detA = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
     const T sc = estimate_scale ? (sig0 + sig1 + (detA < T(0) ? -sig2 : sig2)) / var : T(1);
+    if (as_written) {
+        if (sig2 > sig0 * T(3) * eps) {                        // full rank (numpy matrix_rank, umeyama.py:60,67)
+            T f[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const T a0 = mvs_abs(V[i]), a1 = mvs_abs(V[3 + i]), a2 = mvs_abs(V[6 + i]);
+                const T big = (a0 >= a1 && a0 >= a2) ? V[i] : (a1 >= a2 ? V[3 + i] : V[6 + i]);
+                f[i] = big < T(0) ? T(-1) : T(1);
+            }
+            // pairs (f_i u_i, f_i v_i); true u2 = d det(V') (u0' x u1'), so diag(d) leaves f2 (u0 x u1) in the third term;
+            // entry (i, c) of the untransposed factor is component i of v_c'
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    R[3 * r + c] = f[c] * (f[0] * u0[r] * V[c] + f[1] * u1[r] * V[3 + c] + f[2] * u2[r] * V[6 + c]);
+        }
+        T loss[2];
+#pragma unroll
+        for (int cand = 0; cand < 2; ++cand) {
+            const T sg = cand ? T(-1) : T(1);
+            T acc = T(0);
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const T e = sc * (sg * R[3 * r] * (src[3 * i] - sm[0]) + sg * R[3 * r + 1] * (src[3 * i + 1] - sm[1]) +
+                                      R[3 * r + 2] * (src[3 * i + 2] - sm[2])) + dm[r] - dst[3 * i + r];
+                    acc += e * e;
+                }
+            loss[cand] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)                            // translation: from the negated candidate, whichever wins
+            t[r] = dm[r] - sc * (-R[3 * r] * sm[0] - R[3 * r + 1] * sm[1] + R[3 * r + 2] * sm[2]);
+        if (loss[0] > loss[1]) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { R[3 * r] = -R[3 * r]; R[3 * r + 1] = -R[3 * r + 1]; }
+        }
+        *scale = sc;
+        return true;
+    }
 #pragma unroll
     for (int r = 0; r < 3; ++r) t[r] = dm[r] - sc * (R[3 * r] * sm[0] + R[3 * r + 1] * sm[1] + R[3 * r + 2] * sm[2]);
     *scale = sc;
     return true;
+}
+
+// Single-view depth guess (init_guess.py:54-78, as written): the rest joints pushed along the camera's optical axis by
+//   est_d = fx * (mean 3-D torso height) / (2-D torso height),
+// torso heights: |j5 - j11| and |j6 - j12| in 3-D (rest joints; camera rotation leaves the norms alone), and in 2-D the
+// L-shoulder -- L-hip difference taken TWICE (:66 repeats torso2d[0] - torso2d[2]) over the detection rows (u, v, conf),
+// i.e. the confidence difference is part of the norm.  joints3d = E^-1 (E j + est_d e_z) = j + est_d * R^T e_z.
+template <class T, class C> MVS_HD T single_view_depth(const C& cam, const T* rest, const float* uv, const float* conf) {
+    const T h3 = (mvs_sqrt((rest[15] - rest[33]) * (rest[15] - rest[33]) + (rest[16] - rest[34]) * (rest[16] - rest[34]) +
+                           (rest[17] - rest[35]) * (rest[17] - rest[35])) +
+                  mvs_sqrt((rest[18] - rest[36]) * (rest[18] - rest[36]) + (rest[19] - rest[37]) * (rest[19] - rest[37]) +
+                           (rest[20] - rest[38]) * (rest[20] - rest[38]))) * T(0.5);
+    const T du = T(uv[10]) - T(uv[22]), dv = T(uv[11]) - T(uv[23]), dc = T(conf[5]) - T(conf[11]);
+    const T h2 = mvs_sqrt(du * du + dv * dv + dc * dc);
+    return T(cam.f[0]) * (h3 / h2);
 }
 
 // cv2.Rodrigues, 3x3 rotation -> rotation vector (OpenCV calib3d cvRodrigues2, matrix branch; the input is already

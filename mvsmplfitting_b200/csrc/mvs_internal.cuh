@@ -176,6 +176,8 @@ struct mvs_ctx {
     void* lbfgs = nullptr;           // optimiser state (mvs_lbfgs.cu)
     mvs::Profiler prof;
     void* tc = nullptr;              // tensor-core path state (mvs_tc.cu)
+    float* rest_joints = nullptr;    // [K,3] keypoints of the rest pose at scale rest_scale (mvs_init.cu), computed once
+    float rest_scale = -1.f;
 };
 
 namespace mvs {

@@ -6,9 +6,9 @@ frames of the model's batch at once (the reference: one frame, numpy).
 setting['extris'] [V,4,4], setting['intris'] [V,3,3], setting['fix_scale'], setting['fixed_scale'],
 setting['pose_embedding']; data['keypoints'] = list over views of [B,17,3] arrays (u, v, confidence).
 
-Differences from the reference, all documented in DESIGN.md §7: the alignment is the published Umeyama algorithm (the
-reference's transposed-V variant depends on the LAPACK build); the single-view depth guess (:54-78) is not part of the
-multi-view path and raises."""
+Difference from the reference, documented in DESIGN.md §7: the alignment is the published Umeyama algorithm unless
+`umeyama_as_written=True` is passed (keyword of init_guess / load_init; the reference's transposed-V variant depends on the
+LAPACK build, see include/mvsmpl.h).  One view: the depth guess of :54-78, as written."""
 from __future__ import annotations
 
 import numpy as np
@@ -18,11 +18,9 @@ from ..fitting import model_context
 from ..seqio import camera_arrays
 
 
-def _run_device_guess(setting, data, use_torso, hip_seed):
+def _run_device_guess(setting, data, use_torso, hip_seed, as_written=False):
     model = setting["model"]
     keypoints = data["keypoints"]
-    if len(keypoints) < 2:
-        raise NotImplementedError("single-view depth guess (init_guess.py:54-78) is outside the multi-view path")
     est_scale = not setting["fix_scale"]                                                   # init_guess.py:24
     fixed_scale = 1.0 if setting.get("fixed_scale") is None else float(setting["fixed_scale"])   # :25
     ctx = model_context(model)
@@ -32,7 +30,7 @@ def _run_device_guess(setting, data, use_torso, hip_seed):
     K = kp.shape[2]
     ctx.set_keypoints(np.ascontiguousarray(kp[..., :2]), np.ascontiguousarray(kp[..., 2]), np.ones(K, np.float32))
     params, joints3d = ctx.init_guess(estimate_scale=est_scale, fixed_scale=fixed_scale, use_torso=use_torso,
-                                      hip_seed=hip_seed)
+                                      hip_seed=hip_seed, umeyama_as_written=as_written)
     return params, joints3d, est_scale, fixed_scale
 
 
@@ -42,7 +40,8 @@ def init_guess(setting, data, use_torso=False, **kwargs):
     if kwargs.get("use_3d") and data.get("3d_joint") is not None:
         raise NotImplementedError("3-D joint annotations (init_guess.py:76-77) are outside the path (use_3d = False)")
     model = setting["model"]
-    params, _, est_scale, fixed_scale = _run_device_guess(setting, data, use_torso, hip_seed=0.0)
+    params, _, est_scale, fixed_scale = _run_device_guess(setting, data, use_torso, hip_seed=0.0,
+                                                          as_written=bool(kwargs.get("umeyama_as_written", False)))
     p = params.detach()
     dtype = setting.get("dtype", torch.float32)
     scale = p[:, 85:86].to(dtype) if est_scale else torch.full((p.shape[0], 1), fixed_scale, dtype=dtype, device=p.device)

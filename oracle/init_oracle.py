@@ -49,7 +49,20 @@ def triangulate(extris, intris, keypoints):
     return np.stack([np.linalg.solve(AtA[i], Atb[i]) for i in range(K)])
 
 
-def umeyama_as_written(src, dst, estimate_scale):
+def svd_sign_normalised(A):
+    """numpy's SVD with the sign freedom of every singular pair (u_i, v_i) fixed: the largest-magnitude component of v_i is
+    positive.  The convention of the device's as-written variant (mvs_init.cuh: umeyama_fit(as_written)); numpy's own
+    signs are whatever the LAPACK build produces."""
+    U, S, Vh = np.linalg.svd(A)
+    U, Vh = U.copy(), Vh.copy()
+    for i in range(Vh.shape[0]):
+        if Vh[i, np.argmax(np.abs(Vh[i]))] < 0:
+            Vh[i] *= -1
+            U[:, i] *= -1
+    return U, S, Vh
+
+
+def umeyama_as_written(src, dst, estimate_scale, svd=np.linalg.svd):
     """umeyama.py:18-109, quirks kept: `V` is numpy's V^H and the full-rank branch transposes it (:67); `rot` is a
     VIEW of T, so negating its first two columns for the second candidate (:80-82) also changes the T that the
     returned translation is computed from (:100)."""
@@ -62,7 +75,7 @@ def umeyama_as_written(src, dst, estimate_scale):
     if np.linalg.det(A) < 0:
         d[dim - 1] = -1
     T = np.eye(dim + 1)
-    U, S, V = np.linalg.svd(A)
+    U, S, V = svd(A)
     rank = np.linalg.matrix_rank(A)
     if rank == 0:
         return np.nan * T
@@ -141,12 +154,34 @@ def rotmat_to_aa(R):
     return r * (theta / (2.0 * s))
 
 
+def single_view_joints(extri, intri, keypoints0, rest_joints):
+    """init_guess.py:54-78 line by line: depth guess for single-view input.  keypoints0 [17,3] (u, v, conf) of the only view.
+    Quirks kept: the 2-D torso height is the L-shoulder -- L-hip difference twice (:66), taken over (u, v, conf) rows."""
+    joints = np.asarray(rest_joints, np.float64)
+    extri, intri = np.asarray(extri, np.float64), np.asarray(intri, np.float64)
+    torso3d = joints[[5, 6, 11, 12]]
+    torso2d = np.asarray(keypoints0, np.float64)[[5, 6, 11, 12]]
+    torso3d = np.insert(torso3d, 3, 1, axis=1).T
+    torso3d = (np.dot(extri, torso3d).T)[:, :3]
+    diff3d = np.array([torso3d[0] - torso3d[2], torso3d[1] - torso3d[3]])
+    mean_height3d = np.mean(np.sqrt(np.sum(diff3d ** 2, axis=1)))
+    diff2d = np.array([torso2d[0] - torso2d[2], torso2d[0] - torso2d[2]])
+    mean_height2d = np.mean(np.sqrt(np.sum(diff2d ** 2, axis=1)))
+    est_d = intri[0][0] * (mean_height3d / mean_height2d)
+    cam_joints = np.dot(extri, np.insert(joints.copy(), 3, 1, axis=1).T)
+    cam_joints[2, :] += est_d
+    return (np.dot(np.linalg.inv(extri), cam_joints).T)[:, :3]
+
+
 def init_guess(extris, intris, keypoints, rest_joints, estimate_scale, fixed_scale=1.0, use_torso=True,
-               as_written=False):
-    """init_guess.py:18-107 for >= 2 views: returns dict(joints3d [17,3], global_orient [3], transl [3], scale).
+               as_written=False, svd=np.linalg.svd):
+    """init_guess.py:18-107: returns dict(joints3d [17,3], global_orient [3], transl [3], scale).
     rest_joints [17,3] = the model's joints at zero pose / zero shape / scale = fixed_scale (init_guess.py:36-52)."""
-    j3 = triangulate(extris, intris, keypoints)
+    if len(keypoints) == 1:
+        j3 = single_view_joints(extris[0], intris[0], np.asarray(keypoints[0]).reshape(-1, 3), rest_joints)
+    else:
+        j3 = triangulate(extris, intris, keypoints)
     sel = list(TORSO) if use_torso else list(range(j3.shape[0]))
-    fn = umeyama_as_written if as_written else umeyama
+    fn = (lambda a, b, e: umeyama_as_written(a, b, e, svd=svd)) if as_written else umeyama
     R, t, s = fn(np.asarray(rest_joints, np.float64)[sel], j3[sel], estimate_scale)
     return dict(joints3d=j3, global_orient=rotmat_to_aa(R), transl=t, scale=(s if estimate_scale else fixed_scale), R=R)

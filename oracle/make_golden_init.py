@@ -84,6 +84,49 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, "init_s21.npz"), **out)
     print("wrote", os.path.join(GOLD, "init_s21.npz"), {k: v.shape for k, v in out.items()})
+    whole_init_guess()
+
+
+def whole_init_guess():
+    """tests/golden/init_guess_ref.npz: the reference's own init_guess + fix_params (code/utils/init_guess.py:18-107,190-212),
+    UNMODIFIED, on the synthetic model: multi-view (triangulation) and single-view (depth guess, :54-78) inputs.  The file
+    hard-codes `.cuda()` at :38; Tensor.cuda is a no-op while it runs here."""
+    import torch
+    ns = H.import_reference()
+    with H.in_reference_dir():
+        from utils import init_guess as RIG
+    model = S.make_model(0)
+    rm = H.build_reference_model(model)
+    out = {}
+    cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for tag, V, est in (("mv4", 4, True), ("sv", 1, False), ("sv_est", 1, True)):
+            cams = S.make_cameras(max(V, 4))
+            cams = {k: v[:V] for k, v in cams.items() if isinstance(v, np.ndarray)}
+            fr = S.make_frames(model, cams, 4, seed=700 + V)
+            ext = np.tile(np.eye(4), (V, 1, 1))
+            ext[:, :3, :3], ext[:, :3, 3] = cams["R"], cams["t"]
+            intr = np.tile(np.eye(3), (V, 1, 1))
+            intr[:, 0, 0], intr[:, 1, 1], intr[:, 0, 2], intr[:, 1, 2] = cams["f"][:, 0], cams["f"][:, 1], cams["c"][:, 0], cams["c"][:, 1]
+            res = []
+            for b in range(4):
+                kps = [np.concatenate([fr["gt_uv"][v, b], fr["conf"][v, b][:, None]], axis=1)[None].astype(np.float32) for v in range(V)]
+                setting = dict(model=rm, dtype=torch.float32, batch_size=1, device=torch.device("cpu"), fix_scale=not est,
+                               fixed_scale=None, extris=ext, intris=intr)
+                data = {"keypoints": kps, "3d_joint": None}
+                RIG.init_guess(setting, data, use_torso=True, model_type="smpllsp", use_vposer=False, use_3d=False)
+                RIG.fix_params(setting, scale=None, shape=None)
+                res.append(np.concatenate([rm.betas.detach().numpy().reshape(-1), rm.global_orient.detach().numpy().reshape(-1),
+                                           rm.body_pose.detach().numpy().reshape(-1), rm.transl.detach().numpy().reshape(-1),
+                                           rm.scale.detach().numpy().reshape(-1)]))
+            out[tag + "_ext"], out[tag + "_int"] = ext, intr
+            out[tag + "_uv"], out[tag + "_conf"] = fr["gt_uv"], fr["conf"]
+            out[tag + "_params"] = np.stack(res)
+    finally:
+        torch.Tensor.cuda = cuda
+    np.savez_compressed(os.path.join(GOLD, "init_guess_ref.npz"), **out)
+    print("wrote init_guess_ref.npz", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -137,7 +137,7 @@ def triangulate(cams, uv, conf, use_double=True):
     return X
 
 
-def umeyama(src, dst, estimate_scale, use_double=True):
+def umeyama(src, dst, estimate_scale, use_double=True, as_written=False):
     """mvs_init.cuh umeyama_fit + rotmat_to_aa on the host -> (R [3,3], t [3], scale, aa [3]) or None if degenerate"""
     lib = _build()
     src = np.ascontiguousarray(src, dtype=np.float64)
@@ -145,8 +145,20 @@ def umeyama(src, dst, estimate_scale, use_double=True):
     R, t, s, aa = np.zeros(9), np.zeros(3), np.zeros(1), np.zeros(3)
     lib.hostsim_umeyama.restype = ctypes.c_int
     ok = lib.hostsim_umeyama(ctypes.c_int(src.shape[0]), _P(src), _P(dst), ctypes.c_int(int(estimate_scale)),
-                             ctypes.c_int(int(use_double)), _P(R), _P(t), _P(s), _P(aa))
+                             ctypes.c_int(int(use_double)), _P(R), _P(t), _P(s), _P(aa), ctypes.c_int(int(as_written)))
     return (R.reshape(3, 3), t, float(s[0]), aa) if ok else None
+
+
+def single_view_joints(cam, rest, uv, conf):
+    """mvs_init.cuh single_view_depth on the host: cam dict of ONE view (R [3,3], t, f, c), rest [K,3] -> joints3d [K,3]"""
+    lib = _build()
+    rest = np.ascontiguousarray(rest, dtype=np.float64)
+    uv = np.ascontiguousarray(uv, dtype=np.float32)
+    conf = np.ascontiguousarray(conf, dtype=np.float32)
+    R, t, f, c = (np.ascontiguousarray(np.asarray(cam[k], dtype=np.float32), dtype=np.float64) for k in ("R", "t", "f", "c"))
+    X = np.zeros((rest.shape[0], 3))
+    lib.hostsim_single_view(ctypes.c_int(rest.shape[0]), _P(R), _P(t), _P(f), _P(c), _P(rest), _P(uv), _P(conf), _P(X))
+    return X
 
 
 def rotmat_to_aa(R):

@@ -304,20 +304,31 @@ void hostsim_triangulate(int V, int K, const double* cR, const double* ct, const
 }
 // returns 1 if a transform was found.  src, dst [n,3]; R [9] row-major, t [3], scale [1], aa [3] = rotmat_to_aa(R)
 int hostsim_umeyama(int n, const double* src, const double* dst, int estimate_scale, int use_double, double* R, double* t,
-                    double* scale, double* aa) {
+                    double* scale, double* aa, int as_written) {
     if (use_double) {
-        if (!umeyama_fit<double>(src, dst, n, estimate_scale != 0, R, t, scale)) return 0;
+        if (!umeyama_fit<double>(src, dst, n, estimate_scale != 0, R, t, scale, as_written != 0)) return 0;
         rotmat_to_aa<double>(R, aa);
         return 1;
     }
     float s[51], d[51], Rf[9], tf[3], sf, af[3];
     for (int i = 0; i < 3 * n; ++i) { s[i] = (float)src[i]; d[i] = (float)dst[i]; }
-    if (!umeyama_fit<float>(s, d, n, estimate_scale != 0, Rf, tf, &sf)) return 0;
+    if (!umeyama_fit<float>(s, d, n, estimate_scale != 0, Rf, tf, &sf, as_written != 0)) return 0;
     rotmat_to_aa<float>(Rf, af);
     for (int i = 0; i < 9; ++i) R[i] = Rf[i];
     for (int i = 0; i < 3; ++i) { t[i] = tf[i]; aa[i] = af[i]; }
     *scale = sf;
     return 1;
+}
+// init_guess.py:54-78 on the host: cam (R [9], t [3], f [2], c [2]), rest [K,3], uv [K,2], conf [K] -> joints3d [K,3]
+void hostsim_single_view(int K, const double* cR, const double* ct, const double* cf, const double* cc, const double* rest,
+                         const float* uv, const float* conf, double* X) {
+    CamF cam;
+    for (int i = 0; i < 9; ++i) cam.R[i] = (float)cR[i];
+    for (int i = 0; i < 3; ++i) cam.t[i] = (float)ct[i];
+    for (int i = 0; i < 2; ++i) { cam.f[i] = (float)cf[i]; cam.c[i] = (float)cc[i]; }
+    const double d = single_view_depth<double>(cam, rest, uv, conf);
+    for (int k = 0; k < K; ++k)
+        for (int c = 0; c < 3; ++c) X[3 * k + c] = rest[3 * k + c] + d * (double)cam.R[6 + c];
 }
 void hostsim_rotmat_to_aa(int n, const double* R, double* aa) {
     for (int i = 0; i < n; ++i) rotmat_to_aa<double>(R + 9 * i, aa + 3 * i);

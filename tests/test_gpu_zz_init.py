@@ -14,12 +14,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def worker(B, V, estimate_scale, use_torso):
+def worker(B, V, estimate_scale, use_torso, as_written=False):
     import torch
     sys.path.insert(0, ROOT)
     from mvsmplfitting_b200 import synthetic as S
     from mvsmplfitting_b200.context import FittingContext
-    model, cams = S.make_model(0), S.make_cameras(V)
+    model, cams = S.make_model(0), _cams(S, V)
     fr = S.make_frames(model, cams, B, seed=900 + V)
     ctx = FittingContext(0)
     ctx.set_model(model)
@@ -27,25 +27,41 @@ def worker(B, V, estimate_scale, use_torso):
     ctx.set_batch(B)
     ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
     n0 = ctx.launch_count()
-    params, j3 = ctx.init_guess(estimate_scale=estimate_scale, fixed_scale=1.0, use_torso=use_torso, hip_seed=1.0)
+    params, j3 = ctx.init_guess(estimate_scale=estimate_scale, fixed_scale=1.0, use_torso=use_torso, hip_seed=1.0,
+                                umeyama_as_written=as_written)
     torch.cuda.synchronize()
-    out = dict(params=params.cpu().numpy().tolist(), j3=j3.cpu().numpy().tolist(), launches=int(ctx.launch_count() - n0))
+    n1 = ctx.launch_count()
+    p2, _ = ctx.init_guess(estimate_scale=estimate_scale, fixed_scale=1.0, use_torso=use_torso, hip_seed=1.0,
+                           umeyama_as_written=as_written)                       # rest joints cached: one launch
+    torch.cuda.synchronize()
+    assert torch.equal(p2, params)
+    out = dict(params=params.cpu().numpy().tolist(), j3=j3.cpu().numpy().tolist(), launches=int(n1 - n0),
+               launches_again=int(ctx.launch_count() - n1))
     ctx.close()
     print("RESULT" + json.dumps(out))
 
 
+def _cams(S, V):
+    cams = S.make_cameras(max(V, 4))
+    return {k: (v[:V] if isinstance(v, np.ndarray) else v) for k, v in cams.items()}
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,V,est,torso", [(37, 4, True, True), (64, 8, False, True), (5, 16, True, False)])
-def test_init_guess_matches_oracle(B, V, est, torso):
+@pytest.mark.parametrize("B,V,est,torso,aw", [(37, 4, True, True, False), (64, 8, False, True, False), (5, 16, True, False, False),
+                                              (37, 4, True, True, True), (9, 1, False, True, False), (9, 1, True, True, True)])
+def test_init_guess_matches_oracle(B, V, est, torso, aw):
+    """aw: mvs_init_config.umeyama_as_written (the file's expression under the fixed sign convention); V = 1: the single-view
+    depth guess of init_guess.py:54-78"""
     from mvsmplfitting_b200 import synthetic as S
     from oracle import init_oracle as IO
-    p = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(V), str(int(est)), str(int(torso))],
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(V), str(int(est)), str(int(torso)), str(int(aw))],
                        capture_output=True, text=True, timeout=180)
     assert p.returncode == 0, p.stderr[-2000:]
     out = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1][6:])
     params, j3 = np.array(out["params"]), np.array(out["j3"])
-    assert out["launches"] <= 8                                # seed + forward chain + init kernel
-    model, cams = S.make_model(0), S.make_cameras(V)
+    assert out["launches"] <= 8                                # first call: seed + forward chain + init kernel
+    assert out["launches_again"] == 1                          # rest joints are cached per context
+    model, cams = S.make_model(0), _cams(S, V)
     fr = S.make_frames(model, cams, B, seed=900 + V)
     z = lambda n: np.zeros((1, n))
     rest = S.model_keypoints_np(model, z(10), z(3), z(69), z(3), np.ones((1, 1)), "smpllsp")[0]
@@ -55,16 +71,16 @@ def test_init_guess_matches_oracle(B, V, est, torso):
     intr[:, 0, 0], intr[:, 1, 1], intr[:, 0, 2], intr[:, 1, 2] = cams["f"][:, 0], cams["f"][:, 1], cams["c"][:, 0], cams["c"][:, 1]
     for b in range(B):
         kps = [np.concatenate([fr["gt_uv"][v, b], fr["conf"][v, b][:, None]], axis=1) for v in range(V)]
-        o = IO.init_guess(ext, intr, kps, rest, est, 1.0, torso)
+        o = IO.init_guess(ext, intr, kps, rest, est, 1.0, torso, as_written=aw, svd=IO.svd_sign_normalised)
         assert np.abs(j3[b] - o["joints3d"]).max() / np.abs(o["joints3d"]).max() < 1e-4          # parity bar
         x = params[b]
         assert np.abs(x[10:13] - o["global_orient"]).max() < 2e-3      # rest joints travel as float32
         assert np.abs(x[82:85] - o["transl"]).max() < 2e-3 * max(1.0, np.abs(o["transl"]).max())
         assert abs(x[85] - o["scale"]) < 1e-3 * o["scale"]
         assert (x[:10] == 0).all() and (x[13:19] == 1).all() and (x[19:82] == 0).all()
-        # the guess is useful: the aligned torso lands on the triangulated torso
-        assert np.abs(x[82:85] - fr["gt"]["transl"][b]).max() < 0.5
+        if V > 1 and not aw:       # the guess is useful: the aligned torso lands on the triangulated torso
+            assert np.abs(x[82:85] - fr["gt"]["transl"][b]).max() < 0.5
 
 
 if __name__ == "__main__":
-    worker(int(sys.argv[1]), int(sys.argv[2]), bool(int(sys.argv[3])), bool(int(sys.argv[4])))
+    worker(int(sys.argv[1]), int(sys.argv[2]), bool(int(sys.argv[3])), bool(int(sys.argv[4])), bool(int(sys.argv[5])))

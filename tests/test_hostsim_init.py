@@ -113,3 +113,43 @@ def test_whole_initial_guess_matches_oracle(V, est, torso):
         assert abs(s - (o["scale"] if est else 1.0)) < 1e-4
         if torso:      # the point of the guess: the frame's true translation is recovered to a few cm
             assert np.abs(t - fr["gt"]["transl"][b]).max() < 0.5
+
+
+def test_umeyama_as_written_matches_the_file_under_the_fixed_sign_convention(gold):
+    """umeyama_fit(as_written): the expression of code/utils/umeyama.py (transposed V^H at :67, two-candidate patch, translation
+    from the negated candidate) with the singular pairs' signs fixed; the oracle restatement of the file is pinned bit for bit
+    to the reference run with numpy's own SVD (tests/test_init_golden.py) and takes the same convention through svd=."""
+    differs = 0
+    for k in range(len(gold["um_n"])):
+        n = int(gold["um_n"][k])
+        src, dst, est = gold["um_src"][k, :n], gold["um_dst"][k, :n], bool(gold["um_est"][k])
+        R, t, s = IO.umeyama_as_written(src, dst, est, svd=IO.svd_sign_normalised)
+        got = HS.umeyama(src, dst, est, True, as_written=True)
+        assert np.abs(got[0] - R).max() < 1e-9 and np.abs(got[1] - t).max() < 1e-8 and abs(got[2] - s) < 1e-9
+        assert abs(np.linalg.det(got[0]) - 1) < 1e-9
+        gf = HS.umeyama(src, dst, est, False, as_written=True)
+        assert np.abs(gf[0] - R).max() < 2e-3
+        differs += np.abs(got[0] - IO.umeyama(src, dst, est)[0]).max() > 1e-3
+    assert differs >= len(gold["um_n"]) // 2      # it really is a different rotation from the published algorithm's
+
+
+def test_single_view_depth_guess_matches_the_restatement():
+    from mvsmplfitting_b200 import synthetic as S
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "init_guess_ref.npz"))
+    model = S.make_model(0)
+    z = lambda n: np.zeros((1, n))
+    rest = S.model_keypoints_np(model, z(10), z(3), z(69), z(3), np.ones((1, 1)), "smpllsp")[0].astype(np.float32)
+    ext, intr = g["sv_ext"][0], g["sv_int"][0]
+    cam = dict(R=ext[:3, :3], t=ext[:3, 3], f=np.array([intr[0, 0], intr[1, 1]]), c=np.array([intr[0, 2], intr[1, 2]]))
+    for b in range(g["sv_uv"].shape[1]):
+        kp = np.concatenate([g["sv_uv"][0, b], g["sv_conf"][0, b][:, None]], axis=1)
+        ref = IO.single_view_joints(ext, intr, kp, rest)
+        got = HS.single_view_joints(cam, rest, g["sv_uv"][0, b], g["sv_conf"][0, b])
+        assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
+        # whole single-view guess, as written, under the fixed sign convention
+        o = IO.init_guess(ext[None], intr[None], [kp], rest, False, 1.0, True, as_written=True, svd=IO.svd_sign_normalised)
+        R, t, s, aa = HS.umeyama(rest[list(IO.TORSO)], got[list(IO.TORSO)], False, True, as_written=True)
+        assert np.abs(aa - o["global_orient"]).max() < 1e-4 and np.abs(t - o["transl"]).max() < 1e-3
+        # published algorithm: the guess is a pure translation along the optical axis
+        Rp = HS.umeyama(rest[list(IO.TORSO)], got[list(IO.TORSO)], False, True)[0]
+        assert np.abs(Rp - np.eye(3)).max() < 1e-6

@@ -60,3 +60,26 @@ def test_rotmat_to_aa_is_cv2_rodrigues(gold):
             assert min(np.abs(mine - r).max(), np.abs(mine + r).max()) < 1e-5
         else:
             assert np.abs(mine - r).max() < 1e-9 + 1e-7 * ang
+
+
+REF = os.path.join(os.path.dirname(__file__), "golden", "init_guess_ref.npz")
+
+
+@pytest.mark.parametrize("tag,est", [("mv4", True), ("sv", False), ("sv_est", True)])
+def test_whole_init_guess_as_written_is_the_reference_run(tag, est, syn_model):
+    """init_guess + fix_params of the reference, run unmodified on the synthetic model (oracle/make_golden_init.py), against
+    the restatement with as_written=True and numpy's own SVD (same LAPACK as the authoring run): multi-view triangulation and
+    the single-view depth guess (init_guess.py:54-78)."""
+    from mvsmplfitting_b200 import synthetic as S
+    g = np.load(REF)
+    z = lambda n: np.zeros((1, n))
+    rest = S.model_keypoints_np(syn_model, z(10), z(3), z(69), z(3), np.ones((1, 1)), "smpllsp")[0]
+    V = g[tag + "_ext"].shape[0]
+    for b in range(g[tag + "_params"].shape[0]):
+        kps = [np.concatenate([g[tag + "_uv"][v, b], g[tag + "_conf"][v, b][:, None]], axis=1) for v in range(V)]
+        o = IO.init_guess(g[tag + "_ext"], g[tag + "_int"], kps, rest, est, 1.0, True, as_written=True)
+        x = g[tag + "_params"][b]
+        assert np.abs(o["global_orient"] - x[10:13]).max() < 2e-4, (tag, b)       # the reference's rest joints are float32
+        assert np.abs(o["transl"] - x[82:85]).max() < 2e-4 * max(1.0, np.abs(x[82:85]).max())
+        assert abs(o["scale"] - x[85]) < 1e-4 * x[85]
+        assert (x[:10] == 0).all() and (x[13:19] == 1).all() and (x[19:82] == 0).all()      # fix_params

@@ -30,21 +30,24 @@ class StubCtx:
 
     def set_cameras(self, R, t, f, c):
         self.calls.append("cams")
-        assert np.allclose(R, self.ext[:, :3, :3]) and np.allclose(t, self.ext[:, :3, 3])
-        assert np.allclose(f[:, 0], self.intr[:, 0, 0]) and np.allclose(c[:, 1], self.intr[:, 1, 2])
+        V = R.shape[0]
+        assert np.allclose(R, self.ext[:V, :3, :3]) and np.allclose(t, self.ext[:V, :3, 3])
+        assert np.allclose(f[:, 0], self.intr[:V, 0, 0]) and np.allclose(c[:, 1], self.intr[:V, 1, 2])
 
     def set_keypoints(self, gt_uv, conf, jw):
         self.calls.append("kp")
         self.gt_uv, self.conf = np.asarray(gt_uv), np.asarray(conf)
         assert self.gt_uv.shape[1] == self.B and self.gt_uv.shape[2:] == (17, 2) and jw.sum() == 17
 
-    def init_guess(self, estimate_scale, fixed_scale, use_torso, hip_seed):
+    def init_guess(self, estimate_scale, fixed_scale, use_torso, hip_seed, umeyama_as_written=False):
         self.calls.append(("init", estimate_scale, fixed_scale, use_torso, hip_seed))
+        self.as_written = umeyama_as_written
         V = self.gt_uv.shape[0]
         x = np.zeros((self.B, 86), np.float32)
         for b in range(self.B):
             kps = [np.concatenate([self.gt_uv[v, b], self.conf[v, b][:, None]], 1) for v in range(V)]
-            o = IO.init_guess(self.ext, self.intr, kps, self.rest, estimate_scale, fixed_scale, use_torso)
+            o = IO.init_guess(self.ext[:V], self.intr[:V], kps, self.rest, estimate_scale, fixed_scale, use_torso,
+                              as_written=umeyama_as_written, svd=IO.svd_sign_normalised)
             x[b, 10:13], x[b, 82:85], x[b, 85] = o["global_orient"], o["transl"], o["scale"]
         return torch.tensor(x), None
 
@@ -89,8 +92,10 @@ def test_init_guess_then_fix_params(B, fix_scale, syn_model, monkeypatch):
         assert np.allclose(model.betas.detach().numpy(), 0.5) and np.allclose(model.scale.detach().numpy(), 1.1)
     else:
         assert model.scale.requires_grad and torch.equal(model.scale.detach(), s0)
-    with pytest.raises(NotImplementedError):
-        IG.init_guess(setting, dict(keypoints=data["keypoints"][:1]), use_torso=True)
+    # one view (init_guess.py:54-78) and the as-written alignment reach the context as options of the same call
+    setting1 = dict(setting, extris=setting["extris"][:1], intris=setting["intris"][:1])
+    IG.init_guess(setting1, dict(keypoints=data["keypoints"][:1]), use_torso=True, umeyama_as_written=True)
+    assert stub.as_written is True and stub.gt_uv.shape[0] == 1
 
 
 def test_load_init_warm_start_and_fallback(syn_model, monkeypatch):

@@ -81,6 +81,11 @@ int mvs_set_gmm_prior(mvs_ctx* ctx, int num_gaussians, const float* means, const
 int mvs_set_vposer(mvs_ctx* ctx, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                    const float* out_w, const float* out_b);
 
+/* vposer.decode(pose_embedding, output_type='aa') on its own (what save_results does with the fitted latent code before it
+ * writes a result, code/utils/utils.py:741-743): params_dev [B,86] with the latent code in the first 32 entries of the
+ * body_pose slot -> body_pose_dev [B,69] axis-angle.  Needs mvs_set_vposer. */
+int mvs_vposer_decode(mvs_ctx* ctx, const float* params_dev, float* body_pose_dev, void* stream);
+
 /* PerspectiveCamera list (code/camera.py:41-117, built in code/init.py:108-131): host arrays
  * R [V,3,3], t [V,3], f [V,2] (focal x,y), c [V,2] */
 int mvs_set_cameras(mvs_ctx* ctx, int num_views, const float* R, const float* t, const float* f, const float* c);
@@ -176,6 +181,16 @@ int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last
  *      configuration set.  Synchronises. */
 int mvs_fit(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
             float* final_loss_dev, mvs_lbfgs_stats* stats, void* stream);
+
+/* ---- mvs_fit for video sequences (is_seq, code/main.py:76-79 + code/utils/non_linear_solver.py:157-162): warm_host [B]
+ *      (HOST bytes, may be NULL = mvs_fit) marks the frames that continue a sequence -- their params_dev rows hold the previous
+ *      frame's result as load_init leaves it (code/utils/init_guess.py:137-166 + fix_params) -- and that therefore skip the
+ *      first two stages and run the third with 0.15 x its body_pose_weight; the other frames run every stage.  Frames of
+ *      one call are independent, so a batch is e.g. frame t of S sequences, some of them at their first frame.  Needs
+ *      n_stages > 2 when any frame is warm; not implemented in the batched reference chain (exec mode 1). */
+int mvs_fit_seq(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs,
+                const mvs_lbfgs_config* opt_cfg, const unsigned char* warm_host, float* final_loss_dev,
+                mvs_lbfgs_stats* stats, void* stream);
 
 /* ---- host-buffer entry point (what a caller without device memory uses): copies keypoints and
  *      parameters host->device, runs `n_stages` optimisation stages (one mvs_loss_config each, the weight

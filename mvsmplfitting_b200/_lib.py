@@ -59,8 +59,8 @@ class InitConfig(ctypes.Structure):
 
 EXPORTS = (
     "mvs_version", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
-    "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
-    "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
+    "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_vposer_decode", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
+    "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_seq", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
     "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor", "mvs_init_guess",
 )
 NUM_KERNEL_IDS = 18
@@ -98,8 +98,11 @@ def load() -> ctypes.CDLL:
     lib.mvs_lbfgs_run.argtypes = [vp, vp, vp, ctypes.POINTER(LbfgsConfig), ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_lbfgs_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LbfgsConfig), ci, ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_set_vposer.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mvs_vposer_decode.argtypes = [vp, vp, vp, vp]
     lib.mvs_init_guess.argtypes = [vp, vp, vp, ctypes.POINTER(InitConfig), vp]
     lib.mvs_fit.argtypes = [vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp, ctypes.POINTER(LbfgsStats), vp]
+    lib.mvs_fit_seq.argtypes = [vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp, vp,
+                                ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_fit_host.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp,
                                  ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_sdf_grid.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, vp]

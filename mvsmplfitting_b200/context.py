@@ -117,6 +117,13 @@ class FittingContext:
         assert arrs[0].shape == (512, 32) and arrs[2].shape == (512, 512) and arrs[4].shape == (138, 512)
         _lib.check(self.h, self.lib.mvs_set_vposer(self.h, *[_ptr(a) for a in arrs]), "mvs_set_vposer")
 
+    def vposer_decode(self, params: torch.Tensor) -> torch.Tensor:
+        """vposer.decode(z, 'aa') of the latent codes in params[:, 13:45] (mvs_vposer_decode) -> body_pose [B,69]"""
+        assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous() and params.shape == (self.B, 86)
+        out = torch.empty(self.B, 69, dtype=torch.float32, device=self.device)
+        _lib.check(self.h, self.lib.mvs_vposer_decode(self.h, _ptr(params), _ptr(out), self._stream()), "mvs_vposer_decode")
+        return out
+
     def set_cameras(self, R, t, f, c):
         R, t, f, c = _f32(R), _f32(t), _f32(f), _f32(c)
         self.V = R.shape[0]
@@ -237,16 +244,24 @@ class FittingContext:
                    "mvs_init_guess")
         return params, j3
 
-    def fit(self, params: torch.Tensor, stage_cfgs, opt_cfg=None):
+    def fit(self, params: torch.Tensor, stage_cfgs, opt_cfg=None, warm=None):
         """All stages of a fit on device buffers (mvs_fit): params [B,86] CUDA float32, updated in place.  Frames move
-        from stage to stage on their own; returns (final_loss [B], stats)."""
+        from stage to stage on their own; returns (final_loss [B], stats).  warm [B] bool (mvs_fit_seq): frames that
+        continue a video sequence from the previous frame's result skip stages 0, 1 and damp stage 2's pose prior
+        (non_linear_solver.py:157-162)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
         arr = (_lib.LossConfig * len(stage_cfgs))(*stage_cfgs)
         cfg = opt_cfg or self.make_lbfgs_config()
         final = torch.empty(self.B, dtype=torch.float32, device=self.device)
         st = _lib.LbfgsStats()
-        _lib.check(self.h, self.lib.mvs_fit(self.h, _ptr(params), len(stage_cfgs), arr, ctypes.byref(cfg), _ptr(final),
-                                            ctypes.byref(st), self._stream()), "mvs_fit")
+        if warm is not None:
+            wm = np.ascontiguousarray(np.asarray(warm).astype(np.uint8).reshape(self.B))
+            _lib.check(self.h, self.lib.mvs_fit_seq(self.h, _ptr(params), len(stage_cfgs), arr, ctypes.byref(cfg),
+                                                    wm.ctypes.data_as(ctypes.c_void_p), _ptr(final), ctypes.byref(st),
+                                                    self._stream()), "mvs_fit_seq")
+        else:
+            _lib.check(self.h, self.lib.mvs_fit(self.h, _ptr(params), len(stage_cfgs), arr, ctypes.byref(cfg), _ptr(final),
+                                                ctypes.byref(st), self._stream()), "mvs_fit")
         return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
                            frames_nan=st.frames_nan)
 

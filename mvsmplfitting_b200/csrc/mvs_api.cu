@@ -509,6 +509,14 @@ int mvs_forward(mvs_ctx* ctx, const float* params_dev, float* joints_dev, float*
     return launch_closure(ctx, params_dev, nullptr, nullptr, joints_dev, nullptr, verts_dev, (cudaStream_t)stream, true);
 }
 
+int mvs_vposer_decode(mvs_ctx* ctx, const float* params_dev, float* body_pose_dev, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    MVS_REQUIRE(ctx, ctx->have_model && ctx->ws.B > 0 && ctx->m.vp_w1, "mvs_vposer_decode: model, batch and mvs_set_vposer first");
+    MVS_REQUIRE(ctx, params_dev && body_pose_dev, "mvs_vposer_decode: NULL argument");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return launch_vposer_decode(ctx, params_dev, body_pose_dev, (cudaStream_t)stream);
+}
+
 int mvs_sdf_grid(mvs_ctx* ctx, float* phi_dev, const int* faces_dev, int num_faces, const float* verts_dev, int batch,
                  int n_verts, int grid_size, void* stream) {
     if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");

@@ -178,6 +178,7 @@ struct mvs_ctx {
     void* tc = nullptr;              // tensor-core path state (mvs_tc.cu)
     float* rest_joints = nullptr;    // [K,3] keypoints of the rest pose at scale rest_scale (mvs_init.cu), computed once
     float rest_scale = -1.f;
+    int* stage_rng = nullptr;        // [B][2] per-frame slice of the stage table (mvs_fit_seq), device
 };
 
 namespace mvs {
@@ -263,11 +264,13 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
 int launch_sdf_terms(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);   // mvs_sdf.cu
 // mvs_resident.cu: frame-resident (one CTA per frame) closure and whole-stage optimiser for the sparse regime
 bool resident_closure_available(const mvs_ctx* ctx);
+int launch_vposer_decode(mvs_ctx* ctx, const float* x_dev, float* body_pose_dev, cudaStream_t st);
 int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* grad_dev, float* joints_dev,
                             float* proj_dev, cudaStream_t st);
 bool resident_lbfgs_available(const mvs_ctx* ctx, int history);
 int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg, int history, const void* lp_tab_dev,
-                          const void* lp_tab_host, int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st);
+                          const void* lp_tab_host, int nstages, void* frame_scalars_out, float* last_grad_dev, cudaStream_t st,
+                          const void* stage_rng_dev = nullptr);
 // dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
 int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st, bool allow_tc = true);                                   // mvs_closure.cu

@@ -34,7 +34,8 @@ namespace mvs {
 
 // reset != 0: fresh optimiser (new stage).  reset == 0: next step() of the same optimiser: history, d, t,
 // H_diag, prev_flat_grad, prev_loss and n_iter persist (lbfgs_ls.py:292-300,436-443).
-__global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params, int B, int reset) {
+__global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params, int B, int reset, int nstages,
+                                  const int2* __restrict__ stage_rng) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= B) return;
     VLOOP(i) S.x_eval[(size_t)b * kParams + i] = params[(size_t)b * kParams + i];
@@ -49,6 +50,11 @@ __global__ void lbfgs_init_kernel(LbfgsState S, const float* __restrict__ params
         }
         s.phase = PH_STEP_ENTRY;
         s.final_loss = __int_as_float(0x7fc00000);
+        if (reset) {                                        // this frame's slice of the stage table (mvs_fit_seq)
+            s.stage = stage_rng ? stage_rng[b].x : 0;
+            s.stage_end = stage_rng ? stage_rng[b].y : nstages;
+            if (s.stage >= s.stage_end) s.phase = PH_DONE;  // no stage of this run is for this frame
+        }
         S.sc[b] = s;
     }
 }
@@ -172,7 +178,8 @@ static int ensure_state(mvs_ctx* ctx, int H) {
 // (frame-resident or dense rounds, see run_fit): every frame then walks through the stages at its own pace.
 static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, const mvs_lbfgs_config* c,
                      mvs_lbfgs_stats* stats, cudaStream_t st, int step_mode = 0, int reset = 1,
-                     float* last_grad_dev = nullptr, const LossParams* lps = nullptr, int nst = 1) {
+                     float* last_grad_dev = nullptr, const LossParams* lps = nullptr, int nst = 1,
+                     const int2* stage_rng = nullptr, bool some_inactive = false) {
     const int B = ctx->ws.B;
     const int H = c->history_size > 0 ? c->history_size : 100;
     if (H > 128) return set_error(ctx, MVS_ERR_INVALID, "mvs_lbfgs_run: history_size must be <= 128");
@@ -200,7 +207,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.lp_tab, S.lp_tab_host, (size_t)nst * sizeof(LossParams), cudaMemcpyHostToDevice, st));
     if (!step_mode && resident_lbfgs_available(ctx, H)) {
         // sparse regime: every frame runs its whole stage inside one CTA (mvs_resident.cu): one launch, no rounds
-        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.lp_tab, lps, nst, S.sc, last_grad_dev, st);
+        rc = launch_lbfgs_resident(ctx, params_dev, &cfg, H, S.lp_tab, lps, nst, S.sc, last_grad_dev, st, stage_rng);
         if (rc) return rc;
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));
         long long* th = reinterpret_cast<long long*>(S.na_host) + 1;
@@ -222,7 +229,9 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) is not implemented in the batched "
                                                "reference chain (exec mode 1): use use_vposer = 1 there");
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
-    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset));
+    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, params_dev, B, reset, nst, stage_rng));
+    if (some_inactive)                                      // frames without a stage in this run leave the active list now
+        MVS_LAUNCH(ctx, KID_LBFGS_COMPACT, st, lbfgs_compact_kernel<<<1, 1024, 0, st>>>(S, B, w.fidx, w.na));
     if ((!step_mode || vp2) && hybrid_available(ctx)) {
         // dense regime (SDF term on): four launches per round -- pose blend shapes of the active frames (tcgen05
         // GEMM), skinning + box partials, the SDF term with the adjoint of its (short) vertex list, and the per-frame
@@ -333,7 +342,7 @@ int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, floa
     S.lp_tab_host[0] = ctx->loss;
     MVS_CUDA_OK(ctx, cudaMemcpyAsync(S.lp_tab, S.lp_tab_host, sizeof(LossParams), cudaMemcpyHostToDevice, st));
     MVS_LAUNCH(ctx, KID_MISC, st, iota2_kernel<<<(B + 255) / 256, 256, 0, st>>>(w.fidx, B, w.na));
-    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, x_dev, B, 1));
+    MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_init_kernel<<<B, 32, 0, st>>>(S, x_dev, B, 1, 1, nullptr));
     w.na_bound = B;
     if ((rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, 1, st))) return rc;
     if ((rc = frame_step_begin_run(ctx, st))) return rc;
@@ -353,12 +362,32 @@ int dense_regime_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, floa
 // the stage boundary for the slowest one; the per-frame arithmetic is the sequential schedule's).  exec_mode 2 keeps
 // the stage barrier (one run per stage).
 static int run_fit(mvs_ctx* ctx, float* x_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
-                   float* final_loss_dev, mvs_lbfgs_stats* stats, cudaStream_t st) {
+                   float* final_loss_dev, mvs_lbfgs_stats* stats, cudaStream_t st, const unsigned char* warm_host = nullptr) {
     if (n_stages > 64) return set_error(ctx, MVS_ERR_INVALID, "mvs_fit: at most 64 stages");
     std::vector<LossParams> lps(n_stages);
     for (int i = 0; i < n_stages; ++i) {
         const int rc = make_loss_params(ctx, &stage_cfgs[i], &lps[i]);
         if (rc) return rc;
+    }
+    const int B = ctx->ws.B;
+    // warm-started frames (is_seq, non_linear_solver.py:157-162): no stage 0 and 1, stage 2 with 0.15 x body_pose_weight
+    constexpr int kWarmSkip = 2;
+    bool any_warm = false;
+    if (warm_host)
+        for (int b = 0; b < B; ++b) any_warm |= warm_host[b] != 0;
+    if (any_warm && n_stages <= kWarmSkip)
+        return set_error(ctx, MVS_ERR_INVALID, "mvs_fit_seq: warm-started frames skip the first %d stages, %d given", kWarmSkip, n_stages);
+    std::vector<LossParams> wlps;
+    if (any_warm) {
+        wlps = lps;
+        std::vector<mvs_loss_config> wc(stage_cfgs, stage_cfgs + n_stages);
+        wc[kWarmSkip].body_pose_weight *= 0.15f;
+        const int rc = make_loss_params(ctx, &wc[kWarmSkip], &wlps[kWarmSkip]);
+        if (rc) return rc;
+        if (!ctx->stage_rng) {
+            const int rc2 = dev_alloc(ctx, &ctx->stage_rng, (size_t)B * 2);
+            if (rc2) return rc2;
+        }
     }
     const int H = opt_cfg->history_size > 0 ? opt_cfg->history_size : 100;
     auto regime = [&](const LossParams& lp) {
@@ -366,16 +395,43 @@ static int run_fit(mvs_ctx* ctx, float* x_dev, int n_stages, const mvs_loss_conf
         if (hybrid_available_for(ctx, lp)) return 1;
         return 2;
     };
+    const int max_run = any_warm ? kMaxStages / 2 : kMaxStages;       // the table holds the cold and the warm slice of a run
+    std::vector<int> rng;
     int i = 0;
     while (i < n_stages) {
         const int rg = regime(lps[i]);
         int j = i + 1;
-        while (ctx->exec_mode != 2 && rg != 2 && j < n_stages && j - i < kMaxStages && regime(lps[j]) == rg &&
+        while (ctx->exec_mode != 2 && rg != 2 && j < n_stages && j - i < max_run && regime(lps[j]) == rg &&
                lps[j].sdf_grid == lps[i].sdf_grid && lps[j].sdf_all_faces == lps[i].sdf_all_faces)
             ++j;
         ctx->loss = lps[i];
         ctx->have_loss = true;
-        const int rc = run_stage(ctx, x_dev, final_loss_dev, opt_cfg, stats, st, 0, 1, nullptr, &lps[i], j - i);
+        int rc;
+        if (!any_warm) {
+            rc = run_stage(ctx, x_dev, final_loss_dev, opt_cfg, stats, st, 0, 1, nullptr, &lps[i], j - i);
+        } else {
+            if (rg == 2)
+                return set_error(ctx, MVS_ERR_INVALID, "mvs_fit_seq: warm-started frames are not implemented in the batched "
+                                                       "reference chain (exec mode 1 / a model the resident kernels do not take)");
+            // table of this run: cold stages i .. j-1, then the warm slice max(i, 2) .. j-1
+            std::vector<LossParams> tab(lps.begin() + i, lps.begin() + j);
+            const int wi = i > kWarmSkip ? i : kWarmSkip;
+            const int wbegin = (int)tab.size();
+            for (int k = wi; k < j; ++k) tab.push_back(wlps[k]);
+            const int wend = (int)tab.size();
+            rng.assign((size_t)B * 2, 0);
+            bool inactive = false;
+            for (int b = 0; b < B; ++b) {
+                const bool wm = warm_host[b] != 0;
+                rng[2 * b] = wm ? wbegin : 0;
+                rng[2 * b + 1] = wm ? wend : j - i;
+                inactive |= wm && wbegin == wend;
+            }
+            MVS_CUDA_OK(ctx, cudaMemcpyAsync(ctx->stage_rng, rng.data(), rng.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));           // rng is reused by the next run
+            rc = run_stage(ctx, x_dev, final_loss_dev, opt_cfg, stats, st, 0, 1, nullptr, tab.data(), (int)tab.size(),
+                           reinterpret_cast<const int2*>(ctx->stage_rng), inactive);
+        }
         if (rc) return rc;
         i = j;
     }
@@ -410,6 +466,17 @@ int mvs_lbfgs_step(mvs_ctx* ctx, float* params_dev, float* loss_dev, float* last
     MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof(*stats));
     return run_stage(ctx, params_dev, loss_dev, cfg, stats, (cudaStream_t)stream, 1, reset ? 1 : 0, last_grad_dev);
+}
+
+int mvs_fit_seq(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,
+                const unsigned char* warm_host, float* final_loss_dev, mvs_lbfgs_stats* stats, void* stream) {
+    if (!ctx) return set_error(nullptr, MVS_ERR_INVALID, "ctx is NULL");
+    if (!(ctx->have_model && ctx->have_cams && ctx->have_kp && ctx->ws.B > 0))
+        return set_error(ctx, MVS_ERR_INVALID, "mvs_fit_seq: model, cameras, batch and keypoints must be set first");
+    if (!params_dev || n_stages <= 0 || !stage_cfgs || !opt_cfg) return set_error(ctx, MVS_ERR_INVALID, "mvs_fit_seq: NULL / empty argument");
+    MVS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    return run_fit(ctx, params_dev, n_stages, stage_cfgs, opt_cfg, final_loss_dev, stats, (cudaStream_t)stream, warm_host);
 }
 
 int mvs_fit(mvs_ctx* ctx, float* params_dev, int n_stages, const mvs_loss_config* stage_cfgs, const mvs_lbfgs_config* opt_cfg,

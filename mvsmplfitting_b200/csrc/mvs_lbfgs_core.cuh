@@ -17,6 +17,7 @@ struct FrameScalars {
     int hist_len, hist_head, nan_flag;
     int pushed_slot;                 // ring slot written by the last advance call (-1: none)
     int stage;                       // index into the stage table of a multi-stage run (frames change stage on their own)
+    int stage_end;                   // one past this frame's last entry of the table (warm-started frames own a different slice)
     int nan_acc;                     // NaN / Inf stops of the stages this frame already left
     float t, H_diag, gtd0, t_prev, gtd_prev, d_norm;
     float bt[2], bgtd[2], bf[2];

@@ -78,12 +78,26 @@ closure_resident_kernel(ResidentModel m, CamSet cams, LossParams lp, const float
         for (int i = threadIdx.x; i < kParams; i += kResThreads) grad_out[(size_t)b * kParams + i] = S.lg_new[i];
 }
 
+// VPoser.decode(z, 'aa') alone (result export: code/utils/utils.py:741-743 decodes the fitted latent code before saving)
+__global__ void __launch_bounds__(kResThreads, 2)
+vposer_decode_kernel(ResidentModel m, const float* __restrict__ x, int B, float* __restrict__ body_pose) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
+    VposerSmem& W = *reinterpret_cast<VposerSmem*>(smem_raw + sizeof(ResidentSmem));
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    for (int i = threadIdx.x; i < kParams; i += kResThreads) S.x[i] = x[(size_t)b * kParams + i];
+    __syncthreads();
+    vposer_decode(S, m, W);
+    if (threadIdx.x < 69) body_pose[(size_t)b * 69 + threadIdx.x] = W.th[threadIdx.x];
+}
+
 // ------------------------------------------------------------------------------------------------ whole stage
 __global__ void __launch_bounds__(kResThreads, 2)
 lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict__ lp_tab, int nstages, LbfgsCfg cfg,
                       float* __restrict__ params, const float* __restrict__ gt_uv, const float* __restrict__ conf,
                       const float* __restrict__ joint_w, int B, int H, FrameScalars* __restrict__ sc_out,
-                      float* __restrict__ last_grad_out, int with_vposer) {
+                      float* __restrict__ last_grad_out, int with_vposer, const int2* __restrict__ stage_rng) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
     float* hy = reinterpret_cast<float*>(smem_raw + sizeof(ResidentSmem));
@@ -91,6 +105,18 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
     VposerSmem* W = with_vposer ? reinterpret_cast<VposerSmem*>(hs + (size_t)H * kParams) : nullptr;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (b >= B) return;
+    // this frame's slice of the stage table (all of it unless the run mixes cold and warm-started frames, mvs_fit_seq)
+    const int st_begin = stage_rng ? stage_rng[b].x : 0, st_end = stage_rng ? stage_rng[b].y : nstages;
+    if (st_begin >= st_end) {                                            // nothing to do in this run: parameters stay
+        if (t == 0) {
+            FrameScalars s;
+            memset(&s, 0, sizeof(s));
+            s.phase = PH_DONE;
+            s.final_loss = __int_as_float(0x7fc00000);
+            sc_out[b] = s;
+        }
+        return;
+    }
     resident_setup(S, m);
     for (int i = t; i < kParams; i += kResThreads) { const float v = params[(size_t)b * kParams + i]; S.lx[i] = v; S.lx_eval[i] = v; }
     if (t == 0) {
@@ -99,9 +125,10 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
         s.phase = PH_STEP_ENTRY;
         s.H_diag = 1.f;
         s.final_loss = __int_as_float(0x7fc00000);
+        s.stage = st_begin; s.stage_end = st_end;
         S.fs = s;
     }
-    if (t < (int)(sizeof(LossParams) / 4)) reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[0])[t];
+    if (t < (int)(sizeof(LossParams) / 4)) reinterpret_cast<int*>(&S.lp)[t] = reinterpret_cast<const int*>(&lp_tab[st_begin])[t];
     __syncthreads();
     LbfgsPtrs P{S.lx, S.lg, S.ld, S.lprev_g, S.lx_init, S.lg_prev, S.lbg0, S.lbg1, hy, hs, S.ro, S.al, S.lx_eval, S.lg_new, H,
                 S.gram, S.tl_scratch};
@@ -109,7 +136,7 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
     // against hanging the GPU): every outer step costs at most 1 + max_eval + max_iter evaluations
     const long long eval_cap = (long long)cfg.max_outer * (cfg.max_eval + cfg.max_iter + 2) + 8;
     long long stage_ev0 = 0;
-    int cur_stage = 0;
+    int cur_stage = st_begin;
     while (true) {
         PHASE_MARK(0);
         for (int i = t; i < kParams; i += kResThreads) S.x[i] = S.lx_eval[i];
@@ -121,7 +148,7 @@ lbfgs_resident_kernel(ResidentModel m, CamSet cams, const LossParams* __restrict
             FrameScalars s = S.fs;
             lbfgs_advance_core(s, P, S.sc[2], cfg, lane, S.lp.use_vposer == 2 ? 32 : kOffTransl - kOffPose);
             if (s.evals - stage_ev0 >= eval_cap && s.phase != PH_DONE) { s.phase = PH_DONE; s.nan_flag = 1; }
-            if (s.phase == PH_DONE && s.stage + 1 < nstages) {          // this frame moves on to its next stage
+            if (s.phase == PH_DONE && s.stage + 1 < s.stage_end) {      // this frame moves on to its next stage
                 next_stage_scalars(s);
                 VLOOP(i) S.lx_eval[i] = S.lx[i];
             }
@@ -238,6 +265,15 @@ int launch_closure_resident(mvs_ctx* ctx, const float* x_dev, float* loss_dev, f
     return MVS_OK;
 }
 
+int launch_vposer_decode(mvs_ctx* ctx, const float* x_dev, float* body_pose_dev, cudaStream_t st) {
+    const size_t smem = sizeof(ResidentSmem) + sizeof(VposerSmem);
+    MVS_CUDA_OK(ctx, cudaFuncSetAttribute(vposer_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVS_LAUNCH(ctx, KID_MISC, st,
+               vposer_decode_kernel<<<ctx->ws.B, kResThreads, smem, st>>>(make_resident_model(ctx), x_dev, ctx->ws.B, body_pose_dev));
+    MVS_CUDA_OK(ctx, cudaGetLastError());
+    return MVS_OK;
+}
+
 bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int H) {
     const bool sdf_on = lp.interpenetration && lp.coll_loss_weight > 0.f;
     return resident_supported(ctx) && !sdf_on && H <= 100;
@@ -245,7 +281,8 @@ bool resident_lbfgs_available_for(const mvs_ctx* ctx, const LossParams& lp, int 
 bool resident_lbfgs_available(const mvs_ctx* ctx, int H) { return resident_lbfgs_available_for(ctx, ctx->loss, H); }
 
 int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, int H, const void* lp_tab_dev,
-                          const void* lp_tab_host, int nstages, void* sc_out, float* last_grad_dev, cudaStream_t st) {
+                          const void* lp_tab_host, int nstages, void* sc_out, float* last_grad_dev, cudaStream_t st,
+                          const void* stage_rng_dev) {
     Workspace& w = ctx->ws;
     const LbfgsCfg& cfg = *static_cast<const LbfgsCfg*>(cfg_ptr);
     const LossParams* lph = static_cast<const LossParams*>(lp_tab_host);
@@ -260,7 +297,8 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* cfg_ptr, 
                lbfgs_resident_kernel<<<w.B, kResThreads, smem, st>>>(make_resident_model(ctx), ctx->cams,
                                                                      static_cast<const LossParams*>(lp_tab_dev), nstages, cfg,
                                                                      params_dev, w.gt_uv, w.conf, w.joint_w, w.B, H,
-                                                                     static_cast<FrameScalars*>(sc_out), last_grad_dev, with_vposer));
+                                                                     static_cast<FrameScalars*>(sc_out), last_grad_dev, with_vposer,
+                                                                     static_cast<const int2*>(stage_rng_dev)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

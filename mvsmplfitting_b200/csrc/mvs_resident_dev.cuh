@@ -748,8 +748,9 @@ __device__ __forceinline__ void resident_setup(ResidentSmem& S, const ResidentMo
 // problems, so nothing makes a fast frame wait for the slowest one at a stage boundary.
 __device__ __forceinline__ void next_stage_scalars(FrameScalars& s) {
     const long long it = s.iters, ev = s.evals;
-    const int st = s.stage + 1, nacc = s.nan_acc + s.nan_flag;
+    const int st = s.stage + 1, nacc = s.nan_acc + s.nan_flag, end = s.stage_end;
     memset(&s, 0, sizeof(s));
+    s.stage_end = end;
     s.H_diag = 1.f;
     s.phase = PH_STEP_ENTRY;
     s.final_loss = __int_as_float(0x7fc00000);
@@ -966,7 +967,7 @@ __device__ __forceinline__ void frame_step_body(unsigned char* smem_raw, const F
                     S.lg_new, L.H, S.gram, S.tl_scratch};
         lbfgs_advance_core(s, P, S.sc[2], cfg, lane, S.lp.use_vposer == 2 ? 32 : kOffTransl - kOffPose);
         __syncwarp();
-        if (s.phase == PH_DONE && s.stage + 1 < nstages) {      // this frame moves on to its next stage
+        if (s.phase == PH_DONE && s.stage + 1 < s.stage_end) {  // this frame moves on to its next stage
             next_stage_scalars(s);
             VLOOP(i) S.lx_eval[i] = S.lx[i];
             __syncwarp();

@@ -111,3 +111,39 @@ def test_fit_host_matches_fit_device(syn_model, syn_gmm):
     assert np.array_equal(fh, fd.cpu().numpy(), equal_nan=True)
     assert sh["frame_evals"] == sd["frame_evals"]
     ctx.close()
+
+
+@pytest.mark.parametrize("sdf_from", [None, 2])
+def test_fit_seq_warm_frames_skip_two_stages(sdf_from, syn_model, syn_gmm):
+    """mvs_fit_seq (is_seq, non_linear_solver.py:157-162): a warm frame's result is, bit for bit, what mvs_fit gives it with
+    the stage list [2 (0.15 x body_pose_weight), 3]; a cold frame in the same batch gets the full schedule; no flags = mvs_fit"""
+    cams = S.make_cameras(4)
+    B = 6
+    fr = S.make_frames(syn_model, cams, B, seed=515)
+    X0 = S.pack_params(fr["init"])
+    warm = np.array([1, 0, 1, 1, 0, 0], bool)
+
+    def run(stage_fn, warm_flags=None):
+        ctx = _ctx(syn_model, cams, syn_gmm, B)
+        ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+        x = torch.tensor(X0, device="cuda")
+        final, st = ctx.fit(x, stage_fn(ctx), ctx.make_lbfgs_config(max_outer=4), warm=warm_flags)
+        out = x.cpu().numpy().copy(), final.cpu().numpy().copy(), st
+        ctx.close()
+        return out
+
+    def warm_stages(ctx):
+        st = _stages(ctx, sdf_from)[2:]
+        st[0].body_pose_weight *= 0.15
+        st[0].bending_prior_weight = _stages(ctx, sdf_from)[2].bending_prior_weight        # only the pose prior is damped
+        return st
+
+    x_seq, f_seq, st_seq = run(lambda c: _stages(c, sdf_from), warm)
+    x_cold, f_cold, st_cold = run(lambda c: _stages(c, sdf_from))
+    x_warm, f_warm, _ = run(warm_stages)
+    assert np.array_equal(x_seq[~warm], x_cold[~warm]) and np.array_equal(f_seq[~warm], f_cold[~warm])
+    assert np.array_equal(x_seq[warm], x_warm[warm]) and np.array_equal(f_seq[warm], f_warm[warm])
+    assert not np.array_equal(x_seq[warm], x_cold[warm])
+    assert st_seq["frame_iterations"] < st_cold["frame_iterations"] and st_seq["frames_nan"] == 0
+    x_none, f_none, _ = run(lambda c: _stages(c, sdf_from), np.zeros(B, bool))
+    assert np.array_equal(x_none, x_cold) and np.array_equal(f_none, f_cold)

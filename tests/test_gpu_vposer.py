@@ -74,6 +74,32 @@ def test_closure_with_the_shipped_snapshot_matches_reference(stage, syn_model):
     ctx.close()
 
 
+def test_vposer_decode_entry_point_matches_the_reference_class(syn_model):
+    """mvs_vposer_decode (what save_results does before writing a result, utils.py:741-743) against decode outputs of the
+    unmodified reference class, synthetic weights and the shipped snapshot (incl. decode(0): max |aa| = 0.8225)"""
+    from tests.test_vposer_golden import _real_weights
+    for gold, weights in ((GOLD, None), (REAL, _real_weights())):
+        c = np.load(gold)
+        Z = c["Z"]
+        from mvsmplfitting_b200.context import FittingContext
+        ctx = FittingContext(0)
+        ctx.set_model(syn_model)
+        ctx.set_vposer(S.make_vposer(11) if weights is None else weights)
+        ctx.set_batch(Z.shape[0])
+        x = np.zeros((Z.shape[0], 86), np.float32)
+        x[:, 13:45] = Z
+        aa = ctx.vposer_decode(torch.tensor(x, device="cuda")).cpu().numpy()
+        ref = c["aa_f64"]
+        # rotations near pi flip the axis sign with the last bit: compare as rotations there
+        ang = np.linalg.norm(ref.reshape(-1, 23, 3), axis=2)
+        err = np.abs(aa - ref).reshape(-1, 23, 3).max(axis=2)
+        assert (err[ang < 3.0] < 2e-4 * np.maximum(1.0, ang[ang < 3.0])).all(), gold
+        assert (np.abs(np.linalg.norm(aa.reshape(-1, 23, 3), axis=2) - ang)[ang >= 3.0] < 1e-3).all()
+        if weights is not None:
+            assert abs(np.abs(aa[0]).max() - 0.8225) < 1e-4
+        ctx.close()
+
+
 def test_lbfgs_in_latent_space(syn_model):
     c = np.load(GOLD)
     ctx = _ctx(syn_model, c, 2)

@@ -86,41 +86,102 @@ def test_result_pickle_and_obj(tmp_path):
     assert np.allclose([float(t) for t in lines[0].split()[1:]], verts[0], atol=1e-7)
 
 
+class StubCtx:                                      # records what the drivers ask of a FittingContext
+    def __init__(self, B):
+        self.B, self.calls = B, []
+
+    def set_keypoints(self, gt_uv, conf, jw):
+        self.calls.append(("kp", gt_uv.shape, conf.shape, jw.sum()))
+        self.kp0 = float(gt_uv[0, 0, 0, 0])
+
+    def set_loss(self, config=None):
+        self.calls.append(("loss", config.use_vposer))
+
+    def init_guess(self, **kw):
+        import torch
+        self.calls.append(("init", kw["estimate_scale"], kw["use_torso"], kw["hip_seed"]))
+        return torch.arange(self.B * 86, dtype=torch.float32).reshape(self.B, 86), None
+
+    def fit(self, params, stage_cfgs, opt_cfg, warm=None):
+        import torch
+        self.calls.append(("fit", len(stage_cfgs), None if warm is None else list(map(bool, warm)), params.clone()))
+        params += 1
+        return torch.arange(1, self.B + 1, dtype=torch.float32), dict(frame_iterations=7, frame_evals=9, rounds=1, frames_nan=0)
+
+    def vposer_decode(self, params):
+        import torch
+        self.calls.append(("decode",))
+        return torch.full((self.B, 69), 0.25) + params[:, 13:14]
+
+    def forward_only(self, params, want_verts=True):
+        import torch
+        self.calls.append(("fwd", float(params[0, 13 + 18]), float(params[0, 13 + 17])))
+        return dict(verts=torch.zeros(self.B, 5, 3))
+
+
+def _cfgs(n, use_vposer=0, use_joints_conf=1):
+    from types import SimpleNamespace
+    return [SimpleNamespace(use_vposer=use_vposer, use_joints_conf=use_joints_conf) for _ in range(n)]
+
+
 def test_fit_sequence_drives_the_context_in_batch_order(tmp_path):
-    import torch
     write_demo(str(tmp_path))
     seq = seqio.load_sequence(str(tmp_path / "keypoints"), "0007")
-
-    class StubCtx:                                  # records what the driver asks of a FittingContext
-        B, calls = 4, []
-
-        def set_keypoints(self, gt_uv, conf, jw):
-            self.calls.append(("kp", gt_uv.shape, conf.shape, jw.sum()))
-
-        def init_guess(self, **kw):
-            self.calls.append(("init", kw["estimate_scale"], kw["use_torso"], kw["hip_seed"]))
-            return torch.arange(4 * 86, dtype=torch.float32).reshape(4, 86), None
-
-        def fit(self, params, stage_cfgs, opt_cfg):
-            self.calls.append(("fit", len(stage_cfgs)))
-            params += 1
-            return torch.tensor([1.0, 2.0, 3.0, 4.0]), dict(frame_iterations=7)
-
-        def forward_only(self, params, want_verts=True):
-            self.calls.append(("fwd", float(params[0, 13 + 18]), float(params[0, 13 + 17])))
-            return dict(verts=torch.zeros(4, 5, 3))
-
-    ctx = StubCtx()
-    x, loss, st = seqio.fit_sequence(ctx, seq, stage_cfgs=[1, 2, 3, 4], result_folder=str(tmp_path / "res"),
+    ctx = StubCtx(4)
+    x, loss, st = seqio.fit_sequence(ctx, seq, stage_cfgs=_cfgs(4), result_folder=str(tmp_path / "res"),
                                      mesh_folder=str(tmp_path / "mesh"), faces=np.array([[0, 1, 2]]))
-    assert [c[0] for c in ctx.calls] == ["kp", "init", "fit", "fwd"]
-    assert ctx.calls[0][1:] == ((3, 4, 17, 2), (3, 4, 17), 15.0) and ctx.calls[1][1:] == (False, True, 1.0)
-    assert ctx.calls[3][1] == 0.0 and ctx.calls[3][2] == 13 + 17 + 1          # mesh from the saved (zeroed) pose
+    assert [c[0] for c in ctx.calls] == ["kp", "loss", "init", "fit", "fwd"]
+    assert ctx.calls[0][1:] == ((3, 4, 17, 2), (3, 4, 17), 15.0) and ctx.calls[2][1:] == (False, True, 1.0)
+    assert ctx.calls[4][1] == 0.0 and ctx.calls[4][2] == 13 + 17 + 1          # mesh from the saved (zeroed) pose
     assert x.shape == (4, 86) and x[1, 0] == 87 and loss.tolist() == [1, 2, 3, 4] and st["frame_iterations"] == 7
     for b, fr in enumerate(seq["frames"]):
         got = pickle.load(open(tmp_path / "res" / "0007" / fr / "000.pkl", "rb"))
-        assert got["loss"] == b + 1 and got["transl"][0, 0] == b * 86 + 82 + 1
+        assert got["loss"] == b + 1 and got["transl"][0, 0] == b * 86 + 82 + 1 and got["pose_embedding"] is None
         assert os.path.exists(tmp_path / "mesh" / "0007" / fr / "000.obj")
+    # a (view, frame) without detections is only neutral when the loss uses the confidences (main.py:45-56 drops the view)
+    with pytest.raises(ValueError):
+        seqio.fit_sequence(StubCtx(4), seq, stage_cfgs=_cfgs(4, use_joints_conf=0))
+    with pytest.raises(NotImplementedError):
+        seqio.fit_sequence(StubCtx(4), seq, stage_cfgs=_cfgs(4, use_vposer=1))
+
+
+def test_fit_sequence_with_latent_pose_saves_the_decoded_pose(tmp_path):
+    """use_vposer = 2 (the reference's default configuration): the initial guess sees the stage configuration (latent code
+    starts at 0), results hold decode(latent) with the extremities zeroed plus 'pose_embedding' (utils.py:741-759), the mesh
+    is built from that pose"""
+    write_demo(str(tmp_path))
+    seq = seqio.load_sequence(str(tmp_path / "keypoints"), "0007")
+    ctx = StubCtx(4)
+    x, loss, st = seqio.fit_sequence(ctx, seq, stage_cfgs=_cfgs(4, use_vposer=2), result_folder=str(tmp_path / "res"),
+                                     mesh_folder=str(tmp_path / "mesh"), faces=np.array([[0, 1, 2]]))
+    assert [c[0] for c in ctx.calls] == ["kp", "loss", "init", "fit", "decode", "fwd"] and ctx.calls[1][1] == 2
+    got = pickle.load(open(tmp_path / "res" / "0007" / seq["frames"][1] / "000.pkl", "rb"))
+    dec = 0.25 + x[1, 13]
+    assert np.allclose(got["body_pose"][0, :18], dec) and (got["body_pose"][0, 18:24] == 0).all() and (got["body_pose"][0, 57:] == 0).all()
+    assert got["pose_embedding"].shape == (1, 32) and np.array_equal(got["pose_embedding"][0], x[1, 13:45])
+    assert np.allclose(got["pose"][0, 3:21], dec) and np.array_equal(got["pose"][0, :3], x[1, 10:13])
+    assert ctx.calls[5][1] == 0.0 and np.isclose(ctx.calls[5][2], 0.25 + x[0, 13])       # mesh: decoded pose, zeroed extremities
+
+
+def test_fit_sequences_lockstep_warm_start(tmp_path):
+    """is_seq = True (main.py:76-79, non_linear_solver.py:157-162) for two sequences of different length in lock-step"""
+    write_demo(str(tmp_path))
+    a = seqio.load_sequence(str(tmp_path / "keypoints"), "0007")
+    b = seqio.load_sequence(str(tmp_path / "keypoints"), "0007", frames=a["frames"][:2])
+    ctx = StubCtx(2)
+    res, tot = seqio.fit_sequences(ctx, [a, b], stage_cfgs=_cfgs(4), result_folder=str(tmp_path / "res"), reinit_loss=1.5)
+    fits = [c for c in ctx.calls if c[0] == "fit"]
+    assert len(fits) == 4 and tot["frame_iterations"] == 28
+    assert fits[0][2] is None                                  # first frames: every stage, cold
+    # the stub's losses are (1, 2): sequence 0 stays below the re-initialisation threshold (warm), sequence 1 does not
+    assert fits[1][2] == [True, False] and fits[2][2] == [True, False]
+    p1 = fits[1][3]
+    cold = np.arange(2 * 86, dtype=np.float32).reshape(2, 86)
+    assert np.array_equal(p1[0, :13].numpy(), cold[0, :13] + 1) and np.array_equal(p1[0, 82:].numpy(), cold[0, 82:] + 1)   # carried
+    assert np.array_equal(p1[0, 13:82].numpy(), cold[0, 13:82])                       # fix_params: pose back to the seed
+    assert np.array_equal(p1[1].numpy(), cold[1])                                     # re-initialised
+    assert res[0][0].shape == (4, 86) and res[1][0].shape == (2, 86) and res[1][1].tolist() == [2, 2]
+    assert sorted(os.listdir(tmp_path / "res" / "0007")) == a["frames"]
 
 
 @pytest.mark.needs_reference

@@ -22,14 +22,14 @@ from . import ref_harness as RH
 _SCENE = {}
 
 
-def stage_args(stage_weights: dict, interpenetration: bool) -> dict:
+def stage_args(stage_weights: dict, interpenetration: bool, use_vposer: bool = False) -> dict:
     """the keyword arguments main.py passes on from cfg_files/fit_smpl.yaml (weights from mvsmplfitting_b200.synthetic);
     interactive=True because the solver only builds its result dict in that branch (non_linear_solver.py:274-288)"""
     return dict(batch_size=1, data_weights=list(stage_weights["data_weights"]),
                 body_pose_prior_weights=list(stage_weights["body_pose_prior_weights"]),
                 shape_weights=list(stage_weights["shape_weights"]), coll_loss_weights=list(stage_weights["coll_loss_weights"]),
                 use_joints_conf=True, use_3d=False, rho=float(stage_weights["rho"]), interpenetration=bool(interpenetration),
-                loss_type="smplify", visualize=False, use_vposer=False, interactive=True, is_seq=False,
+                loss_type="smplify", visualize=False, use_vposer=bool(use_vposer), interactive=True, is_seq=False,
                 optim_type="lbfgsls", lr=1.0, maxiters=int(stage_weights["maxiters"]), ftol=float(stage_weights["ftol"]),
                 gtol=float(stage_weights["gtol"]))
 
@@ -54,18 +54,24 @@ def build_scene(model: dict, gmm: dict, cams: dict, device: str = "cpu", dtype=t
 
 
 def fit_frame(sc: dict, frames: dict, b: int, stage_weights: dict, interpenetration: bool = False, image_height: int = 1536,
-              quiet: bool = True) -> dict:
-    """non_linear_solver on frame b of `frames` (synthetic.make_frames layout), starting from frames['init'][b]"""
+              quiet: bool = True, vposer=None) -> dict:
+    """non_linear_solver on frame b of `frames` (synthetic.make_frames layout), starting from frames['init'][b].
+    vposer: a loaded reference VPoser (RH.load_reference_vposer) -> use_vposer=True as in cfg_files/fit_smpl.yaml: L2 body prior
+    (body_prior_type 'l2'), latent code from zero (init_guess.py:96-98)"""
     ns, nls, dev, dtype = sc["ns"], sc["nls"], sc["device"], sc["dtype"]
     init = frames["init"]
     sc["model"].reset_params(**{k: torch.tensor(np.asarray(init[k][b:b + 1]), dtype=dtype, device=dev)
                                 for k in ("betas", "global_orient", "body_pose", "transl", "scale")})
     V = frames["gt_uv"].shape[0]
     kp = np.concatenate([frames["gt_uv"][:, b:b + 1], frames["conf"][:, b:b + 1, :, None]], axis=-1)      # [V,1,17,3]
-    setting = dict(views=V, device=dev, dtype=dtype, vposer=None, model=sc["model"], camera=sc["cams"], pose_embedding=None,
+    emb = None
+    if vposer is not None:
+        vposer = vposer.to(dev)
+        emb = torch.zeros([1, 32], dtype=dtype, device=dev, requires_grad=True)
+    setting = dict(views=V, device=dev, dtype=dtype, vposer=vposer, model=sc["model"], camera=sc["cams"], pose_embedding=emb,
                    joints_weight=torch.tensor(frames["joint_weights"], dtype=dtype, device=dev).unsqueeze(0), seq_start=True,
-                   body_pose_prior=sc["body_pose_prior"], shape_prior=sc["shape_prior"], angle_prior=sc["angle_prior"],
-                   adjustment=False)
+                   body_pose_prior=sc["body_pose_prior"] if vposer is None else ns.prior.create_prior("l2"),
+                   shape_prior=sc["shape_prior"], angle_prior=sc["angle_prior"], adjustment=False)
     data = {"keypoints": kp.astype(np.float32), "3d_joint": None, "img": [np.zeros((image_height, 2, 3), np.uint8)],
             "img_path": None}
     # count what the metric counts without touching the solver: remember every optimiser it creates
@@ -81,7 +87,7 @@ def fit_frame(sc: dict, frames: dict, b: int, stage_weights: dict, interpenetrat
         with (contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()), \
                 (contextlib.redirect_stderr(io.StringIO()) if quiet else contextlib.nullcontext()):
             result = nls.non_linear_solver(setting, data, use_cuda=(dev.type == "cuda"),
-                                           **stage_args(stage_weights, interpenetration))
+                                           **stage_args(stage_weights, interpenetration, vposer is not None))
     finally:
         ns.optim_factory.create_optimizer = factory
     iters = evals = 0
@@ -96,4 +102,5 @@ def fit_frame(sc: dict, frames: dict, b: int, stage_weights: dict, interpenetrat
                              for k in ("betas", "global_orient", "body_pose", "transl", "scale")]).astype(np.float32)
     final = None if result is None else result.get("loss")
     return dict(iterations=iters, evals=evals, per_stage=per_stage, params=params,
-                final_loss=float("nan") if final is None else float(final))
+                final_loss=float("nan") if final is None else float(final),
+                pose_embedding=None if emb is None else emb.detach().cpu().numpy().reshape(-1))

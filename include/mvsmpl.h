@@ -135,7 +135,8 @@ int mvs_closure(mvs_ctx* ctx, const float* params_dev, float* loss_dev, float* g
 
 /* ---- geometry only: replaces SMPL.forward (code/smplx/body_models_scale.py:327-412) when it is called outside
  *      the closure (result export, visualisation): joints_dev [B,K,3] and / or verts_dev [B,n_verts,3].
- *      Needs only the model and the batch size. */
+ *      Needs only the model and the batch size.  The body_pose slot is read as axis-angle whatever the loss configuration
+ *      says: decode latent codes first (mvs_vposer_decode). */
 int mvs_forward(mvs_ctx* ctx, const float* params_dev, float* joints_dev, float* verts_dev, void* stream);
 
 /* ---- optimiser: replaces LBFGS.step + _strong_Wolfe (code/optimizers/lbfgs_ls.py:39-445) driven by

@@ -743,7 +743,7 @@ int launch_closure(mvs_ctx* ctx, const float* x_dev, float* loss_dev, float* gra
         return launch_closure_resident(ctx, x_dev, loss_dev, grad_dev, joints_dev, proj_dev, st);
     if (sdf_on && ctx->exec_mode == 3 && !verts_dev && !joints_dev && !proj_dev && hybrid_available(ctx))
         return dense_regime_closure(ctx, x_dev, loss_dev, grad_dev, st);       // the optimiser's own SDF-stage kernels
-    if (lp.use_vposer == 2)
+    if (lp.use_vposer == 2 && !geometry_only)      // geometry only: the pose slot is axis-angle by definition (mvs_forward)
         return set_error(ctx, MVS_ERR_INVALID, "use_vposer = 2 (VPoser decode on the device) is implemented in the "
                                                "frame-resident closure only (no vertices, no SDF term, exec mode 0 or 2)");
     const int nv = dense ? m.N : m.nsup;

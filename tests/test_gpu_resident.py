@@ -93,6 +93,11 @@ def test_dense_regime_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
         # (2) a longer run
         x = x0.clone()
         final, st = ctx.lbfgs_run(x, ctx.make_lbfgs_config(max_outer=3))
+        # the optimiser decreases ITS objective: in mode 0 that is the dense-regime kernels' (exec mode 3 evaluates one closure
+        # through them).  The as-written SDF objective is discontinuous (parity of ray crossings per voxel), so the fp32 chain can
+        # disagree by a voxel's worth of penetration at a point the optimiser parked next to a sign change.
+        if mode == 0:
+            ctx.set_exec_mode(3)
         l1 = ctx.closure(x, want_grad=False)["loss"].cpu().numpy()
         res.append(dict(l0=c0["loss"].cpu().numpy(), g0=c0["grad"].cpu().numpy(), f1=f1.cpu().numpy(),
                         x1=x1.cpu().numpy(), s1=s1, final=final.cpu().numpy(), st=st, l1=l1))
@@ -102,7 +107,8 @@ def test_dense_regime_lbfgs_matches_batched_lbfgs(syn_model, syn_gmm):
     for r in (a, b):
         assert G.relmax(r["f1"], r["l0"].astype(np.float64)) < 1e-4        # loss at entry incl. the penetration term (two independent
         #                                                                     fp32-class evaluations: 3xTF32 tensor cores vs fp32 SIMT; measured 1e-5)
-        assert r["st"]["frames_nan"] == 0 and (r["l1"] <= r["l0"] * (1 + 1e-6)).all()
+        bad = np.where(~(r["l1"] <= r["l0"] * (1 + 1e-4)))[0]
+        assert r["st"]["frames_nan"] == 0 and bad.size == 0, (r is a, bad, r["l0"][bad], r["l1"][bad], r["final"][bad], r["f1"][bad])
     step_a, step_b = a["x1"] - X0, b["x1"] - X0
     moved = np.abs(step_b).max(axis=1) > 0
     assert moved.sum() >= B - 8

@@ -130,12 +130,14 @@ def test_lbfgs_step_in_latent_space(sdf, syn_model):
         kw.update(interpenetration=True, coll_loss_weight=1000.0, sdf_grid=128)
     X0 = _x_with_latent(c)
     ctx = _ctx(syn_model, c, 2)
+    ctx.set_exec_mode(3 if sdf else 0)          # closures with the SDF term + latent pose exist in the dense-regime kernels only
     ctx.set_loss(**kw)
     xr = torch.tensor(X0, device="cuda")
     ctx.lbfgs_run(xr, ctx.make_lbfgs_config(max_outer=3, max_iter=8, ftol=0.0, gtol=0.0))
     l_run = ctx.closure(xr, want_grad=False)["loss"].cpu().numpy()
     ctx.close()
     ctx = _ctx(syn_model, c, 2)
+    ctx.set_exec_mode(3 if sdf else 0)
     ctx.set_loss(**kw)
     xs = torch.tensor(X0, device="cuda")
     l_entry0 = ctx.closure(xs, want_grad=False)["loss"].cpu().numpy()

@@ -40,6 +40,7 @@ typedef enum {
 
 /* ---- lifetime -------------------------------------------------------------------- */
 int mvs_version(void);
+const char* mvs_build_id(void);    /* hash of the sources this library was compiled from (mvsmplfitting_b200/build.py: source_hash) */
 int mvs_create(int device, mvs_ctx** out);
 void mvs_destroy(mvs_ctx* ctx);
 const char* mvs_last_error(const mvs_ctx* ctx);          /* ctx may be NULL (creation errors) */
@@ -158,6 +159,9 @@ typedef struct {
     long long frame_evals;         /* sum over frames of closure evaluations */
     int rounds;                    /* batched closure launches */
     int frames_nan;                /* frames stopped by the NaN/Inf guard (fitting.py:101-107) */
+    long long dense_frame_evals;   /* of frame_evals: those evaluated by dense (SDF) rounds */
+    int dense_rounds;              /* of rounds: dense rounds (gemm -> skin -> sdf_fused -> frame_step each) */
+    int reserved;
 } mvs_lbfgs_stats;
 /* params_dev [B,86] in/out; final_loss_dev [B] or NULL (run_fitting's return value per frame).
  * Synchronises `stream` before returning (stats are read back). */

@@ -48,7 +48,8 @@ class LbfgsConfig(ctypes.Structure):
 
 class LbfgsStats(ctypes.Structure):
     _fields_ = [("frame_iterations", ctypes.c_longlong), ("frame_evals", ctypes.c_longlong),
-                ("rounds", ctypes.c_int), ("frames_nan", ctypes.c_int)]
+                ("rounds", ctypes.c_int), ("frames_nan", ctypes.c_int), ("dense_frame_evals", ctypes.c_longlong),
+                ("dense_rounds", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class InitConfig(ctypes.Structure):
@@ -58,7 +59,7 @@ class InitConfig(ctypes.Structure):
 
 
 EXPORTS = (
-    "mvs_version", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
+    "mvs_version", "mvs_build_id", "mvs_create", "mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_set_model",
     "mvs_set_gmm_prior", "mvs_set_vposer", "mvs_vposer_decode", "mvs_set_cameras", "mvs_set_batch", "mvs_set_keypoints", "mvs_set_loss_config",
     "mvs_closure", "mvs_forward", "mvs_lbfgs_run", "mvs_lbfgs_step", "mvs_fit", "mvs_fit_seq", "mvs_fit_host", "mvs_sdf_grid", "mvs_profile", "mvs_profile_read",
     "mvs_kernel_name", "mvs_set_exec_mode", "mvs_set_anchor", "mvs_init_guess",
@@ -98,6 +99,8 @@ def load() -> ctypes.CDLL:
     lib.mvs_lbfgs_run.argtypes = [vp, vp, vp, ctypes.POINTER(LbfgsConfig), ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_lbfgs_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(LbfgsConfig), ci, ctypes.POINTER(LbfgsStats), vp]
     lib.mvs_set_vposer.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mvs_build_id.restype = ctypes.c_char_p
+    lib.mvs_build_id.argtypes = []
     lib.mvs_vposer_decode.argtypes = [vp, vp, vp, vp]
     lib.mvs_init_guess.argtypes = [vp, vp, vp, ctypes.POINTER(InitConfig), vp]
     lib.mvs_fit.argtypes = [vp, vp, ci, ctypes.POINTER(LossConfig), ctypes.POINTER(LbfgsConfig), vp, ctypes.POINTER(LbfgsStats), vp]
@@ -113,7 +116,7 @@ def load() -> ctypes.CDLL:
     lib.mvs_kernel_name.argtypes = [ci]
     lib.mvs_kernel_name.restype = ctypes.c_char_p
     for name in EXPORTS:
-        if name not in ("mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_kernel_name"):
+        if name not in ("mvs_destroy", "mvs_last_error", "mvs_launch_count", "mvs_kernel_name", "mvs_build_id"):
             getattr(lib, name).restype = ci
     _lib = lib
     return lib

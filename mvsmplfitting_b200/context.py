@@ -33,6 +33,11 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _stats_dict(st) -> dict:
+    return dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds, frames_nan=st.frames_nan,
+                dense_frame_evals=st.dense_frame_evals, dense_rounds=st.dense_rounds)
+
+
 class FittingContext:
     """Owns the device copies of the model / cameras / detections and launches the closure
     and the batched L-BFGS.  All tensors passed in must live on `device` and be contiguous fp32."""
@@ -215,8 +220,7 @@ class FittingContext:
         st = _lib.LbfgsStats()
         _lib.check(self.h, self.lib.mvs_lbfgs_run(self.h, _ptr(params), _ptr(final), ctypes.byref(cfg), ctypes.byref(st),
                                                   self._stream()), "mvs_lbfgs_run")
-        return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
-                           frames_nan=st.frames_nan)
+        return final, _stats_dict(st)
 
     def lbfgs_step(self, params: torch.Tensor, config=None, reset: bool = False):
         """one LBFGS.step() for every frame; returns (loss at entry [B], grads of the last closure call [B,86], stats)"""
@@ -227,8 +231,7 @@ class FittingContext:
         st = _lib.LbfgsStats()
         _lib.check(self.h, self.lib.mvs_lbfgs_step(self.h, _ptr(params), _ptr(loss), _ptr(grad), ctypes.byref(cfg),
                                                    1 if reset else 0, ctypes.byref(st), self._stream()), "mvs_lbfgs_step")
-        return loss, grad, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
-                                frames_nan=st.frames_nan)
+        return loss, grad, _stats_dict(st)
 
     def init_guess(self, estimate_scale: bool = True, fixed_scale: float = 1.0, use_torso: bool = True,
                    hip_seed: float = 1.0, want_joints3d: bool = True, umeyama_as_written: bool = False):
@@ -262,8 +265,7 @@ class FittingContext:
         else:
             _lib.check(self.h, self.lib.mvs_fit(self.h, _ptr(params), len(stage_cfgs), arr, ctypes.byref(cfg), _ptr(final),
                                                 ctypes.byref(st), self._stream()), "mvs_fit")
-        return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
-                           frames_nan=st.frames_nan)
+        return final, _stats_dict(st)
 
     def fit_host(self, params_host: np.ndarray, gt_uv: np.ndarray, conf: np.ndarray, joint_weights: np.ndarray,
                  stage_cfgs, opt_cfg=None):
@@ -277,8 +279,7 @@ class FittingContext:
         _lib.check(self.h, self.lib.mvs_fit_host(self.h, _ptr(params_host), _ptr(gt_uv), _ptr(conf), _ptr(jw),
                                                  len(stage_cfgs), arr, ctypes.byref(cfg), _ptr(final), ctypes.byref(st),
                                                  self._stream()), "mvs_fit_host")
-        return final, dict(frame_iterations=st.frame_iterations, frame_evals=st.frame_evals, rounds=st.rounds,
-                           frames_nan=st.frames_nan)
+        return final, _stats_dict(st)
 
     def sdf_grid(self, faces: torch.Tensor, verts: torch.Tensor, grid_size: int, num_faces: int | None = None):
         """The reference's `sdf.csrc.sdf` op: phi [B,G,G,G] for verts [B,N,3] normalised to [-1,1]."""

@@ -91,7 +91,13 @@ int make_loss_params(mvs_ctx* ctx, const mvs_loss_config* c, LossParams* out) {
 
 extern "C" {
 
-int mvs_version(void) { return 100; }
+int mvs_version(void) { return 200; }
+
+#ifndef MVS_BUILD_ID
+#define MVS_BUILD_ID "unknown"
+#endif
+static const char kBuildIdTag[] = "MVS_BUILD_ID=" MVS_BUILD_ID;      // the tag makes the id findable in the file (build.py)
+const char* mvs_build_id(void) { return kBuildIdTag + 13; }
 
 const char* mvs_last_error(const mvs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 

@@ -290,6 +290,7 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         if (stats) {
             stats->frame_iterations += th[0]; stats->frame_evals += th[1]; stats->frames_nan += (int)th[2];
             stats->rounds += (int)th[3];
+            stats->dense_frame_evals += th[1]; stats->dense_rounds += (int)th[3];
         }
         MVS_CUDA_OK(ctx, cudaGetLastError());
         return MVS_OK;

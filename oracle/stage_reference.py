@@ -65,6 +65,15 @@ def build_sdf() -> str:
     return out.decode().strip().splitlines()[-1]
 
 
+def main(verbose: bool = True) -> None:
+    stage(verbose)
+    so = os.path.join(HERE, "_ref", "libsdf_refcuda.so")
+    src = os.path.join(SRC, "sdf", "sdf", "csrc", "sdf_cuda_kernel.cu")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "ref_sdf_wrap.cu"))):
+        out = build_sdf()
+        if verbose:
+            print(out)
+
+
 if __name__ == "__main__":
-    stage()
-    print(build_sdf())
+    main()

@@ -47,3 +47,9 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import oracle|from oracle)", src, flags=re.M), f
+
+
+def test_library_was_built_from_these_sources():
+    """mvs_build_id() = hash of csrc/*.cu, *.cuh and include/*.h at compile time; a stale libmvsmpl.so fails here"""
+    from mvsmplfitting_b200 import _lib, build
+    assert _lib.load().mvs_build_id().decode() == build.source_hash() == build.built_id()

@@ -12,7 +12,10 @@ One STEP = one complete four-stage fit (4 x FittingMonitor.run_fitting, maxiters
 30 / strong Wolfe / history 100) of all frames from the same initial guess.
 
   value  = frame-iterations / s (iteration = one pass of lbfgs_ls.py:304-434 for one frame), device
-           resident: keypoints + initial parameters already in HBM, reset by a device copy.
+           resident: keypoints + initial parameters already in HBM, reset by a device copy.  The K steps are
+           shared out among --inflight lanes (context + stream + host thread each) that run concurrently:
+           frames are independent problems, and the long tail of a batch (a few straggler frames) leaves
+           most SMs idle, which the other batches fill.  single_batch = the K steps one after the other.
   e2e    = the same metric through mvs_fit_host: pinned HOST keypoints + parameters copied in, results
            copied out, every step.
 Timed with CUDA events, max over ranks; L2 is flushed between steps (256 MiB write).
@@ -114,77 +117,120 @@ def run_ours(args):
     model = S.make_model(0)
     gmm = S.make_gmm(7)
     cams = S.make_cameras(V)
-    fr = S.make_frames(model, cams, B, seed=1000 + rank)
-    ctx = FittingContext(local)
-    ctx.set_model(model)
-    ctx.set_gmm_from_dict(gmm)
-    ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
-    ctx.set_batch(B)
-    if args.vposer:          # cfg 1 style: pose in VPoser's latent space, decoded on the device (use_vposer = 2), no SDF term
-        ctx.set_vposer(S.make_vposer(11))
-        args.sdf = 0
-        stages = [ctx.make_loss_config(body_prior="l2", use_vposer=2, **{k: v for k, v in st.items() if k != "coll_loss_weight"})
-                  for st in stage_table()]
-    else:
-        stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=bool(args.sdf), sdf_grid=128, **st)
-                  for st in stage_table()]
-    opt = ctx.make_lbfgs_config()
-    X0 = S.pack_params(fr["init"])
-    if args.vposer:          # latent code (zeros = the decoder's mean pose) in the first 32 entries of the pose slot
-        X0[:, 13:82] = 0.0
-    x0_dev = torch.tensor(X0, device=dev)
-    x = x0_dev.clone()
-    gt_dev, conf_dev = torch.tensor(fr["gt_uv"], device=dev), torch.tensor(fr["conf"], device=dev)
-    jw_dev = torch.tensor(fr["joint_weights"], device=dev)
-    ctx.set_keypoints(gt_dev, conf_dev, jw_dev)
-    # pinned host buffers for the end-to-end leg
-    X_pin = torch.from_numpy(X0.copy()).pin_memory()
-    gt_pin, conf_pin = torch.from_numpy(fr["gt_uv"]).pin_memory(), torch.from_numpy(fr["conf"]).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def step_resident():
-        # inputs already in HBM; mvs_fit runs the whole stage schedule (frames change stage on their own)
-        nonlocal stages
-        x.copy_(x0_dev)
-        _, tot = ctx.fit(x, stages, opt)
-        return tot, [tot]
+    class Lane:
+        """one batch in flight: its own context (workspace, optimiser state), frames, stream and pinned host buffers"""
 
-    def step_host():
-        X_pin.copy_(torch.from_numpy(X0))
-        return ctx.fit_host(X_pin.numpy(), gt_pin.numpy(), conf_pin.numpy(), fr["joint_weights"], stages, opt)[1]
+        def __init__(self, i):
+            self.fr = fr = S.make_frames(model, cams, B, seed=1000 + rank + 97 * i)
+            self.ctx = ctx = FittingContext(local)
+            ctx.set_model(model)
+            ctx.set_gmm_from_dict(gmm)
+            ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"])
+            ctx.set_batch(B)
+            if args.vposer:      # cfg 1 style: pose in VPoser's latent space, decoded on the device (use_vposer = 2), no SDF term
+                ctx.set_vposer(S.make_vposer(11))
+                self.stages = [ctx.make_loss_config(body_prior="l2", use_vposer=2, **{k: v for k, v in st.items() if k != "coll_loss_weight"})
+                               for st in stage_table()]
+            else:
+                self.stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=bool(args.sdf), sdf_grid=128, **st)
+                               for st in stage_table()]
+            self.opt = ctx.make_lbfgs_config()
+            self.X0 = X0 = S.pack_params(fr["init"])
+            if args.vposer:      # latent code (zeros = the decoder's mean pose) in the first 32 entries of the pose slot
+                X0[:, 13:82] = 0.0
+            self.x0_dev = torch.tensor(X0, device=dev)
+            self.x = self.x0_dev.clone()
+            ctx.set_keypoints(torch.tensor(fr["gt_uv"], device=dev), torch.tensor(fr["conf"], device=dev),
+                              torch.tensor(fr["joint_weights"], device=dev))
+            # pinned host buffers for the end-to-end leg
+            self.X_pin = torch.from_numpy(X0.copy()).pin_memory()
+            self.gt_pin, self.conf_pin = torch.from_numpy(fr["gt_uv"]).pin_memory(), torch.from_numpy(fr["conf"]).pin_memory()
+            self.stream = torch.cuda.Stream(device=dev)
+
+        def step_resident(self):
+            # inputs already in HBM; mvs_fit runs the whole stage schedule (frames change stage on their own)
+            self.x.copy_(self.x0_dev)
+            return self.ctx.fit(self.x, self.stages, self.opt)[1]
+
+        def step_host(self):
+            self.X_pin.copy_(torch.from_numpy(self.X0))
+            return self.ctx.fit_host(self.X_pin.numpy(), self.gt_pin.numpy(), self.conf_pin.numpy(), self.fr["joint_weights"],
+                                     self.stages, self.opt)[1]
+
+    if args.vposer:
+        args.sdf = 0
+    n_lanes = max(1, args.inflight)
+    lanes = [Lane(i) for i in range(n_lanes)]
+    ctx, fr, X0 = lanes[0].ctx, lanes[0].fr, lanes[0].X0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile_mask=0):
-        for _ in range(warmup):
-            fn()
+    def timed(kind, steps, warmup, profile_mask=0, use_lanes=None):
+        """`steps` steps (one step = one batch through the whole fit) spread over the lanes, which run concurrently: every
+        lane is a host thread driving its own context on its own stream.  One lane = batches strictly one after the other."""
+        L = lanes[:use_lanes] if use_lanes else lanes
+        share_of = lambda n: [n // len(L) + (1 if i < n % len(L) else 0) for i in range(len(L))]
+        stats = [[] for _ in L]
+        err = []
+
+        def work(i, n, record):
+            try:
+                torch.cuda.set_device(local)
+                with torch.cuda.stream(L[i].stream):
+                    for k in range(n):
+                        flush.fill_(k & 0xFF)
+                        st = getattr(L[i], kind)()
+                        if record:
+                            stats[i].append(st)
+                    L[i].stream.synchronize()
+            except Exception as e:                                         # noqa: BLE001 -- re-raised below
+                err.append(e)
+
+        def run(counts, record):
+            th = [threading.Thread(target=work, args=(i, n, record)) for i, n in enumerate(counts) if n > 0]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            if err:
+                raise err[0]
+
+        run([max(1, c) if warmup > 0 else 0 for c in share_of(warmup)], False)
         barrier()
-        if profile_mask:
-            ctx.profile(profile_mask)
-        l0 = ctx.launch_count()
-        ms, stats = 0.0, []
+        for ln in L:
+            if profile_mask:
+                ln.ctx.profile(profile_mask)
+        l0 = sum(ln.ctx.launch_count() for ln in L)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wall0 = time.time()
-        for i in range(steps):
-            flush.fill_(i & 0xFF)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            stats.append(fn())
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
+        e0.record()
+        run(share_of(steps), True)
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
         barrier()
         wall = time.time() - wall0
-        launches = ctx.launch_count() - l0
-        prof = ctx.profile_read() if profile_mask else {}
-        if profile_mask:
-            ctx.profile(0)
+        launches = sum(ln.ctx.launch_count() for ln in L) - l0
+        prof = {}
+        for ln in L:
+            if profile_mask:
+                for k, v in ln.ctx.profile_read().items():
+                    a = prof.get(k, (0.0, 0))
+                    prof[k] = (a[0] + v[0], a[1] + v[1])
+                ln.ctx.profile(0)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), stats, launches, prof, wall
+        return float(t[0]), [s_ for lane_stats in stats for s_ in lane_stats], launches, prof, wall
+
+    def step_resident():
+        return lanes[0].step_resident()
 
     # one fully instrumented warm-up step decides which kernel dominates; that kernel alone is then
     # timed with events INSIDE the timed region (two event records per launch of one kernel)
@@ -201,29 +247,35 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_res, stats_res, launches, prof, wall = timed(lambda: step_resident(), args.steps, max(args.warmup - 1, 0), dom_mask)
-    ms_e2e, stats_e2e, _, _, _ = timed(step_host, args.steps, 1)
+    # headline: `inflight` batches in flight (throughput of a stream of 256-frame batches); then the same workload with ONE
+    # batch at a time (latency of a batch; the dominant kernel's roofline is taken here, undisturbed by concurrent lanes)
+    ms_res, stats_res, launches, _, wall = timed("step_resident", args.steps, args.warmup)
+    ms_e2e, stats_e2e, _, _, _ = timed("step_host", args.steps, max(1, min(args.warmup, n_lanes)))
+    ms_one, stats_one, launches_one, prof, _ = timed("step_resident", args.steps, 1, dom_mask, use_lanes=1)
+    ms_one_e2e, stats_one_e2e, _, _, _ = timed("step_host", args.steps, 1, use_lanes=1)
     clocks = sampler.stop() if rank == 0 else {}
     # auxiliary (not the headline): the same fit with the SDF term off = the reference's shipped default
     # (cfg_files/fit_smpl.yaml: interpenetration false) -> every stage runs frame-resident (regime A)
     aux = None
     if args.sdf:
-        stages_main = stages
-        stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=False, **st) for st in stage_table()]
-        ms_a, stats_a, launches_a, _, _ = timed(lambda: step_resident(), 2, 1)
-        it_a = sum(s_[0]["frame_iterations"] for s_ in stats_a)
-        aux = {"workload": "same frames, SDF term off (all four stages frame-resident)", "ms_per_step": ms_a / 2,
+        stages_main = lanes[0].stages
+        lanes[0].stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=False, **st) for st in stage_table()]
+        ms_a, stats_a, launches_a, _, _ = timed("step_resident", 2, 1, use_lanes=1)
+        it_a = sum(s_["frame_iterations"] for s_ in stats_a)
+        aux = {"workload": "same frames, SDF term off (all four stages frame-resident), one batch at a time", "ms_per_step": ms_a / 2,
                "frame_iterations_per_s_per_gpu": it_a / (ms_a * 1e-3), "gpu_launches_per_step": launches_a / 2}
-        stages = stages_main
+        lanes[0].stages = stages_main
 
-    it = sum(s[0]["frame_iterations"] for s in stats_res)
-    ev = sum(s[0]["frame_evals"] for s in stats_res)
-    rounds = sum(s[0]["rounds"] for s in stats_res)
-    it_e2e = sum(s["frame_iterations"] for s in stats_e2e)
-    cnt = torch.tensor([it, ev, launches, it_e2e], device=dev, dtype=torch.float64)
+    it = sum(s_["frame_iterations"] for s_ in stats_res)
+    ev = sum(s_["frame_evals"] for s_ in stats_res)
+    rounds = sum(s_["rounds"] for s_ in stats_res)
+    it_e2e = sum(s_["frame_iterations"] for s_ in stats_e2e)
+    it_one = sum(s_["frame_iterations"] for s_ in stats_one)
+    it_one_e2e = sum(s_["frame_iterations"] for s_ in stats_one_e2e)
+    cnt = torch.tensor([it, ev, launches, it_e2e, it_one, it_one_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    it_all, ev_all, launches_all, it_e2e_all = [float(v) for v in cnt]
+    it_all, ev_all, launches_all, it_e2e_all, it_one_all, it_one_e2e_all = [float(v) for v in cnt]
 
     # ---- BASELINE configs[4]: the sequence as ONE jointly regularised problem (temporal smoothness), frames sharded over the
     #      ranks, per sweep a 344-byte halo exchange with each neighbour + ONE all-reduce (2 doubles) over NCCL.  Not the
@@ -241,23 +293,26 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json, sustained-copy figure)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         # ---- roofline of the dominant kernel: algorithmic bytes per launch / event time
         dom_ms, dom_n = prof.get(dom, (0.0, 0))
-        # average active frames per closure launch (compaction shrinks launches towards the tail)
-        evals_rank0 = sum(s[0]["frame_evals"] for s in stats_res)
-        na_avg = evals_rank0 / max(rounds, 1)
-        dense_rounds_frac = None
+        # average active frames per launch of the dense-round kernels (compaction shrinks launches towards the tail):
+        # closure evaluations made by dense rounds / dense rounds, both counted by the library (mvs_lbfgs_stats), one-batch leg
+        dense_ev = sum(s_["dense_frame_evals"] for s_ in stats_one)
+        dense_rd = sum(s_["dense_rounds"] for s_ in stats_one)
+        na_avg = (dense_ev / dense_rd) if dense_rd else (sum(s_["frame_evals"] for s_ in stats_one) / max(sum(s_["rounds"] for s_ in stats_one), 1))
         alg = algorithmic_bytes(dom, na_avg, V, dense=bool(args.sdf))
         ach = (alg * dom_n) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (cold caches, 256 active
         # frames): profiles/r01_traffic.json, written from the .ncu-rep files by the profiling scripts
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom]["traffic"]
+            tf = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+            traffic = json.load(open(os.path.join(ROOT, "profiles", tf)))[dom]["traffic"]
         except Exception:
             pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (ach / hbm_peak) if ach else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg, "launches": dom_n, "avg_launch_us": (dom_ms * 1e3 / dom_n) if dom_n else None,
                 "avg_active_frames_per_launch": na_avg, "peak_source": peak_src,
+                "measured_in": "the one-batch-at-a-time timed leg (events around every launch of this kernel on its stream)",
                 "note": "the path is latency / L2 bound, not HBM bound: constants (20 MB) live in the 126 MB L2 and one "
                         "launch moves a few MB; see DESIGN.md section 5",
                 "kernel_time_share_of_step": {k: round(v[0] / max(sum(x_[0] for x_ in share.values()), 1e-9), 4)
@@ -282,6 +337,10 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(B, V, bool(args.sdf)), parallelism="frames sharded, dp%d, no data-path collective" % world,
+                           inflight=n_lanes,
+                           pipelining="%d batches of %d frames in flight per GPU: one libmvsmpl context + CUDA stream + host thread "
+                                      "each, the K steps are shared out among them; single_batch = the same K steps strictly one "
+                                      "after the other" % (n_lanes, B),
                            **({"pose": "VPoser latent code (32-D), decoded on the device (use_vposer = 2), l2 prior |z|^2"} if args.vposer else {})),
             "frame_closure_evals_per_s": ev_all / sec, "evals_per_iteration": ev_all / max(it_all, 1),
             "iterations_per_frame_per_step": it_all / (B * world * args.steps),
@@ -290,11 +349,16 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(fr["gt_uv"].nbytes + fr["conf"].nbytes + fr["joint_weights"].nbytes + X0.nbytes),
                     "d2h_bytes_per_step": int(X0.nbytes + B * 4), "ms_per_step": ms_e2e / args.steps,
                     "api": "mvs_fit_host (C ABI, host buffers)"},
+            "single_batch": {"value": it_one_all / (ms_one * 1e-3), "unit": UNIT, "ms_per_step": ms_one / args.steps,
+                             "rounds_per_step": sum(s_["rounds"] for s_ in stats_one) / args.steps,
+                             "gpu_launches_per_step": launches_one / args.steps,
+                             "e2e": {"value": it_one_e2e_all / (ms_one_e2e * 1e-3), "ms_per_step": ms_one_e2e / args.steps}},
             "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "wall_s_timed_region": wall, "aux_no_sdf": aux, "cfg5": cfg5,
         }
         print(json.dumps(out))
-    ctx.close()
+    for ln in lanes:
+        ln.ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -521,6 +585,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU")
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--sdf", type=int, default=1)
+    ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (contexts + streams + host threads); 1 = serial")
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--smooth", type=float, default=0.0, help="cfg5: temporal-smoothness weight (> 0 runs the cfg5 leg on one rank too)")
     ap.add_argument("--sweeps", type=int, default=6, help="cfg5: block-Jacobi sweeps")

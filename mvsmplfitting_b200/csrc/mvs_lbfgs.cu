@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <chrono>
 #include <cstdio>
 #include <vector>
 #include <cstdlib>
@@ -241,6 +242,10 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         long long rounds = 0;
         int na_host = B;
         static const bool trace_na = getenv("MVS_TRACE_NA") != nullptr;       // debugging aid: active-list size per chunk
+        // debugging aid: how long the host thread waited for the GPU inside the round loop (close to 0 = the GPU waits for the host)
+        static const bool trace_host = getenv("MVS_TRACE_HOST") != nullptr;
+        double blocked_us = 0.0;
+        const auto loop_t0 = std::chrono::steady_clock::now();
         rc = launch_frame_fwd_dense(ctx, S.x_eval, &S, nst, st);
         if (rc) return rc;
         if ((rc = frame_step_begin_run(ctx, st))) return rc;
@@ -268,7 +273,9 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
             MVS_CUDA_OK(ctx, cudaMemcpyAsync(&na_slots[cur], w.na, sizeof(int), cudaMemcpyDeviceToHost, st));
             MVS_CUDA_OK(ctx, cudaEventRecord(S.na_event[cur], st));
             if (pending >= 0) {
+                const auto tb0 = std::chrono::steady_clock::now();
                 MVS_CUDA_OK(ctx, cudaEventSynchronize(S.na_event[pending]));
+                if (trace_host) blocked_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tb0).count();
                 na_host = na_slots[pending];
                 if (trace_na) fprintf(stderr, "[mvs] dense regime: chunk %lld, active frames %d\n", chunk_idx - 1, na_host);
                 if (na_host <= 0) break;
@@ -278,6 +285,14 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
             ++chunk_idx;
         }
         w.na_bound = B;
+        if (trace_host) {
+            const double enq = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - loop_t0).count();
+            const auto td0 = std::chrono::steady_clock::now();
+            MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+            const double drain = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - td0).count();
+            fprintf(stderr, "[mvs] dense regime host loop: %lld rounds, %.0f us in the loop (%.0f us of it blocked on the GPU), %.0f us "
+                            "draining afterwards\n", rounds, enq, blocked_us, drain);
+        }
         MVS_CUDA_OK(ctx, cudaStreamSynchronize(st));
         if ((rc = tc_check_error(ctx))) return rc;
         MVS_LAUNCH(ctx, KID_MISC, st, lbfgs_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, final_loss_dev, S.totals, 1));

@@ -585,7 +585,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU")
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--sdf", type=int, default=1)
-    ap.add_argument("--inflight", type=int, default=4, help="batches in flight per GPU (contexts + streams + host threads); 1 = serial")
+    ap.add_argument("--inflight", type=int, default=8, help="batches in flight per GPU (contexts + streams + host threads); 1 = serial")
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--smooth", type=float, default=0.0, help="cfg5: temporal-smoothness weight (> 0 runs the cfg5 leg on one rank too)")
     ap.add_argument("--sweeps", type=int, default=6, help="cfg5: block-Jacobi sweeps")

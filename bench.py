@@ -516,6 +516,23 @@ def cpu_baseline_sample(V, sdf, max_seconds=30.0):
             "frame_closure_evals_per_s": ev / dt}
 
 
+def run_ref_worker(args):
+    """one worker of the reference arm (see run_reference): READY <seconds of the warm-up fit>, then per GO line the fits"""
+    import warnings
+    warnings.filterwarnings("ignore")
+    V, device = args.views, args.ref_device
+    _ref_scene(V, device)
+    dt = _ref_fit_one((999, V, 0, device))[2] if args.warmup > 0 else 0.0
+    print("READY %.6f" % dt, flush=True)
+    for line in sys.stdin:
+        parts = line.split()
+        if len(parts) != 3 or parts[0] != "GO":
+            continue
+        sdf = int(parts[1])
+        out = [_ref_fit_one((int(q), V, sdf, device)) for q in parts[2].split(",")]
+        print("DONE " + json.dumps(out), flush=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's own implementation of the path (code/utils/non_linear_solver.py -> fitting.py,
     lbfgs_ls.py, smplx/, camera.py, prior.py, unmodified) on the box's host cores, one process per physical core, one
@@ -524,7 +541,6 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     import warnings
     warnings.filterwarnings("ignore")
     from oracle import ref_harness as RH
@@ -539,26 +555,57 @@ def run_reference(args):
     # the reference's SDF term is a CUDA kernel (sdf/sdf/csrc): on the CPU arm the term is off, on the CUDA arm it follows --sdf
     sdf = bool(args.sdf) and on_cuda
     cores = 1 if on_cuda else max(1, min((os.cpu_count() or 2) // 2, args.ref_workers))
-    ctxm = mp.get_context("spawn")
-    with ctxm.Pool(cores) as pool:
-        # warm-up: every worker imports torch + the reference and builds the scene; with W >= 1 it also runs one complete
-        # fit, whose duration sizes the timed sample (a fit is ~10 s: W fits per worker would not fit the time budget)
-        t_fit = pool.map(_ref_warm, [(V, args.ref_device, args.warmup > 0)] * cores, chunksize=1)
+    # One plain subprocess per worker (python bench.py --ref-worker): it imports torch + the reference, builds the scene, runs one
+    # complete warm-up fit (W >= 1; its duration sizes the timed sample -- a fit is ~10 s, W fits per worker would not fit the
+    # time budget), reports READY and waits for its list of frames on stdin.  Results come back as one JSON line per worker.
+    env = dict(os.environ)
+    cmd = [sys.executable, os.path.abspath(__file__), "--ref-worker", "--views", str(V), "--ref-device", args.ref_device,
+           "--warmup", str(args.warmup)]
+    procs = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True)
+             for _ in range(cores)]
+
+    def read_tagged(p, tag):
+        while True:
+            line = p.stdout.readline()
+            if not line:
+                raise RuntimeError("reference worker exited early (rc %s)" % p.poll())
+            if line.startswith(tag):
+                return line[len(tag):].strip()
+
+    try:
+        t_fit = [float(read_tagged(p, "READY")) for p in procs]
         t_f = max(1e-3, float(np.mean(t_fit))) if args.warmup > 0 else 12.0
-        # bounded sample: F complete frame fits per step, sized so that K steps fill about --ref-seconds on `cores` workers;
-        # every fit runs to completion (no wall-time cut), fits are dispatched without a barrier between steps
-        F = int(max(1, min(args.frames, np.floor(args.ref_seconds * cores / (max(1, args.steps) * t_f)))))
-        jobs = [(7000 + i, V, int(sdf), args.ref_device) for i in range(args.steps * F)]
+        # bounded sample: every worker gets the same number of complete frame fits, sized so that the run fills about
+        # --ref-seconds; every fit runs to completion (no wall-time cut), there is no barrier between steps
+        per_worker = int(max(1, min(np.ceil(args.frames * args.steps / cores), np.floor(args.ref_seconds / t_f))))
+        F = per_worker * cores / max(1, args.steps)
         t0 = time.time()
-        res = list(pool.imap_unordered(_ref_fit_one, jobs, chunksize=1))
+        for w, p in enumerate(procs):
+            seeds = [7000 + w * per_worker + i for i in range(per_worker)]
+            p.stdin.write("GO %d %s\n" % (int(sdf), ",".join(str(q) for q in seeds)))
+            p.stdin.flush()
+        res = []
+        for p in procs:
+            res += [tuple(r) for r in json.loads(read_tagged(p, "DONE"))]
         dt = time.time() - t0
+    finally:
+        for p in procs:
+            try:
+                p.stdin.close()
+            except Exception:                                   # noqa: BLE001
+                pass
+        for p in procs:
+            try:
+                p.wait(timeout=30)
+            except Exception:                                   # noqa: BLE001
+                p.kill()
     it, ev = sum(r[0] for r in res), sum(r[1] for r in res)
     val = it / dt
     cfg = dict(workload_config(args.frames, V, sdf),
                parallelism=("1 process, torch-CUDA (cuda:0)" if on_cuda else "%d host processes x 1 thread" % cores),
                reference_arm="UNMODIFIED reference (oracle/_ref/reference: utils/non_linear_solver.py, fitting.py, lbfgs_ls.py, smplx/, "
-                             "camera.py, prior.py) on %s; %s; each step = %d complete frame fits (bounded sample of the %d-frame "
-                             "workload, no wall-time cut)" % (
+                             "camera.py, prior.py) on %s; %s; each step = %.4g complete frame fits (bounded sample of the %d-frame "
+                             "workload: every worker runs the same number of fits to completion, no wall-time cut)" % (
                                  "torch-CUDA with its own SDF kernel (sdf_cuda_kernel.cu compiled unchanged)" if on_cuda else "torch CPU",
                                  "SDF term as configured" if on_cuda else "SDF term OFF: it is a CUDA-only kernel in the reference, "
                                  "this is the only mode the reference can run on host cores (compare with aux_no_sdf of the GPU arm)",
@@ -567,7 +614,7 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
-                            "sample": "%d steps x %d complete 4-stage frame fits x %d views by the unmodified reference, %s; "
+                            "sample": "%d steps x %.4g complete 4-stage frame fits x %d views by the unmodified reference, %s; "
                                       "mean fit %.1f s; %d iterations, %d closure evals in %.1f s" % (
                                           args.steps, F, V, cfg["parallelism"], float(np.mean([r[2] for r in res])), it, ev, dt)},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -595,8 +642,11 @@ def main():
                     "32 on the 64-core B200 hosts: more saturate the memory system, measured in round 1)")
     ap.add_argument("--ref-seconds", type=float, default=200.0, help="target wall time of the --impl reference run (sizes the sample)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: host cores (default) or torch-CUDA")
+    ap.add_argument("--ref-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ref_worker:
+        run_ref_worker(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

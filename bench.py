@@ -561,7 +561,9 @@ def run_reference(args):
     env = dict(os.environ)
     cmd = [sys.executable, os.path.abspath(__file__), "--ref-worker", "--views", str(V), "--ref-device", args.ref_device,
            "--warmup", str(args.warmup)]
-    procs = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True)
+    errlog = open(os.path.join(ROOT, "gpurun_out", "ref_workers.err"), "a") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) \
+        else subprocess.DEVNULL
+    procs = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=errlog, env=env, text=True)
              for _ in range(cores)]
 
     def read_tagged(p, tag):

@@ -142,8 +142,12 @@ def build_reference_gmm(gmm: dict, dtype=torch.float32, tmpdir: str = "/tmp/mvs_
     ns = import_reference()
     os.makedirs(tmpdir, exist_ok=True)
     M = gmm["means"].shape[0]
-    with open(os.path.join(tmpdir, "gmm_%02d.pkl" % M), "wb") as f:
+    # written under a private name and renamed: many worker processes (bench.py --impl reference) build the same file at once
+    dst = os.path.join(tmpdir, "gmm_%02d.pkl" % M)
+    tmp = dst + ".%d.tmp" % os.getpid()
+    with open(tmp, "wb") as f:
         pickle.dump({k: np.asarray(v) for k, v in gmm.items()}, f)
+    os.replace(tmp, dst)
     return ns.prior.create_prior("gmm", prior_folder=tmpdir, num_gaussians=M, dtype=dtype)
 
 

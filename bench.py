@@ -329,7 +329,8 @@ def run_ours(args):
                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 as the TF32 proxy",
                                      "note": "M = frames in flight (skinny GEMM): bound by streaming posedirs once per "
                                              "128-frame tile, not by tensor throughput"}
-        cpu = cpu_baseline_sample(V, bool(args.sdf), max_seconds=args.cpu_seconds) if not args.vposer else \
+        cpu = {"note": "measured at N = 1 only"} if world > 1 else \
+            cpu_baseline_sample(V, bool(args.sdf), max_seconds=args.cpu_seconds) if not args.vposer else \
             {"note": "CPU sample not run for the VPoser workload (oracle fit driver has no latent-space mode)"}
         sec = ms_res * 1e-3
         out = {

@@ -252,8 +252,10 @@ static int run_stage(mvs_ctx* ctx, float* params_dev, float* final_loss_dev, con
         // The host only needs the active count to know when to stop, so chunk k+1 is enqueued BEFORE the count of
         // chunk k is awaited (kernels exit at once when the list is empty): the GPU never idles on the host round trip.
         if (!S.na_event[0]) {
-            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[0], cudaEventDisableTiming));
-            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[1], cudaEventDisableTiming));
+            // blocking sync: the host thread sleeps while it waits for a chunk (several contexts are driven by as many host
+            // threads; spinning ones would compete with the threads that have launches to enqueue)
+            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[0], cudaEventDisableTiming | cudaEventBlockingSync));
+            MVS_CUDA_OK(ctx, cudaEventCreateWithFlags(&S.na_event[1], cudaEventDisableTiming | cudaEventBlockingSync));
         }
         int* na_slots = reinterpret_cast<int*>(S.na_host);           // [0], [1]: two chunks in flight
         int pending = -1;                                             // chunk whose count has not been read yet

@@ -67,3 +67,48 @@ def test_sequence_fitter_smooths_the_track(syn_model, syn_gmm):
             assert es[-1] <= es[0] * 1.05 and np.isfinite(es).all()
         fit.ctx.close()
     assert energies[200.0] < 0.8 * energies[0.0]
+
+
+def test_fit_sequences_lockstep_on_device(syn_model, syn_gmm, tmp_path):
+    """seqio.fit_sequences (is_seq = True, main.py:76-79 + non_linear_solver.py:157-162) with a real context: two sequences in
+    lock-step; first frames = what fit_sequence (cold) gives, later frames warm-started (fewer iterations, finite results)"""
+    import pickle
+    from mvsmplfitting_b200 import seqio
+    from mvsmplfitting_b200.context import FittingContext
+    cams = S.make_cameras(4)
+    T = 3
+
+    def make_seq(seed, serial):
+        fr = S.make_frames(syn_model, cams, T, seed=seed)
+        return dict(gt_uv=fr["gt_uv"], conf=fr["conf"], present=np.ones((4, T), bool), cameras=["c%d" % v for v in range(4)],
+                    frames=["%05d" % (t + 1) for t in range(T)], serial=serial)
+
+    seqs = [make_seq(31, "0001"), make_seq(32, "0002")]
+
+    def ctx_for(B):
+        ctx = FittingContext(0)
+        ctx.set_model(syn_model); ctx.set_gmm_from_dict(syn_gmm)
+        ctx.set_cameras(cams["R"], cams["t"], cams["f"], cams["c"]); ctx.set_batch(B)
+        return ctx
+
+    ctx = ctx_for(2)
+    sw = S.STAGE_WEIGHTS
+    stages = [ctx.make_loss_config(body_prior="gmm", data_weight=500.0 / 1536, body_pose_weight=sw["body_pose_prior_weights"][i],
+                                   shape_weight=sw["shape_weights"][i], bending_prior_weight=3.17 * sw["body_pose_prior_weights"][i])
+              for i in range(4)]
+    opt = ctx.make_lbfgs_config(max_outer=10)
+    res, tot = seqio.fit_sequences(ctx, seqs, stages, opt, estimate_scale=True, result_folder=str(tmp_path / "res"), pose_format="lsp14")
+    ctx.close()
+    assert tot["frames_nan"] == 0 and all(np.isfinite(x).all() and np.isfinite(l).all() for x, l in res)
+    # first frames: identical to the cold whole-sequence driver on the same frames
+    for s_, q in enumerate(seqs):
+        c1 = ctx_for(T)
+        stages1 = [c1.make_loss_config(body_prior="gmm", data_weight=500.0 / 1536, body_pose_weight=sw["body_pose_prior_weights"][i],
+                                       shape_weight=sw["shape_weights"][i], bending_prior_weight=3.17 * sw["body_pose_prior_weights"][i])
+                   for i in range(4)]
+        xc, lc, stc = seqio.fit_sequence(c1, q, stages1, c1.make_lbfgs_config(max_outer=10), estimate_scale=True, pose_format="lsp14")
+        c1.close()
+        assert np.array_equal(xc[0], res[s_][0][0]) and lc[0] == res[s_][1][0]
+        assert not np.array_equal(xc[1], res[s_][0][1])                     # later frames took the warm path
+        got = pickle.load(open(tmp_path / "res" / q["serial"] / q["frames"][2] / "000.pkl", "rb"))
+        assert np.array_equal(got["transl"][0], res[s_][0][2][82:85])

@@ -116,7 +116,12 @@ typedef struct {
     int fix_shape;                 /* no shape prior (fitting.py:340) */
     int interpenetration;          /* SDF term on (needs faces) */
     int sdf_grid;                  /* 128 in the reference call (fitting.py:367-368) */
-    int sdf_all_faces;             /* 0 = as written (kernel sees num_faces == 1), 1 = intended semantics */
+    int sdf_all_faces;             /* 0 = as written (the kernel sees num_faces == 1: triangle 0 only, fitting.py:367);
+                                      1 = intended semantics, all faces, evaluated over per-frame candidate lists (uniform cell
+                                          grid for the distance, central projection from the ray target for the parity;
+                                          bit-identical to 2, ~100x fewer primitive evaluations);
+                                      2 = all faces by brute force (the cross-check of 1).  The batched reference chain
+                                          (exec mode 1, closures that ask for vertices) always uses the brute force. */
     unsigned frozen_mask;          /* bit i set -> parameter tensor i (betas, orient, pose, transl, scale) has
                                       requires_grad=False: its gradient is forced to 0 (init_guess.py:190-212) */
 } mvs_loss_config;

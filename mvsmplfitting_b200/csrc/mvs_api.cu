@@ -37,6 +37,7 @@ template <class T> int dev_upload(mvs_ctx* ctx, T** p, const T* host, size_t cou
     if (count) MVS_CUDA_OK(ctx, cudaMemcpy(*p, host, count * sizeof(T), cudaMemcpyHostToDevice));
     return MVS_OK;
 }
+template int dev_alloc<unsigned short>(mvs_ctx*, unsigned short**, size_t);
 template int dev_alloc<float>(mvs_ctx*, float**, size_t);
 template int dev_alloc<int>(mvs_ctx*, int**, size_t);
 template int dev_alloc<double>(mvs_ctx*, double**, size_t);

@@ -266,11 +266,214 @@ sdf_finalize_kernel(const int* __restrict__ na_ptr, int N, const FrameBox* __res
     o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
 }
 
+// ------------------------------------------------------------------------------------------------ all-faces bins (N3)
+// One CTA per active frame builds the frame's candidate structures of mvs_sdf_bins.cuh: triangle corners in box coordinates,
+// the cell lists (counting sort over kBinCells in shared memory) and the ray-bin lists (the same over kBinRays).  The order of
+// the triangles inside a list is whatever the atomics produce: minimum and parity do not depend on it.
+constexpr int kBinsThreads = 1024;
+constexpr size_t kBinsSmem = (size_t)kBinCells * sizeof(int) + 64 * sizeof(float);
+
+struct SdfBinsArgs {
+    const float* verts; const float* slot_tr; const float* bboxp; const int* faces; int N, F, nbox;
+    float* tri; int* cell_ptr; unsigned short* cell_idx; int* ray_ptr; unsigned short* ray_idx; float* meta;
+};
+
+// exclusive scan of hist[0 .. n) in place (n a multiple of 1024, <= kBinCells), all kBinsThreads threads; returns the total
+__device__ __forceinline__ int block_exclusive_scan(int* hist, int n, int* wtot) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per_warp = n / 32;                               // 32 warps
+    const int base = warp * per_warp;
+    int carry = 0;
+    for (int i = 0; i < per_warp; i += 32) {
+        const int v = hist[base + i + lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        hist[base + i + lane] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) wtot[warp] = carry;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = wtot[lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        wtot[lane] = incl - v;
+        if (lane == 31) wtot[32] = incl;
+    }
+    __syncthreads();
+    const int off = wtot[warp];
+    for (int i = 0; i < per_warp; i += 32) hist[base + i + lane] += off;
+    __syncthreads();
+    return wtot[32];
+}
+
+__global__ void __launch_bounds__(kBinsThreads, 1)
+sdf_bins_kernel(SdfBinsArgs a, const int* __restrict__ na_ptr) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char bins_smem[];
+    int* hist = reinterpret_cast<int*>(bins_smem);
+    float* sf = reinterpret_cast<float*>(bins_smem + (size_t)kBinCells * sizeof(int));      // 64 floats of scratch
+    __shared__ int wtot[33];
+    const int slot = blockIdx.x;
+    if (slot >= *na_ptr) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float* vf = a.verts + (size_t)slot * a.N * 3;
+    const float tr[3] = {a.slot_tr[4 * slot], a.slot_tr[4 * slot + 1], a.slot_tr[4 * slot + 2]};
+    // ---- frame box: min / max of the skinning kernel's chunk boxes (exact operations: any order gives sdf_fused's values)
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int tl = t; tl < a.nbox; tl += kBinsThreads) {
+        const float* bp = a.bboxp + ((size_t)slot * a.nbox + tl) * 12;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], bp[c]); hi[c] = fmaxf(hi[c], bp[3 + c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    float* wb = reinterpret_cast<float*>(hist);                // [32][6] during the prologue
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { wb[warp * 6 + c] = lo[c]; wb[warp * 6 + 3 + c] = hi[c]; }
+    }
+    __syncthreads();
+    float centre[3], scale;
+    {
+        float ext = -1.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float l = wb[c], h2 = wb[3 + c];
+            for (int w = 1; w < kBinsThreads / 32; ++w) { l = fminf(l, wb[w * 6 + c]); h2 = fmaxf(h2, wb[w * 6 + 3 + c]); }
+            const float lc = l + tr[c], hc = h2 + tr[c];       // as sdf_fused_body (body_models_scale.py:403, fitting.py:352-359)
+            centre[c] = (lc + hc) / 2.f;
+            const float e = hc - lc;
+            if (e > ext) ext = e;
+        }
+        scale = 0.6f * ext;
+    }
+    __syncthreads();
+    // ---- triangle corners in box coordinates (the brute force's operands, same expression) + bounding box of the projected mesh
+    float* tri = a.tri + (size_t)slot * a.F * 9;
+    float smn[2] = {3e38f, 3e38f}, smx[2] = {-3e38f, -3e38f};
+    for (int f = t; f < a.F; f += kBinsThreads) {
+        float p[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) p[r] = ((vf[3 * a.faces[3 * f + r / 3] + r % 3] + tr[r % 3]) - centre[r % 3]) / scale;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) tri[9 * f + r] = p[r];
+        float bmn[2], bmx[2];
+        tri_proj_box(p, bmn, bmx);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { smn[q] = fminf(smn[q], bmn[q]); smx[q] = fmaxf(smx[q], bmx[q]); }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            smn[q] = fminf(smn[q], __shfl_xor_sync(0xffffffffu, smn[q], o));
+            smx[q] = fmaxf(smx[q], __shfl_xor_sync(0xffffffffu, smx[q], o));
+        }
+    if (lane == 0) { wb[warp * 4] = smn[0]; wb[warp * 4 + 1] = smn[1]; wb[warp * 4 + 2] = smx[0]; wb[warp * 4 + 3] = smx[1]; }
+    __syncthreads();
+    if (t == 0) {
+        float mn[2] = {wb[0], wb[1]}, mx[2] = {wb[2], wb[3]};
+        for (int w = 1; w < kBinsThreads / 32; ++w) {
+            mn[0] = fminf(mn[0], wb[w * 4]); mn[1] = fminf(mn[1], wb[w * 4 + 1]);
+            mx[0] = fmaxf(mx[0], wb[w * 4 + 2]); mx[1] = fmaxf(mx[1], wb[w * 4 + 3]);
+        }
+        ray_bin_frame(mn, mx, &sf[0], &sf[2]);
+    }
+    __syncthreads();
+    const float s_lo[2] = {sf[0], sf[1]}, s_scale[2] = {sf[2], sf[3]};
+    __syncthreads();
+    // ---- cell lists
+    for (int i = t; i < kBinCells; i += kBinsThreads) hist[i] = 0;
+    __syncthreads();
+    for (int f = t; f < a.F; f += kBinsThreads) {
+        int cl[3], ch[3];
+        tri_cell_range(tri + 9 * f, cl, ch);
+        for (int x = cl[0]; x <= ch[0]; ++x) for (int y = cl[1]; y <= ch[1]; ++y) for (int z = cl[2]; z <= ch[2]; ++z)
+            atomicAdd(&hist[(x * kBinC + y) * kBinC + z], 1);
+    }
+    __syncthreads();
+    const int tot_d = block_exclusive_scan(hist, kBinCells, wtot);
+    int* cptr = a.cell_ptr + (size_t)slot * (kBinCells + 1);
+    for (int i = t; i < kBinCells; i += kBinsThreads) cptr[i] = hist[i];
+    if (t == 0) cptr[kBinCells] = tot_d;
+    __syncthreads();
+    if (tot_d <= kBinCapD) {
+        unsigned short* cidx = a.cell_idx + (size_t)slot * kBinCapD;
+        for (int f = t; f < a.F; f += kBinsThreads) {
+            int cl[3], ch[3];
+            tri_cell_range(tri + 9 * f, cl, ch);
+            for (int x = cl[0]; x <= ch[0]; ++x) for (int y = cl[1]; y <= ch[1]; ++y) for (int z = cl[2]; z <= ch[2]; ++z)
+                cidx[atomicAdd(&hist[(x * kBinC + y) * kBinC + z], 1)] = (unsigned short)f;
+        }
+    }
+    __syncthreads();
+    // ---- ray-bin lists
+    for (int i = t; i < kBinRays; i += kBinsThreads) hist[i] = 0;
+    __syncthreads();
+    for (int f = t; f < a.F; f += kBinsThreads) {
+        float bmn[2], bmx[2];
+        int rl[2], rh[2];
+        tri_proj_box(tri + 9 * f, bmn, bmx);
+        tri_ray_range(bmn, bmx, s_lo, s_scale, rl, rh);
+        for (int x = rl[0]; x <= rh[0]; ++x) for (int y = rl[1]; y <= rh[1]; ++y) atomicAdd(&hist[x * kBinR + y], 1);
+    }
+    __syncthreads();
+    const int tot_r = block_exclusive_scan(hist, kBinRays, wtot);
+    int* rptr = a.ray_ptr + (size_t)slot * (kBinRays + 1);
+    for (int i = t; i < kBinRays; i += kBinsThreads) rptr[i] = hist[i];
+    if (t == 0) rptr[kBinRays] = tot_r;
+    __syncthreads();
+    if (tot_r <= kBinCapR) {
+        unsigned short* ridx = a.ray_idx + (size_t)slot * kBinCapR;
+        for (int f = t; f < a.F; f += kBinsThreads) {
+            float bmn[2], bmx[2];
+            int rl[2], rh[2];
+            tri_proj_box(tri + 9 * f, bmn, bmx);
+            tri_ray_range(bmn, bmx, s_lo, s_scale, rl, rh);
+            for (int x = rl[0]; x <= rh[0]; ++x) for (int y = rl[1]; y <= rh[1]; ++y)
+                ridx[atomicAdd(&hist[x * kBinR + y], 1)] = (unsigned short)f;
+        }
+    }
+    if (t == 0) {
+        float* mt = a.meta + 8 * (size_t)slot;
+        mt[0] = s_lo[0]; mt[1] = s_lo[1]; mt[2] = s_scale[0]; mt[3] = s_scale[1];
+        mt[4] = (tot_d > kBinCapD || tot_r > kBinCapR) ? 1.f : 0.f;      // overflow: sdf_fused falls back to the brute force for this frame
+        mt[5] = (float)tot_d; mt[6] = (float)tot_r; mt[7] = 0.f;
+    }
+}
+
+static int ensure_sdf_bins_ws(mvs_ctx* ctx) {
+    Workspace& w = ctx->ws;
+    if (w.bins_tri) return MVS_OK;
+    if (ctx->m.F > 65535) return set_error(ctx, MVS_ERR_UNSUPPORTED, "accelerated all-faces SDF: more than 65535 faces");
+    const size_t B = (size_t)w.B;
+    int rc;
+    if ((rc = dev_alloc(ctx, &w.bins_tri, B * ctx->m.F * 9))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bins_cell_ptr, B * (kBinCells + 1)))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bins_cell_idx, B * kBinCapD))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bins_ray_ptr, B * (kBinRays + 1)))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bins_ray_idx, B * kBinCapR))) return rc;
+    if ((rc = dev_alloc(ctx, &w.bins_meta, B * 8))) return rc;
+    MVS_CUDA_OK(ctx, cudaFuncSetAttribute(sdf_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinsSmem));
+    return MVS_OK;
+}
+
+// kAll = false: the reference call as written (the kernel sees triangle 0), the default and the benchmark's mode; kAll = true: the
+// intended all-faces field, over candidate lists or by brute force
+template <bool kAll>
 __global__ void __launch_bounds__(kSdfFThreads, 3)
 sdf_fused_kernel(SdfFusedArgs ar, const int* __restrict__ na_ptr, int passes) {
     pdl_wait();
     __shared__ SdfFusedSmem sm;
-    sdf_fused_body(sm, ar, *na_ptr, (int)blockIdx.y, (int)blockIdx.x, passes);
+    sdf_fused_body<kAll>(sm, ar, *na_ptr, (int)blockIdx.y, (int)blockIdx.x, passes);
 }
 
 int ensure_sdf_fused_ws(mvs_ctx* ctx) {
@@ -303,6 +506,10 @@ SdfFusedArgs make_sdf_fused_args(mvs_ctx* ctx) {
     a.At = w.At; a.ldA = w.ldA; a.ell_j = m.ell_j; a.ell_w = m.ell_w; a.KW = m.KW; a.Wd = m.Wd; a.Qk = m.Qk;
     a.parts5 = w.sdf_parts5; a.part = w.sdf_part; a.pflag = w.sdf_pflag; a.boxout = reinterpret_cast<FrameBox*>(w.sdf_box);
     a.gcoord = w.sdf_gcoord;
+    // sdf_all_faces: 0 as written (triangle 0), 1 all faces over candidate lists (accelerated), 2 all faces by brute force
+    const bool binned = lp.sdf_all_faces == 1 && w.bins_tri != nullptr;
+    a.bins.tri = binned ? w.bins_tri : nullptr; a.bins.cell_ptr = w.bins_cell_ptr; a.bins.cell_idx = w.bins_cell_idx;
+    a.bins.ray_ptr = w.bins_ray_ptr; a.bins.ray_idx = w.bins_ray_idx; a.bins.meta = w.bins_meta; a.bins.F = m.F;
     return a;
 }
 
@@ -322,9 +529,22 @@ int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st) {
     int rc = ensure_sdf_fused_ws(ctx);
     if (rc) return rc;
     dim3 g(nparts, nb);
+    if (ctx->loss.sdf_all_faces == 1) {                  // accelerated all-faces mode: this round's candidate lists first
+        if ((rc = ensure_sdf_bins_ws(ctx))) return rc;
+        SdfBinsArgs ba;
+        ba.verts = w.verts; ba.slot_tr = w.slot_tr; ba.bboxp = w.bboxp; ba.faces = m.faces; ba.N = N; ba.F = m.F; ba.nbox = (N + 63) / 64;
+        ba.tri = w.bins_tri; ba.cell_ptr = w.bins_cell_ptr; ba.cell_idx = w.bins_cell_idx; ba.ray_ptr = w.bins_ray_ptr;
+        ba.ray_idx = w.bins_ray_idx; ba.meta = w.bins_meta;
+        MVS_LAUNCH(ctx, KID_SDF_BBOX, st,
+                   MVS_CUDA_OK(ctx, launch_pdl(sdf_bins_kernel, dim3(nb), dim3(kBinsThreads), kBinsSmem, st, ba, (const int*)w.na)));
+    }
     const SdfFusedArgs sa = make_sdf_fused_args(ctx);
-    MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
-               MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel, g, dim3(kSdfFThreads), 0, st, sa, (const int*)w.na, passes)));
+    if (ctx->loss.sdf_all_faces)
+        MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
+                   MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel<true>, g, dim3(kSdfFThreads), 0, st, sa, (const int*)w.na, passes)));
+    else
+        MVS_LAUNCH(ctx, KID_SDF_FRAME, st,
+                   MVS_CUDA_OK(ctx, launch_pdl(sdf_fused_kernel<false>, g, dim3(kSdfFThreads), 0, st, sa, (const int*)w.na, passes)));
     MVS_CUDA_OK(ctx, cudaGetLastError());
     return MVS_OK;
 }

@@ -3,81 +3,10 @@
 #pragma once
 #include "mvs_internal.cuh"
 #include "mvs_tc_dev.cuh"
+#include "mvs_sdf_geom.cuh"
+#include "mvs_sdf_bins.cuh"
 
 namespace mvs {
-
-// ---------------------------------------------------------------------------------- geometry (float, as the reference)
-__device__ __forceinline__ float dist3(const float* a, const float* b) {
-    const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
-    return sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-}
-__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-
-// sdf_cuda_kernel.cu:73-92
-__device__ __forceinline__ float segment_distance(const float* x0, const float* x1, const float* x2, float* r) {
-    const float dx[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-    const float m2 = dot3(dx, dx);
-    float s12 = (dot3(x2, dx) - dot3(x0, dx)) / m2;
-    s12 = s12 < 0.f ? 0.f : (s12 > 1.f ? 1.f : s12);
-    r[0] = s12 * x1[0] + (1.f - s12) * x2[0];
-    r[1] = s12 * x1[1] + (1.f - s12) * x2[1];
-    r[2] = s12 * x1[2] + (1.f - s12) * x2[2];
-    return dist3(x0, r);
-}
-// sdf_cuda_kernel.cu:155-237 (closest point), returns the distance
-__device__ __forceinline__ float triangle_distance(const float* x0, const float* x1, const float* x2, const float* x3) {
-    float x13[3], x23[3], x03[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { x13[i] = x1[i] - x3[i]; x23[i] = x2[i] - x3[i]; x03[i] = x0[i] - x3[i]; }
-    const float m13 = dot3(x13, x13), m23 = dot3(x23, x23), d = dot3(x13, x23);
-    const float invdet = 1.f / fmaxf(m13 * m23 - d * d, 1e-30f);
-    const float a = dot3(x13, x03), b = dot3(x23, x03);
-    const float w23 = invdet * (m23 * a - d * b);
-    const float w31 = invdet * (m13 * b - d * a);
-    const float w12 = 1.f - w23 - w31;
-    float r[3];
-    if (w23 >= 0.f && w31 >= 0.f && w12 >= 0.f) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = w23 * x1[i] + w31 * x2[i] + w12 * x3[i];
-        return dist3(x0, r);
-    }
-    float r2[3], d1, d2;
-    if (w23 > 0.f) { d1 = segment_distance(x0, x1, x2, r); d2 = segment_distance(x0, x1, x3, r2); }
-    else if (w31 > 0.f) { d1 = segment_distance(x0, x1, x2, r); d2 = segment_distance(x0, x2, x3, r2); }
-    else { d1 = segment_distance(x0, x1, x3, r); d2 = segment_distance(x0, x2, x3, r2); }
-    // the reference returns the closest POINT and the caller re-measures the distance to it (:281-282)
-    return (d1 < d2) ? dist3(x0, r) : dist3(x0, r2);
-}
-// sdf_cuda_kernel.cu:95-150: ray from the voxel centre towards (-1,-1,-1); hit counted iff t >= 0
-__device__ __forceinline__ bool ray_hits(const float* c, const float* v0, const float* v1, const float* v2) {
-    const float dir[3] = {-1.f - c[0], -1.f - c[1], -1.f - c[2]};
-    float e1[3], e2[3], tv[3], pv[3], qv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { e1[i] = v1[i] - v0[i]; e2[i] = v2[i] - v0[i]; }
-    pv[0] = dir[1] * e2[2] - dir[2] * e2[1];
-    pv[1] = dir[2] * e2[0] - dir[0] * e2[2];
-    pv[2] = dir[0] * e2[1] - dir[1] * e2[0];
-    const float det = dot3(e1, pv);
-    if (det > -1e-6 && det < 1e-6) return false;
-    const float inv_det = (float)(1.0 / (double)det);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) tv[i] = c[i] - v0[i];
-    const float u = dot3(tv, pv) * inv_det;
-    if (u < 0.f || u > 1.f) return false;
-    qv[0] = tv[1] * e1[2] - tv[2] * e1[1];
-    qv[1] = tv[2] * e1[0] - tv[0] * e1[2];
-    qv[2] = tv[0] * e1[1] - tv[1] * e1[0];
-    const float v = dot3(dir, qv) * inv_det;
-    if (v < 0.f || (u + v) > 1.f) return false;
-    const float t = dot3(e2, qv) * inv_det;
-    return t >= 0.f;
-}
-__device__ __forceinline__ void voxel_centre(int i, int j, int k, int G, float* c) {     // sdf_cuda_kernel.cu:260-263
-    const float dx = (float)(2. / (G - 1));
-    c[0] = (float)(-1 + (i + 0.5) * dx);
-    c[1] = (float)(-1 + (j + 0.5) * dx);
-    c[2] = (float)(-1 + (k + 0.5) * dx);
-}
 
 // ---------------------------------------------------------------------------------- dense regime, v4: fused adjoint
 // sdf_fused_kernel: P CTAs per frame, 1, 2 or 4 blocks of 256 vertices each.  Per CTA: fold the skinning kernel's box partials (all
@@ -90,13 +19,20 @@ __device__ __forceinline__ void voxel_centre(int i, int j, int k, int G, float* 
 constexpr int kSdfFThreads = 256;
 constexpr int kSdfFChunk = 128;                              // list entries per adjoint pass
 
+// device-side entry of the candidate-list evaluation: kept out of line so that the (default) as-written path of sdf_fused_kernel
+// keeps its register budget
+__device__ __noinline__ float phi_binned_dev(const float* c, const SdfBinsView* v) { return phi_binned(c, *v, nullptr); }
+
+// kAll = false: the as-written kernel (triangle 0 only) carries none of the all-faces code
+template <bool kAll>
 __device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, const int* __restrict__ faces,
                                               const float* __restrict__ vf, const float* tr, const FrameBox& fb,
-                                              const float* tri0) {
-    if (num_faces == 1) {
+                                              const float* tri0, const SdfBinsView* bins) {
+    if (!kAll || num_faces == 1) {
         if (!ray_hits(c, tri0, tri0 + 3, tri0 + 6)) return 0.f;
         return triangle_distance(c, tri0, tri0 + 3, tri0 + 6);
     }
+    if (bins) return phi_binned_dev(c, bins);          // all faces over candidate lists (mvs_sdf_bins.cuh): identical bits
     int hits = 0;
     float min_d = 1000.f;
     for (int f = 0; f < num_faces; ++f) {
@@ -110,6 +46,13 @@ __device__ __forceinline__ float voxel_phi_at(const float* c, int num_faces, con
     }
     return (hits % 2 == 0) ? 0.f : min_d;
 }
+
+// per-slot bin structures of the accelerated all-faces mode (null pointers: brute force)
+struct SdfBinsDev {
+    const float* tri; const int* cell_ptr; const unsigned short* cell_idx; const int* ray_ptr; const unsigned short* ray_idx;
+    const float* meta;                     // [B][8]: s_lo[2], s_scale[2], overflow flag, -, -, -
+    int F;
+};
 
 // Shared-memory working set of sdf_fused_body (static in sdf_fused_kernel, a slice of the dynamic buffer in the persistent
 // dense-round kernel)
@@ -137,9 +80,11 @@ struct SdfFusedArgs {
     int N, nbox; const float* bboxp; const int* faces; int num_faces, f0, f1, f2, G;
     const float* At; int ldA; const int* ell_j; const float* ell_w; int KW; const float* Wd; const float* Qk;
     float* parts5; float* part; int* pflag; FrameBox* boxout; float* gcoord;
+    SdfBinsDev bins;
 };
 
 // One CTA of sdf_fused_kernel's virtual grid (pidx = block group of the frame in `slot`).  All kSdfFThreads threads call.
+template <bool kAll>
 __device__ __forceinline__ void sdf_fused_body(SdfFusedSmem& sm, const SdfFusedArgs& ar, const int na, const int slot, const int pidx,
                                                const int passes) {
     const float* verts = ar.verts; const float* slot_tr = ar.slot_tr; const float* bboxp = ar.bboxp;
@@ -248,6 +193,21 @@ __device__ __forceinline__ void sdf_fused_body(SdfFusedSmem& sm, const SdfFusedA
     //      vertex lists and adjoint partials are emitted PER BLOCK, so the arithmetic of a frame does not depend on
     //      how many blocks this launch gave to one CTA (i.e. not on how many other frames are still active): frames
     //      stay bit-for-bit independent problems.  All passes are sampled before the first barrier.
+    // accelerated all-faces mode: this frame's candidate lists (built by sdf_bins_kernel just before this launch)
+    SdfBinsView bview;
+    const SdfBinsView* bvp = nullptr;
+    if (kAll && num_faces > 1 && ar.bins.tri != nullptr) {
+        const float* mt = ar.bins.meta + 8 * (size_t)slot;
+        if (mt[4] == 0.f) {                                 // no list overflow for this frame
+            bview.tri = ar.bins.tri + (size_t)slot * ar.bins.F * 9;
+            bview.cell_ptr = ar.bins.cell_ptr + (size_t)slot * (kBinCells + 1);
+            bview.cell_idx = ar.bins.cell_idx + (size_t)slot * kBinCapD;
+            bview.ray_ptr = ar.bins.ray_ptr + (size_t)slot * (kBinRays + 1);
+            bview.ray_idx = ar.bins.ray_idx + (size_t)slot * kBinCapR;
+            bview.s_lo[0] = mt[0]; bview.s_lo[1] = mt[1]; bview.s_scale[0] = mt[2]; bview.s_scale[1] = mt[3];
+            bvp = &bview;
+        }
+    }
     const bool cull = (num_faces == 1);
     const bool tab = (G <= 256);
     const int nblocks = (N + kSdfFThreads - 1) / kSdfFThreads;
@@ -382,7 +342,7 @@ __device__ __forceinline__ void sdf_fused_body(SdfFusedSmem& sm, const SdfFusedA
                         if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
                     }
                     const float cc[3] = {cx[ox], cy[oy], cz[oz]};
-                    const float p = voxel_phi_at(cc, num_faces, faces, vf, tr, fb, tri);
+                    const float p = voxel_phi_at<kAll>(cc, num_faces, faces, vf, tr, fb, tri, bvp);
                     if (p == 0.f) continue;
                     const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
                     val += p * wx * wy * wz;

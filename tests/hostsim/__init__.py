@@ -19,7 +19,7 @@ class HostLoss(ctypes.Structure):
 def _build():
     src = os.path.join(_HERE, "closure_hostsim.cpp")
     csrc = os.path.join(_HERE, "..", "..", "mvsmplfitting_b200", "csrc")
-    hdrs = [os.path.join(csrc, "mvs_math.cuh"), os.path.join(csrc, "mvs_init.cuh")]
+    hdrs = [os.path.join(csrc, n) for n in ("mvs_math.cuh", "mvs_init.cuh", "mvs_sdf_geom.cuh", "mvs_sdf_bins.cuh")]
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     if (not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(q) for q in [src] + hdrs)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
@@ -167,3 +167,18 @@ def rotmat_to_aa(R):
     aa = np.zeros((R.shape[0], 3))
     lib.hostsim_rotmat_to_aa(ctypes.c_int(R.shape[0]), _P(R), _P(aa))
     return aa
+
+
+def sdf_bins(tri, G, voxel_ids, brute=True):
+    """mvs_sdf_bins.cuh on the host: tri [F,3,3] float32 box coordinates -> (phi over candidate lists, phi by brute force or None,
+    dict(ray_evals, dist_evals, cell_entries, ray_entries))"""
+    lib = _build()
+    tri = np.ascontiguousarray(tri, dtype=np.float32).reshape(-1, 9)
+    vox = np.ascontiguousarray(voxel_ids, dtype=np.int64)
+    ob, of = np.zeros(vox.shape[0], np.float32), np.zeros(vox.shape[0], np.float32)
+    ev = np.zeros(4, np.int64)
+    lib.hostsim_sdf_bins.restype = ctypes.c_int
+    rc = lib.hostsim_sdf_bins(ctypes.c_int(tri.shape[0]), _P(tri), ctypes.c_int(int(G)), ctypes.c_long(vox.shape[0]), _P(vox), _P(ob),
+                              _P(of) if brute else None, _P(ev))
+    assert rc == 0, "list capacity exceeded (%d)" % rc
+    return ob, (of if brute else None), dict(ray_evals=int(ev[0]), dist_evals=int(ev[1]), cell_entries=int(ev[2]), ray_entries=int(ev[3]))

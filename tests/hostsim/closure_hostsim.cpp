@@ -9,6 +9,8 @@
 
 #include "../../mvsmplfitting_b200/csrc/mvs_math.cuh"
 #include "../../mvsmplfitting_b200/csrc/mvs_init.cuh"
+#include "../../mvsmplfitting_b200/csrc/mvs_sdf_bins.cuh"
+#include <vector>
 
 using namespace mvs;
 
@@ -332,5 +334,71 @@ void hostsim_single_view(int K, const double* cR, const double* ct, const double
 }
 void hostsim_rotmat_to_aa(int n, const double* R, double* aa) {
     for (int i = 0; i < n; ++i) rotmat_to_aa<double>(R + 9 * i, aa + 3 * i);
+}
+
+// mvs_sdf_bins.cuh on the host: the frame's bin structures built serially (what sdf_bins_kernel does with a counting sort),
+// then phi at the listed voxels over the candidate lists AND by brute force over all F triangles with the same primitives.
+// tri [F][9] box coordinates; vox [n] flat voxel ids (i + G (j + G k)); out_b / out_f [n]; evals [2] totals; returns 0, or 1 / 2
+// if a list capacity would overflow.
+int hostsim_sdf_bins(int F, const float* tri, int G, long n, const long* vox, float* out_b, float* out_f, long* evals) {
+    std::vector<int> cell_cnt(kBinCells + 1, 0), ray_cnt(kBinRays + 1, 0);
+    float mn[2] = {3e38f, 3e38f}, mx[2] = {-3e38f, -3e38f};
+    for (int f = 0; f < F; ++f) {
+        float a[2], b[2];
+        tri_proj_box(tri + 9 * f, a, b);
+        for (int q = 0; q < 2; ++q) { mn[q] = fminf(mn[q], a[q]); mx[q] = fmaxf(mx[q], b[q]); }
+    }
+    SdfBinsView v;
+    ray_bin_frame(mn, mx, v.s_lo, v.s_scale);
+    for (int f = 0; f < F; ++f) {
+        int lo[3], hi[3];
+        tri_cell_range(tri + 9 * f, lo, hi);
+        for (int x = lo[0]; x <= hi[0]; ++x) for (int y = lo[1]; y <= hi[1]; ++y) for (int z = lo[2]; z <= hi[2]; ++z)
+            cell_cnt[(x * kBinC + y) * kBinC + z + 1]++;
+        float a[2], b[2];
+        int rl[2], rh[2];
+        tri_proj_box(tri + 9 * f, a, b);
+        tri_ray_range(a, b, v.s_lo, v.s_scale, rl, rh);
+        for (int x = rl[0]; x <= rh[0]; ++x) for (int y = rl[1]; y <= rh[1]; ++y) ray_cnt[x * kBinR + y + 1]++;
+    }
+    for (int i = 0; i < kBinCells; ++i) cell_cnt[i + 1] += cell_cnt[i];
+    for (int i = 0; i < kBinRays; ++i) ray_cnt[i + 1] += ray_cnt[i];
+    if (cell_cnt[kBinCells] > kBinCapD) return 1;
+    if (ray_cnt[kBinRays] > kBinCapR) return 2;
+    std::vector<unsigned short> cell_idx(cell_cnt[kBinCells] + 1), ray_idx(ray_cnt[kBinRays] + 1);
+    std::vector<int> cc(cell_cnt.begin(), cell_cnt.end()), rc(ray_cnt.begin(), ray_cnt.end());
+    for (int f = F - 1; f >= 0; --f) {               // any order inside a bin: min and parity do not depend on it
+        int lo[3], hi[3];
+        tri_cell_range(tri + 9 * f, lo, hi);
+        for (int x = lo[0]; x <= hi[0]; ++x) for (int y = lo[1]; y <= hi[1]; ++y) for (int z = lo[2]; z <= hi[2]; ++z)
+            cell_idx[cc[(x * kBinC + y) * kBinC + z]++] = (unsigned short)f;
+        float a[2], b[2];
+        int rl[2], rh[2];
+        tri_proj_box(tri + 9 * f, a, b);
+        tri_ray_range(a, b, v.s_lo, v.s_scale, rl, rh);
+        for (int x = rl[0]; x <= rh[0]; ++x) for (int y = rl[1]; y <= rh[1]; ++y) ray_idx[rc[x * kBinR + y]++] = (unsigned short)f;
+    }
+    v.tri = tri; v.cell_ptr = cell_cnt.data(); v.cell_idx = cell_idx.data(); v.ray_ptr = ray_cnt.data(); v.ray_idx = ray_idx.data();
+    evals[0] = evals[1] = 0; evals[2] = cell_cnt[kBinCells]; evals[3] = ray_cnt[kBinRays];
+    for (long q = 0; q < n; ++q) {
+        const long id = vox[q];
+        float c[3];
+        voxel_centre((int)(id % G), (int)((id / G) % G), (int)(id / ((long)G * G)), G, c);
+        int ev[2] = {0, 0};
+        out_b[q] = phi_binned(c, v, ev);
+        evals[0] += ev[0]; evals[1] += ev[1];
+        if (out_f) {
+            int hits = 0;
+            float min_d = 1000.f;
+            for (int f = 0; f < F; ++f) {
+                const float* p = tri + 9 * f;
+                const float dd = triangle_distance(c, p, p + 3, p + 6);
+                if (dd < min_d) min_d = dd;
+                if (ray_hits(c, p, p + 3, p + 6)) ++hits;
+            }
+            out_f[q] = (hits % 2 == 0) ? 0.f : min_d;
+        }
+    }
+    return 0;
 }
 }

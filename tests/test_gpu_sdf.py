@@ -113,3 +113,45 @@ def test_dense_regime_closure_matches_oracle(all_faces, grid, B, syn_model, syn_
         assert np.linalg.norm(d[b]) > 0
         cos = -(d[b] * g[b]).sum() / (np.linalg.norm(d[b]) * np.linalg.norm(g[b]))
         assert cos > 1 - 1e-6, (b, cos)
+
+
+@pytest.mark.parametrize("grid", [64, 128])
+def test_accelerated_all_faces_equals_brute_force_bitwise(grid, syn_model, syn_gmm):
+    """sdf_all_faces = 1 evaluates the intended all-faces field over candidate lists (cell grid + projected ray bins,
+    csrc/mvs_sdf_bins.cuh, rebuilt per frame and evaluation by sdf_bins_kernel), sdf_all_faces = 2 over all 13 776 triangles.
+    Same primitives on the same operands: loss and gradient must be IDENTICAL; a short optimiser run stays identical too."""
+    import time
+    cams = S.make_cameras(4)
+    B = 3
+    fr = S.make_frames(syn_model, cams, B, seed=7)
+    w = dict(data_weight=500.0 / 1536, body_pose_weight=57.4, shape_weight=10.0, bending_prior_weight=3.17 * 57.4)
+    X = S.pack_params(fr["init"])
+    res = {}
+    for mode in (1, 2):
+        ctx = make_ctx(syn_model, cams, B, syn_gmm)
+        ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+        ctx.set_exec_mode(3)                                  # closures through the dense-round kernels (sdf_fused)
+        ctx.set_loss(body_prior="gmm", interpenetration=True, coll_loss_weight=0.05, sdf_grid=grid, sdf_all_faces=mode, **w)
+        x = torch.tensor(X, device="cuda")
+        out = ctx.closure(x)                                  # warm-up (allocations)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out = ctx.closure(x)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        xr = x.clone()
+        final, st = ctx.lbfgs_run(xr, ctx.make_lbfgs_config(max_outer=1, max_iter=3))
+        res[mode] = (out["loss"].cpu().numpy(), out["grad"].cpu().numpy(), xr.cpu().numpy(), final.cpu().numpy(), dt)
+        ctx.close()
+    a, b = res[1], res[2]
+    print("all-faces closure of %d frames at G=%d: candidate lists %.1f ms, brute force %.1f ms" % (B, grid, a[4] * 1e3, b[4] * 1e3))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3], equal_nan=True)
+    # the term is active: it changes the loss against the no-SDF closure
+    ctx = make_ctx(syn_model, cams, B, syn_gmm)
+    ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    ctx.set_loss(body_prior="gmm", **w)
+    l0 = ctx.closure(torch.tensor(X, device="cuda"), want_grad=False)["loss"].cpu().numpy()
+    ctx.close()
+    assert (a[0] - l0 > 0).all()
+    assert a[4] < b[4] / 5                                     # and it is what it is for: much faster than the brute force

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_sdf.py tests/test_gpu_sdf_refpin.py -m gpu -q -s > gpurun_out/r2u_tests.log 2>&1; grep -n "^E  \|^FAILED\|passed\|failed\|all-faces closure" gpurun_out/r2u_tests.log | cut -c1-300 | head -40

@@ -420,8 +420,8 @@ def algorithmic_bytes(kernel: str, na: float, V: int, dense: bool) -> float:
     w_bytes = nv * 4 * 8                            # skinning weights (4 (joint, weight) pairs)
     if kernel == "vertex_fwd":
         return q_bytes + w_bytes + na * (218 * 4 + 288 * 4 + 2 * nv * 12)
-    if kernel == "posedirs_gemm_tc":                # posedirs once, pose features in, pose offsets out
-        return 3 * N * 207 * 4 + na * (207 * 4 + 3 * N * 4)
+    if kernel == "posedirs_gemm_tc":                # posedirs (hi + lo parts of the 3xTF32 split) once, pose features (hi + lo) in,
+        return 2 * 3 * N * 207 * 4 + na * (2 * 207 * 4 + 3 * N * 4)     # pose offsets out
     if kernel == "skin":                            # offsets in, template/shapedirs/weights once, v_posed + verts out
         return N * 33 * 4 + N * 32 + na * (3 * N * 4 + 288 * 4 + 40 + 2 * N * 12)
     if kernel == "vertex_bwd":

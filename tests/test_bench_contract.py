@@ -37,5 +37,14 @@ def test_committed_traffic_file_matches_kernel_names():
     from mvsmplfitting_b200 import _lib
     lib = _lib.load()
     names = {lib.mvs_kernel_name(k).decode() for k in range(_lib.NUM_KERNEL_IDS)}
-    tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-    assert set(tr) <= names and all(v["traffic"] > 0 for v in tr.values())
+    for f in ("r01_traffic.json", "r02_traffic.json"):
+        tr = json.load(open(os.path.join(ROOT, "profiles", f)))
+        assert set(tr) <= names and all(v["traffic"] > 0 for v in tr.values())
+
+
+def test_lanes_and_reference_worker_flags_parse():
+    """--inflight (batches in flight) and the hidden --ref-worker mode are part of the command line the driver / the reference arm use"""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True).stdout
+    assert "--inflight" in out and "--impl" in out and "--ref-device" in out and "--ref-worker" not in out

@@ -47,4 +47,4 @@ def test_lanes_and_reference_worker_flags_parse():
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True).stdout
-    assert "--inflight" in out and "--impl" in out and "--ref-device" in out and "--ref-worker" not in out
+    assert "--inflight" in out and "--impl" in out and "--ref-device" in out and "--ref-worker " not in out

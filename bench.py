@@ -134,8 +134,8 @@ def run_ours(args):
                 self.stages = [ctx.make_loss_config(body_prior="l2", use_vposer=2, **{k: v for k, v in st.items() if k != "coll_loss_weight"})
                                for st in stage_table()]
             else:
-                self.stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=bool(args.sdf), sdf_grid=128, **st)
-                               for st in stage_table()]
+                self.stages = [ctx.make_loss_config(body_prior="gmm", interpenetration=bool(args.sdf), sdf_grid=128,
+                                                    sdf_all_faces=args.sdf_all_faces, **st) for st in stage_table()]
             self.opt = ctx.make_lbfgs_config()
             self.X0 = X0 = S.pack_params(fr["init"])
             if args.vposer:      # latent code (zeros = the decoder's mean pose) in the first 32 entries of the pose slot
@@ -337,7 +337,10 @@ def run_ours(args):
             "metric": METRIC, "value": it_all / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(B, V, bool(args.sdf)), parallelism="frames sharded, dp%d, no data-path collective" % world,
+            "config": dict(workload_config(B, V, bool(args.sdf)),
+                           **({"sdf_semantics": "ALL faces (intended field), %s" % ("candidate lists (mvs_sdf_bins.cuh)" if args.sdf_all_faces == 1
+                                                                                  else "brute force")} if args.sdf_all_faces else {}),
+                           parallelism="frames sharded, dp%d, no data-path collective" % world,
                            inflight=n_lanes,
                            pipelining="%d batches of %d frames in flight per GPU: one libmvsmpl context + CUDA stream + host thread "
                                       "each, the K steps are shared out among them; single_batch = the same K steps strictly one "
@@ -635,6 +638,8 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU")
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--sdf", type=int, default=1)
+    ap.add_argument("--sdf-all-faces", type=int, default=0, help="0: the reference call as written (triangle 0; the benchmark), 1: the "
+                    "intended all-faces field over candidate lists (SURVEY N3), 2: the same by brute force")
     ap.add_argument("--inflight", type=int, default=8, help="batches in flight per GPU (contexts + streams + host threads); 1 = serial")
     ap.add_argument("--vposer", type=int, default=0, help="1: fit VPoser's 32-D latent code (decoded on the device), no SDF")
     ap.add_argument("--smooth", type=float, default=0.0, help="cfg5: temporal-smoothness weight (> 0 runs the cfg5 leg on one rank too)")

@@ -276,13 +276,13 @@ int launch_lbfgs_resident(mvs_ctx* ctx, float* params_dev, const void* lbfgs_cfg
                           const void* stage_rng_dev = nullptr);
 // dense regime (SDF term): per round  posedirs_gemm_tc -> skin -> sdf_fused -> frame_step
 bool hybrid_available(const mvs_ctx* ctx);
-int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st, bool allow_tc = true);                                   // mvs_closure.cu
+int launch_vertex_fwd_dense(mvs_ctx* ctx, cudaStream_t st, bool allow_tc = true, bool need_vposed = true);                                   // mvs_closure.cu
 int launch_frame_fwd(mvs_ctx* ctx, const float* x_dev, cudaStream_t st);                      // mvs_closure.cu
 int launch_sdf_fused(mvs_ctx* ctx, cudaStream_t st);   // mvs_sdf.cu
 // mvs_tc.cu: tcgen05 / TMA dense vertex forward
 int tc_upload_model(mvs_ctx* ctx, const float* Qk_host);
 bool tc_available(const mvs_ctx* ctx);
-int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st);
+int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st, bool need_vposed = true);
 int tc_check_error(mvs_ctx* ctx);
 float* tc_poffT(mvs_ctx* ctx);                 // [3N][ldA] pose offsets of the tensor-core contraction (allocated on first use)
 int tc_prepare(mvs_ctx* ctx);                  // tensor maps + pose-offset buffer (idempotent)

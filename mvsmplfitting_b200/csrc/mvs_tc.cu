@@ -306,7 +306,7 @@ const void* tc_maps(mvs_ctx* ctx) {            // [map_a, map_a8, map_b] (CUtens
 }
 int* tc_err_flag(mvs_ctx* ctx) { TcState* T = static_cast<TcState*>(ctx->tc); return T ? T->err : nullptr; }
 
-int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
+int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st, bool need_vposed) {
     TcState* T = static_cast<TcState*>(ctx->tc);
     Workspace& w = ctx->ws;
     const DevModel& m = ctx->m;
@@ -319,7 +319,7 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st) {
                MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_a8, T->map_b, w.ldA,
                                            3 * m.N, (const int*)w.na, ctx->sm_count, ntiles, T->poffT, T->err)));
     const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (nb + 31) / 32;
-    const SkinArgs sa{T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N, w.vposed, w.verts, w.bboxp};
+    const SkinArgs sa{T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N, need_vposed ? w.vposed : nullptr, w.verts, w.bboxp};
     if (nb <= kSkinSmallMax) {                          // straggler tail: lane = vertex, one chunk per CTA
         MVS_LAUNCH(ctx, KID_SKIN, st,
                    MVS_CUDA_OK(ctx, launch_pdl(skin_small_kernel, dim3(nchunks), dim3(kSkinSmallThreads), 0, st, sa, (const int*)w.na)));

@@ -43,7 +43,7 @@ __device__ long long g_tc_clk[32];      // clock64 stamps of CTA (0,0): see scri
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a8,
-                        const __grid_constant__ CUtensorMap map_b, int ldA, int ncols,
+                        const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, int ldA, int ncols,
                         const int* __restrict__ na_ptr, int cta_slots, int ntiles, float* __restrict__ poffT,
                         int* __restrict__ err_flag) {
     pdl_wait();
@@ -51,7 +51,8 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = base;                                        // A hi: 7 x [128 rows][128 B], 1024-aligned, resident
     unsigned char* sR = sA + (size_t)kTcKCh * kTcABytes;             // ring: kTcStages x (A lo chunk 16 KB | B hi chunk 12 KB | B lo chunk 12 KB)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)kTcStages * kTcStageBytes);
+    float* sO = reinterpret_cast<float*>(sR + (size_t)kTcStages * kTcStageBytes);       // epilogue staging tile [32 columns][128 frames]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)kTcStages * kTcStageBytes + kTcEpiBytes);
     uint64_t* a_full = bars;                      // [1]
     uint64_t* b_full = bars + 1;                  // [stages]
     uint64_t* b_empty = b_full + kTcStages;       // [stages]
@@ -167,8 +168,6 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         // ---------------- epilogue: lane = frame row of the M tile; pose offsets go out TRANSPOSED
         //                  poffT[column][slot] so that a warp's 32 frames form one 128-byte store
         const int row = 32 * (warp & 3) + lane;
-        const int slot = m0 + row;
-        const bool live = slot < na;
         int buf = 0; uint32_t tphase[2] = {0, 0};
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             if (!mbar_wait(&t_full[buf], tphase[buf], err_flag)) return;
@@ -184,14 +183,25 @@ posedirs_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&t_empty[buf]);                              // accumulator copied out: the MMA warp may reuse it
             buf ^= 1;
-            if (live) {
-                const int c0 = tile * kTcBN;
+            // The tile leaves through shared memory and the TMA store engine, 32 columns ([column][frame] rows of 512 B) at a
+            // time: the four epilogue warps fill the staging tile (lane = frame: conflict-free), one thread issues the bulk
+            // tensor store, which clips the box at the array bounds (last vertex tile, frame padding).  Rows of slots that are
+            // not active hold whatever the accumulator held: nobody reads them.
+            const int c0 = tile * kTcBN;
 #pragma unroll
-                for (int c = 0; c < kTcBN; ++c)
-                    if (c0 + c < ncols) poffT[(size_t)(c0 + c) * ldA + slot] = __uint_as_float(acc[c]);
+            for (int ch = 0; ch < kTcBN / kTcEpiCols; ++ch) {          // unrolled: acc[] stays in registers
+                if (c0 + ch * kTcEpiCols >= ncols) break;
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < kTcEpiCols; ++c) sO[c * kTcBM + row] = __uint_as_float(acc[ch * kTcEpiCols + c]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (threadIdx.x == 128) tma_store_2d(&map_o, sO, m0, c0 + ch * kTcEpiCols);
             }
             if (threadIdx.x == 128) TC_MARK(9 + 2 * (tile - tile_begin));
         }
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");         // all stores of this CTA have landed
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -215,7 +225,7 @@ skin_small_kernel(SkinArgs ar, const int* __restrict__ na_ptr) {
 
 // ------------------------------------------------------------------------------------------------ host side
 struct TcState {
-    CUtensorMap map_a, map_a8, map_b;
+    CUtensorMap map_a, map_a8, map_b, map_o;
     float* Qtc = nullptr;       // [2][3N][224] posedirs rows split into TF32 hi | lo parts (columns >= 207 zero)
     float* poffT = nullptr;     // [3N][ldA] pose offsets, frame fastest (output of the tensor-core contraction)
     int* err = nullptr;
@@ -249,6 +259,23 @@ static int encode_map(mvs_ctx* ctx, CUtensorMap* map, const float* ptr, uint64_t
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(ctx, MVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MVS_OK;
+}
+
+// output of the contraction: poffT [ncols][ldA] fp32, frame fastest; box = 128 frames x kTcEpiCols columns, no swizzle
+static int encode_out_map(mvs_ctx* ctx, CUtensorMap* map, float* ptr, uint64_t ldA, uint64_t ncols) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+        return set_error(ctx, MVS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    auto fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    cuuint64_t dims[2] = {(cuuint64_t)ldA, (cuuint64_t)ncols};
+    cuuint64_t strides[1] = {(cuuint64_t)ldA * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBM, (cuuint32_t)kTcEpiCols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ctx, MVS_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
     return MVS_OK;
 }
 
@@ -286,6 +313,7 @@ int tc_prepare(mvs_ctx* ctx) {
         if ((rc = encode_map(ctx, &T->map_a8, w.PhiTc, (uint64_t)2 * w.ldA, 8))) return rc;
         if ((rc = encode_map(ctx, &T->map_b, T->Qtc, (uint64_t)2 * 3 * m.N, kTcBN))) return rc;
         if ((rc = dev_alloc(ctx, &T->poffT, (size_t)3 * m.N * w.ldA))) return rc;
+        if ((rc = encode_out_map(ctx, &T->map_o, T->poffT, (uint64_t)w.ldA, (uint64_t)3 * m.N))) return rc;
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(posedirs_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         MVS_CUDA_OK(ctx, cudaFuncSetAttribute(skin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinSmem));
         T->ready = true;
@@ -316,7 +344,7 @@ int launch_vertex_fwd_tc(mvs_ctx* ctx, cudaStream_t st, bool need_vposed) {
     const int mtiles = (nb + kTcBM - 1) / kTcBM;
     dim3 grid(std::min(ctx->sm_count, ntiles), mtiles);          // surplus CTAs exit: the kernel splits the tiles from *na
     MVS_LAUNCH(ctx, KID_VERTEX_FWD_TC, st,
-               MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_a8, T->map_b, w.ldA,
+               MVS_CUDA_OK(ctx, launch_pdl(posedirs_gemm_tc_kernel, grid, dim3(kTcThreads), kTcSmem, st, T->map_a, T->map_a8, T->map_b, T->map_o, w.ldA,
                                            3 * m.N, (const int*)w.na, ctx->sm_count, ntiles, T->poffT, T->err)));
     const int nchunks = (m.N + kSkinV - 1) / kSkinV, fgroups = (nb + 31) / 32;
     const SkinArgs sa{T->poffT, m.ST, w.Phi, w.At, w.ldA, m.ell_j, m.ell_w, m.KW, m.N, need_vposed ? w.vposed : nullptr, w.verts, w.bboxp};

@@ -139,4 +139,65 @@ MVS_HD float phi_binned(const float* c, const SdfBinsView& v, int* evals) {
     return min_d;
 }
 
+#if defined(__CUDACC__)
+// The same evaluation by a whole warp for ONE voxel centre (all 32 lanes pass the same c): the lanes share out the candidates of
+// every list, the parity is a sum and the distance a minimum over the lanes -- both exact, so the result is phi_binned's bit for bit.
+__device__ __noinline__ float phi_binned_warp(const float* c, const SdfBinsView* vp) {
+    const SdfBinsView& v = *vp;
+    const int lane = threadIdx.x & 31;
+    float s[2];
+    sdf_project(c, s);
+    const float sf0 = (s[0] - v.s_lo[0]) * v.s_scale[0], sf1 = (s[1] - v.s_lo[1]) * v.s_scale[1];
+    if (!(sf0 >= 0.f && sf0 < (float)kBinR && sf1 >= 0.f && sf1 < (float)kBinR)) return 0.f;
+    const int rb = (int)floorf(sf0) * kBinR + (int)floorf(sf1);
+    int hits = 0;
+    for (int e = v.ray_ptr[rb] + lane; e < v.ray_ptr[rb + 1]; e += 32) {
+        const float* p = v.tri + 9 * (int)v.ray_idx[e];
+        if (ray_hits(c, p, p + 3, p + 6)) ++hits;
+    }
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if (hits % 2 == 0) return 0.f;
+    int cc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) cc[a] = bin_clamp((c[a] + 1.f) * (0.5f * kBinC), kBinC);
+    const float h = 2.f / (float)kBinC;
+    float min_d = 1000.f;
+    for (int r = 1; r <= kBinC; ++r) {
+        const int x0 = cc[0] - r < 0 ? 0 : cc[0] - r, x1 = cc[0] + r > kBinC - 1 ? kBinC - 1 : cc[0] + r;
+        const int y0 = cc[1] - r < 0 ? 0 : cc[1] - r, y1 = cc[1] + r > kBinC - 1 ? kBinC - 1 : cc[1] + r;
+        const int z0 = cc[2] - r < 0 ? 0 : cc[2] - r, z1 = cc[2] + r > kBinC - 1 ? kBinC - 1 : cc[2] + r;
+        for (int x = x0; x <= x1; ++x)
+            for (int y = y0; y <= y1; ++y) {
+                // the cells of one (x, y) column are consecutive in memory: their lists form ONE contiguous range
+                int za = z0, zb = z1;
+                if (r > 1) {
+                    const int dx = x > cc[0] ? x - cc[0] : cc[0] - x, dy = y > cc[1] ? y - cc[1] : cc[1] - y;
+                    if ((dx > dy ? dx : dy) < r) {          // inner column: only its two end cells belong to the shell
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int z = pass ? cc[2] + r : cc[2] - r;
+                            if (z < 0 || z > kBinC - 1) continue;
+                            const int cell = (x * kBinC + y) * kBinC + z;
+                            for (int e = v.cell_ptr[cell] + lane; e < v.cell_ptr[cell + 1]; e += 32) {
+                                const float* p = v.tri + 9 * (int)v.cell_idx[e];
+                                const float dd = triangle_distance(c, p, p + 3, p + 6);
+                                if (dd < min_d) min_d = dd;
+                            }
+                        }
+                        continue;
+                    }
+                }
+                const int base = (x * kBinC + y) * kBinC;
+                for (int e = v.cell_ptr[base + za] + lane; e < v.cell_ptr[base + zb + 1]; e += 32) {
+                    const float* p = v.tri + 9 * (int)v.cell_idx[e];
+                    const float dd = triangle_distance(c, p, p + 3, p + 6);
+                    if (dd < min_d) min_d = dd;
+                }
+            }
+        min_d = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(min_d)));      // distances are >= 0: same order as uint
+        if (min_d < (float)r * h * (1.f - 1e-4f)) break;
+    }
+    return min_d;
+}
+#endif
+
 }  // namespace mvs

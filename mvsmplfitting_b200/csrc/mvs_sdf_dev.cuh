@@ -260,6 +260,52 @@ __device__ __forceinline__ void sdf_fused_body(SdfFusedSmem& sm, const SdfFusedA
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float gcv[3] = {0.f, 0.f, 0.f};
         const bool skip = __shfl_sync(0xffffffffu, (int)my_skip, pass) != 0;
+        // all faces over candidate lists: the warp evaluates its 32 vertices' voxels ONE AT A TIME, the lanes sharing out the
+        // candidates (phi_binned_warp); every lane then goes on with its own eight values exactly as in the other modes
+        float pc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool have_pc = false;
+        if constexpr (kAll) {
+            if (bvp != nullptr) {
+                const bool act = n < N && !skip;
+                int j0[3] = {0, 0, 0};
+                float ccx[2] = {0.f, 0.f}, ccy[2] = {0.f, 0.f}, ccz[2] = {0.f, 0.f};
+                if (act) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float lc = ((vme[c] + tr[c]) - fb.centre[c]) / fb.scale;
+                        j0[c] = (int)floorf(((lc + 1.f) * G - 1.f) / 2.f);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const int ii = min(max(j0[0] + o, 0), G - 1), jj = min(max(j0[1] + o, 0), G - 1), kk = min(max(j0[2] + o, 0), G - 1);
+                        if (tab) { ccx[o] = ctab[ii]; ccy[o] = ctab[jj]; ccz[o] = ctab[kk]; }
+                        else { float c3[3]; voxel_centre(ii, jj, kk, G, c3); ccx[o] = c3[0]; ccy[o] = c3[1]; ccz[o] = c3[2]; }
+                    }
+                }
+                const unsigned actm = __ballot_sync(0xffffffffu, act);
+                for (int src = 0; src < 32; ++src) {
+                    if (!((actm >> src) & 1u)) continue;
+                    const int b0 = __shfl_sync(0xffffffffu, j0[0], src), b1 = __shfl_sync(0xffffffffu, j0[1], src),
+                              b2 = __shfl_sync(0xffffffffu, j0[2], src);
+                    float bx[2], by[2], bz[2];
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        bx[o] = __shfl_sync(0xffffffffu, ccx[o], src); by[o] = __shfl_sync(0xffffffffu, ccy[o], src);
+                        bz[o] = __shfl_sync(0xffffffffu, ccz[o], src);
+                    }
+#pragma unroll
+                    for (int corner = 0; corner < 8; ++corner) {
+                        const int ox = corner & 1, oy = (corner >> 1) & 1, oz = corner >> 2;
+                        const int ii = b0 + ox, jj = b1 + oy, kk = b2 + oz;
+                        if (ii < 0 || ii >= G || jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+                        const float cc[3] = {bx[ox], by[oy], bz[oz]};
+                        const float p = phi_binned_warp(cc, bvp);
+                        if (lane == src) pc[corner] = p;
+                    }
+                }
+                have_pc = true;
+            }
+        }
         if (n < N && !skip) {
             float loc[3], w1[3];
             int i0[3];
@@ -342,7 +388,7 @@ __device__ __forceinline__ void sdf_fused_body(SdfFusedSmem& sm, const SdfFusedA
                         if ((pd > pm && sp < -pm) || (pd < -pm && sp > pm)) continue;      // corner side of the triangle plane
                     }
                     const float cc[3] = {cx[ox], cy[oy], cz[oz]};
-                    const float p = voxel_phi_at<kAll>(cc, num_faces, faces, vf, tr, fb, tri, bvp);
+                    const float p = (kAll && have_pc) ? pc[corner] : voxel_phi_at<kAll>(cc, num_faces, faces, vf, tr, fb, tri, bvp);
                     if (p == 0.f) continue;
                     const float wx = ox ? w1[0] : 1.f - w1[0], wy = oy ? w1[1] : 1.f - w1[1], wz = oz ? w1[2] : 1.f - w1[2];
                     val += p * wx * wy * wz;

@@ -226,7 +226,7 @@ static __device__ void vposer_decode(const ResidentSmem& S, const ResidentModel&
     __syncthreads();
     {
         float a0 = m.vp_b2[t], a1 = m.vp_b2[t + kResThreads];
-#pragma unroll 8
+#pragma unroll 32
         for (int i = 0; i < kVpH; ++i) {
             const float hi = W.h1[i];
             a0 = fmaf(__ldg(m.vp_w2t + (size_t)i * kVpH + t), hi, a0);
@@ -237,7 +237,7 @@ static __device__ void vposer_decode(const ResidentSmem& S, const ResidentModel&
     __syncthreads();
     if (t < kVpO) {
         float a = m.vp_b3[t];
-#pragma unroll 8
+#pragma unroll 32
         for (int i = 0; i < kVpH; ++i) a = fmaf(__ldg(m.vp_w3t + (size_t)i * kVpO + t), W.h2[i], a);
         W.o6[t] = a;
     }
@@ -264,7 +264,7 @@ static __device__ void vposer_decode_bwd(const ResidentModel& m, VposerSmem& W) 
     __syncthreads();
     {   // d h2 = lrelu'(h2) .* (W3^T d o6)
         float a0 = 0.f, a1 = 0.f;
-#pragma unroll 6
+#pragma unroll 23
         for (int o = 0; o < kVpO; ++o) {
             const float d = W.red[o];
             a0 = fmaf(__ldg(m.vp_w3 + (size_t)o * kVpH + t), d, a0);
@@ -276,7 +276,7 @@ static __device__ void vposer_decode_bwd(const ResidentModel& m, VposerSmem& W) 
     __syncthreads();
     {   // d h1 = lrelu'(h1) .* (W2^T d h2)   (result overwrites h2, no longer needed)
         float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
+#pragma unroll 32
         for (int o = 0; o < kVpH; ++o) {
             const float d = W.dh[o];
             a0 = fmaf(__ldg(m.vp_w2 + (size_t)o * kVpH + t), d, a0);

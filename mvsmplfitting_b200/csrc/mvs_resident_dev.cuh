@@ -559,12 +559,19 @@ static __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m,
         if (t < kFeatPad) {
             float a = 0.f;
             int col = 0;
-            for (; col + 12 <= ncol_all; col += 12) {          // 12 independent L2 loads in flight per thread
-                float qv[12];
+            for (; col + 32 <= ncol_all; col += 32) {          // 32 independent L2 loads in flight per thread: the phase is as long
+                float qv[32];                                  // as its round trips to L2 (258 rows: 8 instead of 21)
 #pragma unroll
-                for (int u = 0; u < 12; ++u) qv[u] = __ldg(m.Qk + (size_t)S.rowbase[col + u] * kFeatPad + t);
+                for (int u = 0; u < 32; ++u) qv[u] = __ldg(m.Qk + (size_t)S.rowbase[col + u] * kFeatPad + t);
 #pragma unroll
-                for (int u = 0; u < 12; ++u) a = fmaf(S.dvp[col + u], qv[u], a);
+                for (int u = 0; u < 32; ++u) a = fmaf(S.dvp[col + u], qv[u], a);
+            }
+            for (; col + 8 <= ncol_all; col += 8) {
+                float qv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) qv[u] = __ldg(m.Qk + (size_t)S.rowbase[col + u] * kFeatPad + t);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a = fmaf(S.dvp[col + u], qv[u], a);
             }
             for (; col < ncol_all; ++col) a = fmaf(S.dvp[col], __ldg(m.Qk + (size_t)S.rowbase[col] * kFeatPad + t), a);
             if (din.part) {
@@ -627,8 +634,8 @@ static __device__ void resident_closure(ResidentSmem& S, const ResidentModel& m,
             const float* P = m.gmm_prec + (size_t)mm * 69 * 69 + i;
             const float* df = &S.gm_diff[mm * 69];
             float y = 0.f;
-#pragma unroll 23
-            for (int j = 0; j < 69; ++j) y = fmaf(__ldg(P + j * 69), df[j], y);       // 23 independent loads in flight
+#pragma unroll
+            for (int j = 0; j < 69; ++j) y = fmaf(__ldg(P + j * 69), df[j], y);       // all 69 loads of the row in flight
             S.gm_y[e] = y;
         }
     }

@@ -147,3 +147,23 @@ def test_fit_seq_warm_frames_skip_two_stages(sdf_from, syn_model, syn_gmm):
     assert st_seq["frame_iterations"] < st_cold["frame_iterations"] and st_seq["frames_nan"] == 0
     x_none, f_none, _ = run(lambda c: _stages(c, sdf_from), np.zeros(B, bool))
     assert np.array_equal(x_none, x_cold) and np.array_equal(f_none, f_cold)
+
+
+def test_fit_seq_guards(syn_model, syn_gmm):
+    """warm frames skip two stages, so a two-stage schedule leaves them nothing (the reference would return an undefined loss);
+    the batched reference chain (exec mode 1) has no per-frame stage table"""
+    from mvsmplfitting_b200._lib import MvsError
+    cams = S.make_cameras(4)
+    B = 2
+    fr = S.make_frames(syn_model, cams, B, seed=3)
+    ctx = _ctx(syn_model, cams, syn_gmm, B)
+    ctx.set_keypoints(fr["gt_uv"], fr["conf"], fr["joint_weights"])
+    x = torch.tensor(S.pack_params(fr["init"]), device="cuda")
+    with pytest.raises(MvsError):
+        ctx.fit(x, _stages(ctx)[:2], ctx.make_lbfgs_config(max_outer=1), warm=[True, False])
+    ctx.set_exec_mode(1)
+    with pytest.raises(MvsError):
+        ctx.fit(x, _stages(ctx), ctx.make_lbfgs_config(max_outer=1), warm=[True, False])
+    final, st = ctx.fit(x, _stages(ctx), ctx.make_lbfgs_config(max_outer=1), warm=[False, False])      # no warm frame: plain mvs_fit
+    assert st["frames_nan"] == 0 and torch.isfinite(final).all()
+    ctx.close()

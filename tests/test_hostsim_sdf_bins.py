@@ -70,3 +70,18 @@ def test_brute_force_of_the_shared_primitives_is_the_reference_restatement(syn_m
     if ref is None:
         pytest.skip("oracle has no per-voxel entry point")
     assert np.abs(np.asarray(ref, np.float32) - pf).max() < 1e-6 and ((np.asarray(ref) > 0) == (pf > 0)).all()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_binned_phi_far_voxels_and_odd_grids(seed, syn_model):
+    """voxels anywhere in the grid (deep inside the body the ring search has to go past the first ring; outside the projected mesh the
+    parity test exits early) and grid sizes that are not powers of two"""
+    G = [20, 50, 97, 128][seed - 11]
+    tri = _mesh(syn_model, seed)
+    rng = np.random.RandomState(seed)
+    vox = np.unique(rng.randint(0, G ** 3, 2500))
+    pb, pf, ev = HS.sdf_bins(tri, G, vox)
+    assert np.array_equal(pb, pf)
+    assert (pf > 0).sum() >= 3                      # some of the random voxels are inside the body
+    if G >= 50:
+        assert pf.max() > 2.0 / 32 * 1.01           # ... at least one of them farther from the surface than one cell: rings > 1 were searched
